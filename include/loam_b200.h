@@ -1,0 +1,179 @@
+/* loam_b200.h -- C ABI of libloam_b200.so: the B200 (sm_100a) implementation of LOAM's per-sweep registration hot
+ * path behind the reference's Basic* classes (laboshinl/loam_velodyne).
+ *
+ * Plain pointers and sizes only.  Every entry point returns 0 on success or a negative loam_b200_status; nothing
+ * throws across this boundary.  A context owns one device, one stream and all device memory; it is not thread-safe
+ * (the reference classes are used from one thread each, e.g. LaserOdometry.cpp:254-270) but several contexts may
+ * coexist.  Unless stated otherwise host buffers are only read/written during the call (the call synchronises its
+ * stream before returning), so callers may reuse them immediately.
+ *
+ * Points are packed float[4] = (x, y, z, intensity); indices are int32 (nanoflann_pcl.h:102).
+ * "Too few points / too few correspondences" are results, not errors: they are reported through counts so the
+ * caller can mirror the reference's `continue`s (BasicLaserOdometry.cpp:484-488, BasicLaserMapping.cpp:826-828).
+ */
+#ifndef LOAM_B200_H
+#define LOAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct loam_b200_ctx loam_b200_ctx;
+
+typedef enum {
+  LOAM_B200_OK = 0,
+  LOAM_B200_ERR_ARG = -1,      /* null pointer / negative size / inconsistent ranges */
+  LOAM_B200_ERR_CUDA = -2,     /* a CUDA runtime call failed; loam_b200_last_error() has the text */
+  LOAM_B200_ERR_NO_DEVICE = -3,/* no CUDA device / device is not sm_100 */
+  LOAM_B200_ERR_STATE = -4,    /* call sequence violated (e.g. iterate before set) */
+  LOAM_B200_ERR_CAPACITY = -5, /* caller-provided output capacity too small */
+  LOAM_B200_ERR_COMM = -6      /* NCCL failure */
+} loam_b200_status;
+
+const char* loam_b200_strerror(int status);
+/* text of the last CUDA/NCCL failure seen by this context (empty string if none) */
+const char* loam_b200_last_error(const loam_b200_ctx* ctx);
+/* library version: major*10000 + minor*100 + patch */
+int loam_b200_version(void);
+
+/* Create a context on CUDA device `device` (>= 0).  Fails with LOAM_B200_ERR_NO_DEVICE when there is no usable GPU:
+ * there is deliberately no CPU fallback. */
+int loam_b200_create(loam_b200_ctx** out, int device);
+int loam_b200_destroy(loam_b200_ctx* ctx);
+int loam_b200_sync(loam_b200_ctx* ctx);
+/* cudaStream_t of the context (as void*) so callers can order their own work / time with events */
+void* loam_b200_stream(loam_b200_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scan registration: replaces BasicScanRegistration::extractFeatures with setScanBuffersFor / setRegionBuffersFor /
+ * markAsPicked (BasicScanRegistration.cpp:155-254, 284-386) including the per-ring VoxelGrid of the less-flat points
+ * (:246-252).  Parameter names follow RegistrationParams (BasicScanRegistration.h:37-71).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int nFeatureRegions;              /* 6  */
+  int curvatureRegion;              /* 5  */
+  int maxCornerSharp;               /* 2  */
+  int maxCornerLessSharp;           /* 20 */
+  int maxSurfaceFlat;               /* 4  */
+  float lessFlatFilterSize;         /* 0.2 */
+  float surfaceCurvatureThreshold;  /* 0.1 */
+} loam_b200_reg_params;
+
+typedef struct {
+  /* picks in the reference's output order (ring-major, region-major, pick order), as indices into the input cloud */
+  int32_t* sharp_idx;       int sharp_cap;       int n_sharp;
+  int32_t* less_sharp_idx;  int less_sharp_cap;  int n_less_sharp;
+  int32_t* flat_idx;        int flat_cap;        int n_flat;
+  /* per-point label, n entries: 2 sharp, 1 less sharp, 0 less flat, -1 flat (PointLabel, BasicScanRegistration.h:24-30),
+   * 127 = not inside any feature region.  May be NULL. */
+  int8_t* label;
+  /* voxel-filtered less-flat cloud (ring-major; within a ring ascending voxel index, like pcl::VoxelGrid) */
+  float* less_flat_ds;      int less_flat_cap;   int n_less_flat;
+} loam_b200_features;
+
+/* pts: n packed points, ring-ordered; ring_start/ring_end: the inclusive IndexRange of each ring exactly as
+ * processScanlines builds _scanIndices (BasicScanRegistration.cpp:38-41), so empty rings are (c, c-1) or (0, 0). */
+int loam_b200_extract_features(loam_b200_ctx* ctx, const float* pts, int n, const int32_t* ring_start,
+                               const int32_t* ring_end, int n_rings, const loam_b200_reg_params* params,
+                               loam_b200_features* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * k-NN search structure: replaces nanoflann::KdTreeFLANN<PointXYZI>::setInputCloud / nearestKSearch
+ * (nanoflann_pcl.h:131-152; nanoflann.hpp:1217-1262, 1354-1412) with a Morton-sorted linear BVH held in HBM.
+ * Slots: the reference keeps four trees alive (last corner / last surface in odometry, corner / surface map in
+ * mapping, BasicLaserOdometry.h:83-84, BasicLaserMapping.cpp:623-624).
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum { LOAM_B200_TREE_ODOM_CORNER = 0, LOAM_B200_TREE_ODOM_SURF = 1, LOAM_B200_TREE_MAP_CORNER = 2,
+       LOAM_B200_TREE_MAP_SURF = 3, LOAM_B200_NUM_TREES = 4 };
+
+/* upload m points and (re)build the tree of `slot`; m may be 0 */
+int loam_b200_tree_build(loam_b200_ctx* ctx, int slot, const float* pts, int m);
+int loam_b200_tree_size(loam_b200_ctx* ctx, int slot);
+/* exact k nearest neighbours (k <= 8) of nq queries (packed float[4], intensity ignored), ascending squared distance,
+ * float L2 accumulated x->y->z like nanoflann's L2_Simple_Adaptor (nanoflann.hpp:372-379).  Only points with
+ * d2 < max_d2 are reported (pass INFINITY for the plain search); missing neighbours have idx -1 and d2 = FLT_MAX. */
+int loam_b200_tree_knn(loam_b200_ctx* ctx, int slot, const float* queries, int nq, int k, float max_d2,
+                       int32_t* idx_out, float* d2_out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scan-to-map Gauss-Newton iteration: replaces the body of the iteration loop of
+ * BasicLaserMapping::optimizeTransformTobeMapped up to and including AtA / AtB
+ * (BasicLaserMapping.cpp:665-866: pointAssociateToMap, 5-NN, line / plane fit, residual weight, Jacobian rows,
+ * normal equations).  The 6x6 solve and pose update stay with the caller (:867-922).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* DS corner / surface stacks of this sweep (BasicLaserMapping.cpp:519-527), sensor frame */
+int loam_b200_map_set_queries(loam_b200_ctx* ctx, const float* corner, int n_corner, const float* surf, int n_surf);
+
+typedef struct {
+  float rot[3];   /* rot_x, rot_y, rot_z of _transformTobeMapped */
+  float sin_[3];  /* Angle::sin() of the three, as cached by the host (Angle.h:23-26) */
+  float cos_[3];
+  float pos[3];
+} loam_b200_pose;
+
+typedef struct {
+  float AtA[36];      /* row-major 6x6, columns (rot_x, rot_y, rot_z, x, y, z) */
+  float AtB[6];
+  int n_selected;     /* laserCloudSelNum (BasicLaserMapping.cpp:826) */
+  int n_corner_selected;
+} loam_b200_normal_eq;
+
+int loam_b200_map_iterate(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b200_normal_eq* out);
+/* debug / parity variant: additionally returns per query (corner queries first, then surface) the coefficient
+ * (s*n, s*d) of _coeffSel and a selected flag; coeff: (n_corner+n_surf) x 4 floats, selected: (n_corner+n_surf) */
+int loam_b200_map_iterate_debug(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b200_normal_eq* out,
+                                float* coeff, int8_t* selected);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scan-to-scan Gauss-Newton iteration: replaces the body of the iteration loop of BasicLaserOdometry::process up to
+ * AtA / AtB (BasicLaserOdometry.cpp:246-557: transformToStart, 1-NN + adjacent-ring search every 5th iteration,
+ * point-to-line / point-to-plane residuals, Jacobian rows, normal equations).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* last less-sharp / less-flat clouds (already transformed to the sweep end, integer-ring intensities) */
+int loam_b200_odom_set_last(loam_b200_ctx* ctx, const float* corner, int n_corner, const float* surf, int n_surf);
+/* current sharp / flat feature clouds (intensity = ring + relTime) */
+int loam_b200_odom_set_current(loam_b200_ctx* ctx, const float* sharp, int n_sharp, const float* flat, int n_flat);
+
+typedef struct {
+  float rot[3];
+  float sin_[3];
+  float cos_[3];
+  float pos[3];
+  float inv_scan_period; /* 1.f / _scanPeriod (BasicLaserOdometry.cpp:42) */
+  int iter;              /* iterCount: search on iter % 5 == 0, weights on iter >= 5 */
+} loam_b200_odom_pose;
+
+int loam_b200_odom_iterate(loam_b200_ctx* ctx, const loam_b200_odom_pose* pose, loam_b200_normal_eq* out);
+/* debug: coefficient + selected flag per query (sharp first, then flat) and the correspondence indices
+ * (ind: (n_sharp+n_flat) x 3 ints: closest, second, third (-1 when absent)) */
+int loam_b200_odom_iterate_debug(loam_b200_ctx* ctx, const loam_b200_odom_pose* pose, loam_b200_normal_eq* out,
+                                 float* coeff, int8_t* selected, int32_t* ind);
+
+/* BasicLaserOdometry::transformToEnd (BasicLaserOdometry.cpp:57-87) without IMU terms, in place on n host points */
+int loam_b200_transform_to_end(loam_b200_ctx* ctx, float* pts, int n, const loam_b200_odom_pose* pose);
+/* pointAssociateToMap over n host points in place (BasicLaserMapping.cpp:207-219, 235-240) */
+int loam_b200_transform_to_map(loam_b200_ctx* ctx, float* pts, int n, const loam_b200_pose* pose);
+
+/* pcl::VoxelGrid<PointXYZI> centroid filter (call sites BasicLaserMapping.cpp:519-527,580-588): writes at most
+ * cap points, ascending voxel index; *n_out receives the count. */
+int loam_b200_voxel_grid(loam_b200_ctx* ctx, const float* pts, int n, float leaf, float* out, int cap, int* n_out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Kernel timing (CUDA events on the context's stream) for bench.py's roofline: accumulated GPU milliseconds and
+ * launch counts per kernel family since the last reset.
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum { LOAM_B200_K_FEATURES = 0, LOAM_B200_K_TREE_BUILD = 1, LOAM_B200_K_KNN = 2, LOAM_B200_K_MAP_ITER = 3,
+       LOAM_B200_K_ODOM_ITER = 4, LOAM_B200_K_TRANSFORM = 5, LOAM_B200_K_VOXEL = 6, LOAM_B200_NUM_KERNEL_FAMILIES = 7 };
+int loam_b200_profile_enable(loam_b200_ctx* ctx, int on);
+int loam_b200_profile_reset(loam_b200_ctx* ctx);
+int loam_b200_profile_get(loam_b200_ctx* ctx, int family, double* gpu_ms, long long* launches);
+/* total kernel launches issued by this context since creation */
+long long loam_b200_launch_count(loam_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOAM_B200_H */

@@ -1,0 +1,81 @@
+/* loam_b200_host.h -- C handles over the C++ drop-in classes loam::BasicScanRegistration / BasicLaserOdometry /
+ * BasicLaserMapping (loam_velodyne_b200/csrc/host/loam_velodyne/*.h), for callers that cannot include C++ headers
+ * (the Python package, bench.py, ctypes tests).  C++ callers -- including the reference's ROS adapters, which derive
+ * from the Basic* classes (ScanRegistration.h:55, LaserOdometry.h:56, LaserMapping.h:54 upstream) -- use the classes
+ * directly.
+ *
+ * Points are packed float[4] = (x, y, z, intensity); twists are float[6] = (rot_x, rot_y, rot_z, pos.x, pos.y, pos.z).
+ * Functions returning int give 0 on success and a negative value on failure; loam_b200_host_last_error() has the text
+ * (per thread).  A failure here is always loud: there is no CPU fallback behind these handles.
+ */
+#ifndef LOAM_B200_HOST_H
+#define LOAM_B200_HOST_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* loam_b200_host_last_error(void);
+/* CUDA device used by objects created afterwards (default: $LOAM_B200_DEVICE, else $LOCAL_RANK, else 0) */
+void loam_b200_host_set_device(int device);
+
+/* ---- loam::BasicScanRegistration ---- */
+void* loam_b200_scanreg_create(void);
+void loam_b200_scanreg_destroy(void* h);
+int loam_b200_scanreg_configure(void* h, float scanPeriod, int nFeatureRegions, int curvatureRegion, int maxCornerSharp,
+                                int maxSurfaceFlat, float lessFlatFilterSize, float surfaceCurvatureThreshold);
+/* processScanlines: ring r = ring_sizes[r] consecutive points */
+int loam_b200_scanreg_process(void* h, const float* pts, const int* ring_sizes, int n_rings);
+/* which: 0 laserCloud, 1 cornerPointsSharp, 2 cornerPointsLessSharp, 3 surfacePointsFlat, 4 surfacePointsLessFlat */
+int loam_b200_scanreg_cloud_size(void* h, int which);
+int loam_b200_scanreg_cloud_copy(void* h, int which, float* out);
+/* which: 1 sharp, 2 less sharp, 3 flat -> indices into laserCloud */
+int loam_b200_scanreg_index_size(void* h, int which);
+int loam_b200_scanreg_index_copy(void* h, int which, int* out);
+
+/* ---- loam::BasicLaserOdometry ---- */
+void* loam_b200_odom_create(float scanPeriod, int maxIterations);
+void loam_b200_odom_destroy(void* h);
+int loam_b200_odom_set_inputs(void* h, const float* sharp, int n_sharp, const float* less_sharp, int n_less_sharp,
+                              const float* flat, int n_flat, const float* less_flat, int n_less_flat,
+                              const float* full, int n_full);
+int loam_b200_odom_process(void* h);
+int loam_b200_odom_full_to_end(void* h); /* transformToEnd(laserCloud()), as LaserOdometry::publishResult does */
+/* which: 0 transform, 1 transformSum */
+int loam_b200_odom_get_twist(void* h, int which, float* out6);
+/* which: 0 lastCornerCloud, 1 lastSurfaceCloud, 2 laserCloud */
+int loam_b200_odom_cloud_size(void* h, int which);
+int loam_b200_odom_cloud_copy(void* h, int which, float* out);
+int loam_b200_odom_last_iterations(void* h);
+
+/* ---- loam::BasicLaserMapping ---- */
+void* loam_b200_map_create(float scanPeriod, int maxIterations);
+void loam_b200_map_destroy(void* h);
+int loam_b200_map_seed(void* h, const float* corner, int n_corner, const float* surf, int n_surf);
+int loam_b200_map_set_inputs(void* h, const float* corner_last, int n_corner, const float* surf_last, int n_surf,
+                             const float* full, int n_full);
+int loam_b200_map_update_odometry(void* h, const float* sum6);
+int loam_b200_map_process(void* h); /* 1 processed, 0 frame skipped, <0 error */
+/* which: 0 transformAftMapped, 1 transformBefMapped, 2 transformTobeMapped */
+int loam_b200_map_get_twist(void* h, int which, float* out6);
+/* which: 0 laserCloud (registered), 1 laserCloudSurroundDS, 2 cornerFromMap, 3 surfFromMap, 4 cornerStackDS,
+ *        5 surfStackDS, 6 all corner cubes, 7 all surf cubes */
+int loam_b200_map_cloud_size(void* h, int which);
+int loam_b200_map_cloud_copy(void* h, int which, float* out);
+int loam_b200_map_last_iterations(void* h);
+
+/* ---- the three chained in-process: registration -> odometry -> mapping on one sweep ---- */
+void* loam_b200_pipeline_create(float scanPeriod, int odomMaxIter, int mapMaxIter);
+void loam_b200_pipeline_destroy(void* h);
+int loam_b200_pipeline_seed_map(void* h, const float* corner, int n_corner, const float* surf, int n_surf);
+/* stage_seconds[5]: registration, odometry, full->end, mapping, total (steady_clock, host wall time) */
+int loam_b200_pipeline_sweep(void* h, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
+                             float* map_aft6, double* stage_seconds);
+void* loam_b200_pipeline_scanreg(void* h);
+void* loam_b200_pipeline_odom(void* h);
+void* loam_b200_pipeline_map(void* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

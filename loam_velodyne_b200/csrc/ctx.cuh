@@ -1,0 +1,193 @@
+// Context, device-buffer management and launch bookkeeping for libloam_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/loam_b200.h"
+
+namespace loamb {
+
+// growable device allocation (never shrinks; geometric growth so steady-state sweeps allocate nothing)
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = cap ? cap : 256;
+    while (want < n) want = want + want / 2 + 256;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// pinned host staging buffer
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = cap ? cap : 256;
+    while (want < n) want = want + want / 2 + 256;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// 64-byte BVH node: both child boxes + child links, one 64 B aligned read per visit.
+// child < 0  ->  leaf, leaf id = ~child
+struct __align__(16) BvhNode {
+  float4 lo0;  // child0 min xyz, w = bit pattern of child0 link
+  float4 hi0;  // child0 max xyz, w = bit pattern of child1 link
+  float4 lo1;  // child1 min xyz
+  float4 hi1;  // child1 max xyz
+};
+
+struct Tree {
+  int m = 0;        // points
+  int n_leaf = 0;   // leaves (LEAF_SIZE consecutive Morton-sorted points each)
+  int root = 0;     // root link (>= 0 internal node, < 0 leaf)
+  DevBuf<float4> pts;      // original order (xyz, intensity)
+  DevBuf<float4> sorted;   // Morton order (xyz, original index as int bits)
+  DevBuf<BvhNode> nodes;   // n_leaf - 1 internal nodes
+  DevBuf<uint32_t> leaf_key;
+  DevBuf<int> parent;      // parent of internal node i / of leaf (stored at n_leaf-1+leaf)
+  DevBuf<int> flags;
+  DevBuf<float4> box_lo, box_hi;  // per-node total boxes during refit (internal then leaves)
+};
+
+struct SortScratch {
+  DevBuf<uint32_t> keys_a, keys_b;
+  DevBuf<int> vals_a, vals_b;
+  DevBuf<uint32_t> hist;
+};
+
+}  // namespace loamb
+
+struct loam_b200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  long long launches = 0;
+
+  // profiling
+  bool prof_on = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double prof_ms[LOAM_B200_NUM_KERNEL_FAMILIES] = {0};
+  long long prof_launches[LOAM_B200_NUM_KERNEL_FAMILIES] = {0};
+  int prof_family = -1;
+  long long prof_launches_at_begin = 0;
+
+  // scan registration
+  loamb::DevBuf<float4> reg_pts;
+  loamb::DevBuf<int> reg_ring_start, reg_ring_end;
+  loamb::DevBuf<int> reg_picks;        // per ring: sharp | less sharp | flat slots
+  loamb::DevBuf<int> reg_counts;       // per ring: n_sharp, n_less_sharp, n_flat, n_less_flat_ds
+  loamb::DevBuf<int8_t> reg_label;
+  loamb::DevBuf<float4> reg_lessflat;  // per ring slots of voxel-filtered less-flat points
+  loamb::PinBuf<unsigned char> stage;  // generic pinned staging
+  loamb::PinBuf<unsigned char> stage2;
+
+  // trees
+  loamb::Tree tree[LOAM_B200_NUM_TREES];
+  loamb::SortScratch sort;
+  loamb::DevBuf<float> bbox;  // 6 floats (encoded) for the tree build
+  loamb::DevBuf<float4> knn_q;
+  loamb::DevBuf<int> knn_idx;
+  loamb::DevBuf<float> knn_d2;
+
+  // mapping
+  loamb::DevBuf<float4> map_q;  // corner queries then surf queries
+  int map_nc = 0, map_ns = 0;
+  loamb::DevBuf<float> partials;   // per-block partial normal equations
+  loamb::DevBuf<float> result;     // 36 floats
+  loamb::DevBuf<unsigned int> ticket;
+  loamb::DevBuf<float4> dbg_coeff;
+  loamb::DevBuf<int8_t> dbg_sel;
+  loamb::PinBuf<float> result_host;
+
+  // odometry
+  loamb::DevBuf<float4> od_q;  // sharp then flat
+  int od_nsharp = 0, od_nflat = 0;
+  loamb::DevBuf<int> od_ind;   // (n_sharp + n_flat) x 3 persisted correspondence indices
+  bool od_last_set = false;
+
+  // generic scratch
+  loamb::DevBuf<float4> tmp_pts;
+  loamb::DevBuf<float4> tmp_pts2;
+  loamb::DevBuf<uint32_t> vox_key;
+  loamb::DevBuf<int> vox_val;
+  loamb::DevBuf<int> vox_scalars;
+};
+
+namespace loamb {
+
+inline int fail_cuda(loam_b200_ctx* c, cudaError_t e, const char* what, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s failed at line %d: %s", what, line, cudaGetErrorString(e));
+  if (c) c->last_error = buf;
+  cudaGetLastError();  // clear sticky-less error state
+  return LOAM_B200_ERR_CUDA;
+}
+
+#define LB_CUDA(ctx, expr)                                                   \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, #expr, __LINE__); \
+  } while (0)
+
+#define LB_LAUNCH_CHECK(ctx)                                                            \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, "kernel launch", __LINE__); \
+  } while (0)
+
+// RAII-less profiling bracket: begin/end around a family's kernels on the ctx stream
+inline void prof_begin(loam_b200_ctx* c, int family) {
+  if (!c->prof_on) return;
+  c->prof_family = family;
+  c->prof_launches_at_begin = c->launches;
+  cudaEventRecord(c->ev0, c->stream);
+}
+inline void prof_end(loam_b200_ctx* c) {
+  if (!c->prof_on || c->prof_family < 0) return;
+  cudaEventRecord(c->ev1, c->stream);
+  cudaEventSynchronize(c->ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->prof_ms[c->prof_family] += ms;
+  c->prof_launches[c->prof_family] += c->launches - c->prof_launches_at_begin;
+  c->prof_family = -1;
+}
+
+}  // namespace loamb

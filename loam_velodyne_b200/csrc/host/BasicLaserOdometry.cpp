@@ -1,0 +1,244 @@
+// Host side of the laser-odometry drop-in.  Control flow mirrors upstream BasicLaserOdometry::process
+// (src/lib/BasicLaserOdometry.cpp:196-666); per-point work happens in loam_b200_odom_iterate.
+#include "loam_velodyne/BasicLaserOdometry.h"
+
+#include <cassert>
+#include <cmath>
+
+#include "b200_runtime.h"
+#include "host_math.h"
+
+namespace loam {
+
+using hostmath::rad2deg;
+
+BasicLaserOdometry::BasicLaserOdometry(float scanPeriod, size_t maxIterations)
+    : _scanPeriod(scanPeriod), _frameCount(0), _maxIterations(maxIterations), _systemInited(false), _deltaTAbort(0.1),
+      _deltaRAbort(0.1), _lastCornerCloud(new b200::Cloud()), _lastSurfaceCloud(new b200::Cloud()),
+      _cornerPointsSharp(new b200::Cloud()), _cornerPointsLessSharp(new b200::Cloud()),
+      _surfPointsFlat(new b200::Cloud()), _surfPointsLessFlat(new b200::Cloud()), _laserCloud(new b200::Cloud()),
+      _gpu(new b200::Context()), _solver(new b200::GaussNewtonSolver()) {}
+
+BasicLaserOdometry::~BasicLaserOdometry() {
+  delete _solver;
+  delete _gpu;
+}
+
+bool BasicLaserOdometry::hasIMU() const {
+  return _imuRollStart.rad() != 0.f || _imuPitchStart.rad() != 0.f || _imuYawStart.rad() != 0.f ||
+         _imuRollEnd.rad() != 0.f || _imuPitchEnd.rad() != 0.f || _imuYawEnd.rad() != 0.f ||
+         _imuShiftFromStart.x() != 0.f || _imuShiftFromStart.y() != 0.f || _imuShiftFromStart.z() != 0.f;
+}
+
+void BasicLaserOdometry::updateIMU(pcl::PointCloud<pcl::PointXYZ> const& imuTrans) {
+  assert(4 == imuTrans.size());
+  _imuPitchStart = imuTrans.points[0].x;
+  _imuYawStart = imuTrans.points[0].y;
+  _imuRollStart = imuTrans.points[0].z;
+  _imuPitchEnd = imuTrans.points[1].x;
+  _imuYawEnd = imuTrans.points[1].y;
+  _imuRollEnd = imuTrans.points[1].z;
+  _imuShiftFromStart = imuTrans.points[2];
+  _imuVeloFromStart = imuTrans.points[3];
+}
+
+static void fillOdomPose(const Twist& t, float scanPeriod, int iter, loam_b200_odom_pose& p) {
+  p.rot[0] = t.rot_x.rad(); p.rot[1] = t.rot_y.rad(); p.rot[2] = t.rot_z.rad();
+  // upstream re-evaluates std::sin/std::cos of the float angle per Jacobian row (:504-509): same values as the
+  // Angle caches
+  p.sin_[0] = t.rot_x.sin(); p.sin_[1] = t.rot_y.sin(); p.sin_[2] = t.rot_z.sin();
+  p.cos_[0] = t.rot_x.cos(); p.cos_[1] = t.rot_y.cos(); p.cos_[2] = t.rot_z.cos();
+  p.pos[0] = t.pos.x(); p.pos[1] = t.pos.y(); p.pos[2] = t.pos.z();
+  p.inv_scan_period = 1.f / scanPeriod;
+  p.iter = iter;
+}
+
+size_t BasicLaserOdometry::transformToEnd(pcl::PointCloud<pcl::PointXYZI>::Ptr& cloud) {
+  const size_t n = cloud->points.size();
+  if (n == 0) return 0;
+  b200::pack(*cloud, _bufA);
+  loam_b200_odom_pose p;
+  fillOdomPose(_transform, _scanPeriod, 0, p);
+  _gpu->check(loam_b200_transform_to_end(_gpu->get(), _bufA.data(), (int)n, &p), "loam_b200_transform_to_end");
+  b200::unpack(_bufA.data(), n, *cloud);
+  if (hasIMU()) {
+    // IMU terms of upstream :78-83 (identity when no IMU): undo the plain "+ pos", redo with the shift, then rotate
+    for (auto& pt : cloud->points) {
+      pt.x += -_imuShiftFromStart.x();
+      pt.y += -_imuShiftFromStart.y();
+      pt.z += -_imuShiftFromStart.z();
+      hostmath::rotateZXY(pt, _imuRollStart, _imuPitchStart, _imuYawStart);
+      hostmath::rotateYXZ(pt, -_imuYawEnd, -_imuPitchEnd, -_imuRollEnd);
+    }
+  }
+  return n;
+}
+
+void BasicLaserOdometry::uploadLast() {
+  b200::pack(*_lastCornerCloud, _bufA);
+  b200::pack(*_lastSurfaceCloud, _bufB);
+  _gpu->check(loam_b200_odom_set_last(_gpu->get(), _bufA.data(), (int)_lastCornerCloud->size(), _bufB.data(),
+                                      (int)_lastSurfaceCloud->size()),
+              "loam_b200_odom_set_last");
+}
+
+void BasicLaserOdometry::process() {
+  if (!_systemInited) {
+    _cornerPointsLessSharp.swap(_lastCornerCloud);
+    _surfPointsLessFlat.swap(_lastSurfaceCloud);
+    uploadLast();
+    _transformSum.rot_x += _imuPitchStart;
+    _transformSum.rot_z += _imuRollStart;
+    _systemInited = true;
+    return;
+  }
+
+  _frameCount++;
+  _transform.pos -= _imuVeloFromStart * _scanPeriod;
+  _lastIterations = 0;
+
+  size_t lastCornerCloudSize = _lastCornerCloud->points.size();
+  size_t lastSurfaceCloudSize = _lastSurfaceCloud->points.size();
+
+  if (lastCornerCloudSize > 10 && lastSurfaceCloudSize > 100) {
+    // non-finite feature points would be dropped here upstream (removeNaNFromPointCloud, :230); inputs are dense
+    b200::pack(*_cornerPointsSharp, _bufA);
+    b200::pack(*_surfPointsFlat, _bufB);
+    _gpu->check(loam_b200_odom_set_current(_gpu->get(), _bufA.data(), (int)_cornerPointsSharp->size(), _bufB.data(),
+                                           (int)_surfPointsFlat->size()),
+                "loam_b200_odom_set_current");
+
+    for (size_t iterCount = 0; iterCount < _maxIterations; iterCount++) {
+      _lastIterations = iterCount + 1;
+      loam_b200_odom_pose pose;
+      fillOdomPose(_transform, _scanPeriod, (int)iterCount, pose);
+      loam_b200_normal_eq ne;
+      _gpu->check(loam_b200_odom_iterate(_gpu->get(), &pose, &ne), "loam_b200_odom_iterate");
+      if (ne.n_selected < 10) continue;
+
+      float x[6];
+      _solver->solve(ne, iterCount == 0, 10.f, x);
+
+      _transform.rot_x = _transform.rot_x.rad() + x[0];
+      _transform.rot_y = _transform.rot_y.rad() + x[1];
+      _transform.rot_z = _transform.rot_z.rad() + x[2];
+      _transform.pos.x() += x[3];
+      _transform.pos.y() += x[4];
+      _transform.pos.z() += x[5];
+
+      if (!std::isfinite(_transform.rot_x.rad())) _transform.rot_x = Angle();
+      if (!std::isfinite(_transform.rot_y.rad())) _transform.rot_y = Angle();
+      if (!std::isfinite(_transform.rot_z.rad())) _transform.rot_z = Angle();
+      if (!std::isfinite(_transform.pos.x())) _transform.pos.x() = 0.0;
+      if (!std::isfinite(_transform.pos.y())) _transform.pos.y() = 0.0;
+      if (!std::isfinite(_transform.pos.z())) _transform.pos.z() = 0.0;
+
+      const float deltaR = std::sqrt(std::pow(rad2deg(x[0]), 2) + std::pow(rad2deg(x[1]), 2) + std::pow(rad2deg(x[2]), 2));
+      const float deltaT = std::sqrt(std::pow(x[3] * 100, 2) + std::pow(x[4] * 100, 2) + std::pow(x[5] * 100, 2));
+      if (deltaR < _deltaRAbort && deltaT < _deltaTAbort) break;
+    }
+  }
+
+  Angle rx, ry, rz;
+  accumulateRotation(_transformSum.rot_x, _transformSum.rot_y, _transformSum.rot_z, -_transform.rot_x,
+                     -_transform.rot_y.rad() * 1.05, -_transform.rot_z, rx, ry, rz);
+
+  Vector3 v(_transform.pos.x() - _imuShiftFromStart.x(), _transform.pos.y() - _imuShiftFromStart.y(),
+            _transform.pos.z() * 1.05 - _imuShiftFromStart.z());
+  hostmath::rotateZXY(v, rz, rx, ry);
+  Vector3 trans = _transformSum.pos - v;
+
+  pluginIMURotation(rx, ry, rz, _imuPitchStart, _imuYawStart, _imuRollStart, _imuPitchEnd, _imuYawEnd, _imuRollEnd, rx,
+                    ry, rz);
+
+  _transformSum.rot_x = rx;
+  _transformSum.rot_y = ry;
+  _transformSum.rot_z = rz;
+  _transformSum.pos = trans;
+
+  transformToEnd(_cornerPointsLessSharp);
+  transformToEnd(_surfPointsLessFlat);
+
+  _cornerPointsLessSharp.swap(_lastCornerCloud);
+  _surfPointsLessFlat.swap(_lastSurfaceCloud);
+
+  lastCornerCloudSize = _lastCornerCloud->points.size();
+  lastSurfaceCloudSize = _lastSurfaceCloud->points.size();
+  if (lastCornerCloudSize > 10 && lastSurfaceCloudSize > 100) uploadLast();
+}
+
+// Euler-angle composition helpers: closed-form products of ZXY rotations, as published with LOAM
+// (upstream BasicLaserOdometry.cpp:91-179).
+void BasicLaserOdometry::pluginIMURotation(const Angle& bcx, const Angle& bcy, const Angle& bcz, const Angle& blx,
+                                           const Angle& bly, const Angle& blz, const Angle& alx, const Angle& aly,
+                                           const Angle& alz, Angle& acx, Angle& acy, Angle& acz) {
+  const float sbcx = bcx.sin(), cbcx = bcx.cos(), sbcy = bcy.sin(), cbcy = bcy.cos(), sbcz = bcz.sin(), cbcz = bcz.cos();
+  const float sblx = blx.sin(), cblx = blx.cos(), sbly = bly.sin(), cbly = bly.cos(), sblz = blz.sin(), cblz = blz.cos();
+  const float salx = alx.sin(), calx = alx.cos(), saly = aly.sin(), caly = aly.cos(), salz = alz.sin(), calz = alz.cos();
+
+  const float srx = -sbcx * (salx * sblx + calx * caly * cblx * cbly + calx * cblx * saly * sbly) -
+                    cbcx * cbcz * (calx * saly * (cbly * sblz - cblz * sblx * sbly) -
+                                   calx * caly * (sbly * sblz + cbly * cblz * sblx) + cblx * cblz * salx) -
+                    cbcx * sbcz * (calx * caly * (cblz * sbly - cbly * sblx * sblz) -
+                                   calx * saly * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sblz);
+  acx = -std::asin(srx);
+
+  const float srycrx = (cbcy * sbcz - cbcz * sbcx * sbcy) * (calx * saly * (cbly * sblz - cblz * sblx * sbly) -
+                                                             calx * caly * (sbly * sblz + cbly * cblz * sblx) +
+                                                             cblx * cblz * salx) -
+                       (cbcy * cbcz + sbcx * sbcy * sbcz) * (calx * caly * (cblz * sbly - cbly * sblx * sblz) -
+                                                             calx * saly * (cbly * cblz + sblx * sbly * sblz) +
+                                                             cblx * salx * sblz) +
+                       cbcx * sbcy * (salx * sblx + calx * caly * cblx * cbly + calx * cblx * saly * sbly);
+  const float crycrx = (cbcz * sbcy - cbcy * sbcx * sbcz) * (calx * caly * (cblz * sbly - cbly * sblx * sblz) -
+                                                             calx * saly * (cbly * cblz + sblx * sbly * sblz) +
+                                                             cblx * salx * sblz) -
+                       (sbcy * sbcz + cbcy * cbcz * sbcx) * (calx * saly * (cbly * sblz - cblz * sblx * sbly) -
+                                                             calx * caly * (sbly * sblz + cbly * cblz * sblx) +
+                                                             cblx * cblz * salx) +
+                       cbcx * cbcy * (salx * sblx + calx * caly * cblx * cbly + calx * cblx * saly * sbly);
+  acy = std::atan2(srycrx / acx.cos(), crycrx / acx.cos());
+
+  const float srzcrx = sbcx * (cblx * cbly * (calz * saly - caly * salx * salz) -
+                               cblx * sbly * (caly * calz + salx * saly * salz) + calx * salz * sblx) -
+                       cbcx * cbcz * ((caly * calz + salx * saly * salz) * (cbly * sblz - cblz * sblx * sbly) +
+                                      (calz * saly - caly * salx * salz) * (sbly * sblz + cbly * cblz * sblx) -
+                                      calx * cblx * cblz * salz) +
+                       cbcx * sbcz * ((caly * calz + salx * saly * salz) * (cbly * cblz + sblx * sbly * sblz) +
+                                      (calz * saly - caly * salx * salz) * (cblz * sbly - cbly * sblx * sblz) +
+                                      calx * cblx * salz * sblz);
+  const float crzcrx = sbcx * (cblx * sbly * (caly * salz - calz * salx * saly) -
+                               cblx * cbly * (saly * salz + caly * calz * salx) + calx * calz * sblx) +
+                       cbcx * cbcz * ((saly * salz + caly * calz * salx) * (sbly * sblz + cbly * cblz * sblx) +
+                                      (caly * salz - calz * salx * saly) * (cbly * sblz - cblz * sblx * sbly) +
+                                      calx * calz * cblx * cblz) -
+                       cbcx * sbcz * ((saly * salz + caly * calz * salx) * (cblz * sbly - cbly * sblx * sblz) +
+                                      (caly * salz - calz * salx * saly) * (cbly * cblz + sblx * sbly * sblz) -
+                                      calx * calz * cblx * sblz);
+  acz = std::atan2(srzcrx / acx.cos(), crzcrx / acx.cos());
+}
+
+void BasicLaserOdometry::accumulateRotation(Angle cx, Angle cy, Angle cz, Angle lx, Angle ly, Angle lz, Angle& ox,
+                                            Angle& oy, Angle& oz) {
+  const float srx = lx.cos() * cx.cos() * ly.sin() * cz.sin() - cx.cos() * cz.cos() * lx.sin() -
+                    lx.cos() * ly.cos() * cx.sin();
+  ox = -std::asin(srx);
+
+  const float srycrx = lx.sin() * (cy.cos() * cz.sin() - cz.cos() * cx.sin() * cy.sin()) +
+                       lx.cos() * ly.sin() * (cy.cos() * cz.cos() + cx.sin() * cy.sin() * cz.sin()) +
+                       lx.cos() * ly.cos() * cx.cos() * cy.sin();
+  const float crycrx = lx.cos() * ly.cos() * cx.cos() * cy.cos() -
+                       lx.cos() * ly.sin() * (cz.cos() * cy.sin() - cy.cos() * cx.sin() * cz.sin()) -
+                       lx.sin() * (cy.sin() * cz.sin() + cy.cos() * cz.cos() * cx.sin());
+  oy = std::atan2(srycrx / ox.cos(), crycrx / ox.cos());
+
+  const float srzcrx = cx.sin() * (lz.cos() * ly.sin() - ly.cos() * lx.sin() * lz.sin()) +
+                       cx.cos() * cz.sin() * (ly.cos() * lz.cos() + lx.sin() * ly.sin() * lz.sin()) +
+                       lx.cos() * cx.cos() * cz.cos() * lz.sin();
+  const float crzcrx = lx.cos() * lz.cos() * cx.cos() * cz.cos() -
+                       cx.cos() * cz.sin() * (ly.cos() * lz.sin() - lz.cos() * lx.sin() * ly.sin()) -
+                       cx.sin() * (ly.sin() * lz.sin() + ly.cos() * lz.cos() * lx.sin());
+  oz = std::atan2(srzcrx / ox.cos(), crzcrx / ox.cos());
+}
+
+}  // namespace loam

@@ -1,0 +1,92 @@
+// Glue between the pcl::PointCloud-based Basic* classes and the C ABI (include/loam_b200.h).
+// Nothing here computes on the CPU: a missing GPU / failed call surfaces as std::runtime_error from process*().
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <pcl/point_cloud.h>
+#include <pcl/filters/voxel_grid.h>
+
+#include "loam_b200.h"
+#include "loam_velodyne/Angle.h"
+#include "loam_velodyne/Twist.h"
+
+namespace loam {
+namespace b200 {
+
+// device selected for contexts created by the Basic* classes (default: $LOAM_B200_DEVICE, else $LOCAL_RANK, else 0)
+int defaultDevice();
+void setDefaultDevice(int device);
+
+class Context {
+ public:
+  Context() : ctx_(nullptr) {}
+  ~Context() { if (ctx_) loam_b200_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  loam_b200_ctx* get();  // created on first use; throws when no GPU is usable
+  void check(int status, const char* what);
+
+ private:
+  loam_b200_ctx* ctx_;
+};
+
+typedef pcl::PointCloud<pcl::PointXYZI> Cloud;
+
+// pcl::PointXYZI (32 B) <-> packed float4 (16 B)
+inline void pack(const Cloud& c, std::vector<float>& out) {
+  out.resize(c.points.size() * 4);
+  for (std::size_t i = 0; i < c.points.size(); i++) {
+    out[4 * i + 0] = c.points[i].x;
+    out[4 * i + 1] = c.points[i].y;
+    out[4 * i + 2] = c.points[i].z;
+    out[4 * i + 3] = c.points[i].intensity;
+  }
+}
+inline void unpack(const float* p, std::size_t n, Cloud& c) {
+  c.points.resize(n);
+  for (std::size_t i = 0; i < n; i++) {
+    c.points[i].x = p[4 * i + 0];
+    c.points[i].y = p[4 * i + 1];
+    c.points[i].z = p[4 * i + 2];
+    c.points[i].intensity = p[4 * i + 3];
+  }
+  c.width = static_cast<std::uint32_t>(n);
+  c.height = 1;
+  c.is_dense = true;
+}
+
+inline float leafOf(const pcl::VoxelGrid<pcl::PointXYZI>& f) {
+#ifdef LOAM_B200_COMPAT_PCL
+  return f.leafX();
+#else
+  return f.getLeafSize()[0];
+#endif
+}
+
+inline void fillPose(const Twist& t, loam_b200_pose& p) {
+  p.rot[0] = t.rot_x.rad(); p.rot[1] = t.rot_y.rad(); p.rot[2] = t.rot_z.rad();
+  p.sin_[0] = t.rot_x.sin(); p.sin_[1] = t.rot_y.sin(); p.sin_[2] = t.rot_z.sin();
+  p.cos_[0] = t.rot_x.cos(); p.cos_[1] = t.rot_y.cos(); p.cos_[2] = t.rot_z.cos();
+  p.pos[0] = t.pos.x(); p.pos[1] = t.pos.y(); p.pos[2] = t.pos.z();
+}
+
+// Solve + degeneracy handling shared by odometry and mapping (BasicLaserOdometry.cpp:559-597,
+// BasicLaserMapping.cpp:867-905): x = colPivHouseholderQr(AtA).solve(AtB); on the first iteration the eigenvalues of
+// AtA below `eigenThreshold` (ascending, stop at the first that is not) zero ROWS of the eigenvector matrix copy and
+// P = V^-1 * V2; degenerate -> x = P x.
+struct GaussNewtonSolver {
+  bool isDegenerate = false;
+  float P[36];  // row-major
+  void solve(const loam_b200_normal_eq& ne, bool firstIteration, float eigenThreshold, float x[6]);
+};
+
+// host-side pcl::VoxelGrid replacement: one GPU call
+void voxelFilter(Context& ctx, const Cloud& in, float leaf, Cloud& out, std::vector<float>& scratchIn,
+                 std::vector<float>& scratchOut);
+
+}  // namespace b200
+}  // namespace loam

@@ -1,0 +1,247 @@
+// C handles over the C++ drop-in classes (include/loam_b200_host.h).
+#include "loam_b200_host.h"
+
+#include <chrono>
+#include <cstring>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "b200_runtime.h"
+#include "loam_velodyne/BasicLaserMapping.h"
+#include "loam_velodyne/BasicLaserOdometry.h"
+#include "loam_velodyne/BasicScanRegistration.h"
+
+namespace {
+
+typedef pcl::PointCloud<pcl::PointXYZI> Cloud;
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return -1;
+  }
+}
+
+void fill(Cloud& c, const float* p, int n) {
+  loam::b200::unpack(p, (size_t)(n > 0 ? n : 0), c);
+}
+void dump(const Cloud& c, float* out) {
+  for (size_t i = 0; i < c.points.size(); i++) {
+    out[4 * i + 0] = c.points[i].x;
+    out[4 * i + 1] = c.points[i].y;
+    out[4 * i + 2] = c.points[i].z;
+    out[4 * i + 3] = c.points[i].intensity;
+  }
+}
+void twist6(const loam::Twist& t, float* o) {
+  o[0] = t.rot_x.rad(); o[1] = t.rot_y.rad(); o[2] = t.rot_z.rad();
+  o[3] = t.pos.x(); o[4] = t.pos.y(); o[5] = t.pos.z();
+}
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct RegH {
+  loam::BasicScanRegistration r;
+  std::vector<Cloud> rings;
+  const Cloud& cloud(int which) {
+    switch (which) {
+      case 0: return r.laserCloud();
+      case 1: return r.cornerPointsSharp();
+      case 2: return r.cornerPointsLessSharp();
+      case 3: return r.surfacePointsFlat();
+      default: return r.surfacePointsLessFlat();
+    }
+  }
+  const std::vector<int>& index(int which) {
+    return which == 1 ? r.sharpIndices() : which == 2 ? r.lessSharpIndices() : r.flatIndices();
+  }
+  void process(const float* pts, const int* ring_sizes, int n_rings) {
+    rings.resize(n_rings);
+    int off = 0;
+    for (int i = 0; i < n_rings; i++) {
+      fill(rings[i], pts + 4 * (size_t)off, ring_sizes[i]);
+      off += ring_sizes[i];
+    }
+    r.processScanlines(loam::Time(), rings);
+  }
+};
+struct OdomH {
+  loam::BasicLaserOdometry o;
+  OdomH(float sp, int it) : o(sp, it) {}
+  const Cloud& cloud(int which) {
+    return which == 0 ? *o.lastCornerCloud() : which == 1 ? *o.lastSurfaceCloud() : *o.laserCloud();
+  }
+};
+struct MapH {
+  loam::BasicLaserMapping m;
+  Cloud scratchA, scratchB;
+  MapH(float sp, int it) : m(sp, it) {}
+  const Cloud& cloud(int which) {
+    switch (which) {
+      case 0: return m.laserCloud();
+      case 1: return m.laserCloudSurroundDS();
+      case 2: return m.cornerFromMap();
+      case 3: return m.surfFromMap();
+      case 4: return m.cornerStackDS();
+      case 5: return m.surfStackDS();
+      case 6: m.collectMap(scratchA, scratchB); return scratchA;
+      default: m.collectMap(scratchA, scratchB); return scratchB;
+    }
+  }
+};
+struct PipeH {
+  RegH reg;
+  OdomH odom;
+  MapH map;
+  PipeH(float sp, int oi, int mi) : odom(sp, oi), map(sp, mi) {}
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* loam_b200_host_last_error(void) { return g_err.c_str(); }
+void loam_b200_host_set_device(int device) { loam::b200::setDefaultDevice(device); }
+
+void* loam_b200_scanreg_create(void) { return new RegH(); }
+void loam_b200_scanreg_destroy(void* h) { delete (RegH*)h; }
+int loam_b200_scanreg_configure(void* h, float scanPeriod, int nFeatureRegions, int curvatureRegion, int maxCornerSharp,
+                                int maxSurfaceFlat, float lessFlatFilterSize, float surfaceCurvatureThreshold) {
+  return guarded([&] {
+    loam::RegistrationParams p(scanPeriod, 200, nFeatureRegions, curvatureRegion, maxCornerSharp, maxSurfaceFlat,
+                               lessFlatFilterSize, surfaceCurvatureThreshold);
+    return ((RegH*)h)->r.configure(p) ? 0 : -1;
+  });
+}
+int loam_b200_scanreg_process(void* h, const float* pts, const int* ring_sizes, int n_rings) {
+  return guarded([&] { ((RegH*)h)->process(pts, ring_sizes, n_rings); return 0; });
+}
+int loam_b200_scanreg_cloud_size(void* h, int which) { return (int)((RegH*)h)->cloud(which).size(); }
+int loam_b200_scanreg_cloud_copy(void* h, int which, float* out) { dump(((RegH*)h)->cloud(which), out); return 0; }
+int loam_b200_scanreg_index_size(void* h, int which) { return (int)((RegH*)h)->index(which).size(); }
+int loam_b200_scanreg_index_copy(void* h, int which, int* out) {
+  const auto& v = ((RegH*)h)->index(which);
+  if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(int));
+  return 0;
+}
+
+void* loam_b200_odom_create(float scanPeriod, int maxIterations) { return new OdomH(scanPeriod, maxIterations); }
+void loam_b200_odom_destroy(void* h) { delete (OdomH*)h; }
+int loam_b200_odom_set_inputs(void* h, const float* sharp, int n_sharp, const float* less_sharp, int n_less_sharp,
+                              const float* flat, int n_flat, const float* less_flat, int n_less_flat,
+                              const float* full, int n_full) {
+  return guarded([&] {
+    auto& o = ((OdomH*)h)->o;
+    fill(*o.cornerPointsSharp(), sharp, n_sharp);
+    fill(*o.cornerPointsLessSharp(), less_sharp, n_less_sharp);
+    fill(*o.surfPointsFlat(), flat, n_flat);
+    fill(*o.surfPointsLessFlat(), less_flat, n_less_flat);
+    fill(*o.laserCloud(), full, n_full);
+    return 0;
+  });
+}
+int loam_b200_odom_process(void* h) { return guarded([&] { ((OdomH*)h)->o.process(); return 0; }); }
+int loam_b200_odom_full_to_end(void* h) {
+  return guarded([&] { auto& o = ((OdomH*)h)->o; o.transformToEnd(o.laserCloud()); return 0; });
+}
+int loam_b200_odom_get_twist(void* h, int which, float* out6) {
+  auto& o = ((OdomH*)h)->o;
+  twist6(which == 0 ? o.transform() : o.transformSum(), out6);
+  return 0;
+}
+int loam_b200_odom_cloud_size(void* h, int which) { return (int)((OdomH*)h)->cloud(which).size(); }
+int loam_b200_odom_cloud_copy(void* h, int which, float* out) { dump(((OdomH*)h)->cloud(which), out); return 0; }
+int loam_b200_odom_last_iterations(void* h) { return (int)((OdomH*)h)->o.lastIterationCount(); }
+
+void* loam_b200_map_create(float scanPeriod, int maxIterations) { return new MapH(scanPeriod, maxIterations); }
+void loam_b200_map_destroy(void* h) { delete (MapH*)h; }
+int loam_b200_map_seed(void* h, const float* corner, int n_corner, const float* surf, int n_surf) {
+  return guarded([&] {
+    Cloud c, s;
+    fill(c, corner, n_corner);
+    fill(s, surf, n_surf);
+    ((MapH*)h)->m.seedMap(c, s);
+    return 0;
+  });
+}
+int loam_b200_map_set_inputs(void* h, const float* corner_last, int n_corner, const float* surf_last, int n_surf,
+                             const float* full, int n_full) {
+  return guarded([&] {
+    auto& m = ((MapH*)h)->m;
+    fill(m.laserCloudCornerLast(), corner_last, n_corner);
+    fill(m.laserCloudSurfLast(), surf_last, n_surf);
+    fill(m.laserCloud(), full, n_full);
+    return 0;
+  });
+}
+int loam_b200_map_update_odometry(void* h, const float* s) {
+  loam::Twist t;
+  t.rot_x = s[0]; t.rot_y = s[1]; t.rot_z = s[2];
+  t.pos = loam::Vector3(s[3], s[4], s[5]);
+  ((MapH*)h)->m.updateOdometry(t);
+  return 0;
+}
+int loam_b200_map_process(void* h) {
+  return guarded([&] { return ((MapH*)h)->m.process(loam::Time()) ? 1 : 0; });
+}
+int loam_b200_map_get_twist(void* h, int which, float* out6) {
+  auto& m = ((MapH*)h)->m;
+  twist6(which == 0 ? m.transformAftMapped() : which == 1 ? m.transformBefMapped() : m.transformTobeMapped(), out6);
+  return 0;
+}
+int loam_b200_map_cloud_size(void* h, int which) { return (int)((MapH*)h)->cloud(which).size(); }
+int loam_b200_map_cloud_copy(void* h, int which, float* out) { dump(((MapH*)h)->cloud(which), out); return 0; }
+int loam_b200_map_last_iterations(void* h) { return (int)((MapH*)h)->m.lastIterationCount(); }
+
+void* loam_b200_pipeline_create(float scanPeriod, int odomMaxIter, int mapMaxIter) {
+  return new PipeH(scanPeriod, odomMaxIter, mapMaxIter);
+}
+void loam_b200_pipeline_destroy(void* h) { delete (PipeH*)h; }
+int loam_b200_pipeline_seed_map(void* h, const float* corner, int n_corner, const float* surf, int n_surf) {
+  return loam_b200_map_seed(&((PipeH*)h)->map, corner, n_corner, surf, n_surf);
+}
+void* loam_b200_pipeline_scanreg(void* h) { return &((PipeH*)h)->reg; }
+void* loam_b200_pipeline_odom(void* h) { return &((PipeH*)h)->odom; }
+void* loam_b200_pipeline_map(void* h) { return &((PipeH*)h)->map; }
+
+int loam_b200_pipeline_sweep(void* hh, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
+                             float* map_aft6, double* st) {
+  return guarded([&] {
+    PipeH* h = (PipeH*)hh;
+    const double t0 = now();
+    h->reg.process(pts, ring_sizes, n_rings);
+    const double t1 = now();
+    // the hop ScanRegistration::publishResult -> LaserOdometry::*Handler (plain cloud copies upstream)
+    auto& o = h->odom.o;
+    *o.cornerPointsSharp() = h->reg.r.cornerPointsSharp();
+    *o.cornerPointsLessSharp() = h->reg.r.cornerPointsLessSharp();
+    *o.surfPointsFlat() = h->reg.r.surfacePointsFlat();
+    *o.surfPointsLessFlat() = h->reg.r.surfacePointsLessFlat();
+    *o.laserCloud() = h->reg.r.laserCloud();
+    o.updateIMU(h->reg.r.imuTransform());
+    o.process();
+    const double t2 = now();
+    o.transformToEnd(o.laserCloud());
+    const double t3 = now();
+    auto& m = h->map.m;
+    m.laserCloudCornerLast() = *o.lastCornerCloud();
+    m.laserCloudSurfLast() = *o.lastSurfaceCloud();
+    m.laserCloud() = *o.laserCloud();
+    m.updateOdometry(o.transformSum());
+    const int ok = m.process(loam::Time()) ? 1 : 0;
+    const double t4 = now();
+    twist6(o.transformSum(), odom_sum6);
+    twist6(m.transformAftMapped(), map_aft6);
+    if (st) { st[0] = t1 - t0; st[1] = t2 - t1; st[2] = t3 - t2; st[3] = t4 - t3; st[4] = t4 - t0; }
+    return ok;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// loam::BasicScanRegistration -- drop-in for upstream include/loam_velodyne/BasicScanRegistration.h:135-164.
+// Same public surface (processScanlines, configure, updateIMUData, projectPointToStartOfSweep and the const-ref
+// accessors) so `class ScanRegistration : protected BasicScanRegistration` (upstream ScanRegistration.h:55) keeps
+// compiling; the feature extraction itself (extractFeatures / setScanBuffersFor / setRegionBuffersFor /
+// markAsPicked, BasicScanRegistration.cpp:155-254,284-386) runs on the GPU through loam_b200_extract_features.
+#pragma once
+
+#include <utility>
+#include <vector>
+
+#include <pcl/point_cloud.h>
+
+#include "Angle.h"
+#include "Vector3.h"
+#include "time_utils.h"
+
+namespace loam {
+
+namespace b200 { class Context; }
+
+typedef std::pair<size_t, size_t> IndexRange;
+
+enum PointLabel {
+  CORNER_SHARP = 2,
+  CORNER_LESS_SHARP = 1,
+  SURFACE_LESS_FLAT = 0,
+  SURFACE_FLAT = -1
+};
+
+class RegistrationParams {
+ public:
+  RegistrationParams(const float& scanPeriod_ = 0.1, const int& imuHistorySize_ = 200, const int& nFeatureRegions_ = 6,
+                     const int& curvatureRegion_ = 5, const int& maxCornerSharp_ = 2, const int& maxSurfaceFlat_ = 4,
+                     const float& lessFlatFilterSize_ = 0.2, const float& surfaceCurvatureThreshold_ = 0.1);
+  float scanPeriod;
+  int imuHistorySize;
+  int nFeatureRegions;
+  int curvatureRegion;
+  int maxCornerSharp;
+  int maxCornerLessSharp;
+  int maxSurfaceFlat;
+  float lessFlatFilterSize;
+  float surfaceCurvatureThreshold;
+};
+
+typedef struct IMUState {
+  Time stamp;
+  Angle roll;
+  Angle pitch;
+  Angle yaw;
+  Vector3 position;
+  Vector3 velocity;
+  Vector3 acceleration;
+  static void interpolate(const IMUState& start, const IMUState& end, const float& ratio, IMUState& result);
+} IMUState;
+
+class BasicScanRegistration {
+ public:
+  BasicScanRegistration();
+  ~BasicScanRegistration();
+  BasicScanRegistration(const BasicScanRegistration&) = delete;
+  BasicScanRegistration& operator=(const BasicScanRegistration&) = delete;
+
+  void processScanlines(const Time& scanTime, std::vector<pcl::PointCloud<pcl::PointXYZI>> const& laserCloudScans);
+  bool configure(const RegistrationParams& config = RegistrationParams());
+  void updateIMUData(Vector3& acc, IMUState& newState);
+  void projectPointToStartOfSweep(pcl::PointXYZI& point, float relTime);
+
+  auto const& imuTransform() { return _imuTrans; }
+  auto const& sweepStart() { return _sweepStart; }
+  auto const& laserCloud() { return _laserCloud; }
+  auto const& cornerPointsSharp() { return _cornerPointsSharp; }
+  auto const& cornerPointsLessSharp() { return _cornerPointsLessSharp; }
+  auto const& surfacePointsFlat() { return _surfacePointsFlat; }
+  auto const& surfacePointsLessFlat() { return _surfacePointsLessFlat; }
+  auto const& config() { return _config; }
+
+  // extension: indices (into laserCloud()) of the picked features and the per-point labels of the last sweep
+  std::vector<int> const& sharpIndices() const { return _sharpIdx; }
+  std::vector<int> const& lessSharpIndices() const { return _lessSharpIdx; }
+  std::vector<int> const& flatIndices() const { return _flatIdx; }
+  std::vector<signed char> const& pointLabels() const { return _labels; }
+
+ private:
+  bool hasIMUData() const { return !_imuHistory.empty(); }
+  void reset(const Time& scanTime);
+  void interpolateIMUStateFor(const float& relTime, IMUState& outputState);
+  void setIMUTransformFor(const float& relTime);
+  void transformToStartIMU(pcl::PointXYZI& point);
+  void updateIMUTransform();
+
+  RegistrationParams _config;
+  pcl::PointCloud<pcl::PointXYZI> _laserCloud;
+  std::vector<IndexRange> _scanIndices;
+  pcl::PointCloud<pcl::PointXYZI> _cornerPointsSharp, _cornerPointsLessSharp, _surfacePointsFlat, _surfacePointsLessFlat;
+
+  Time _sweepStart, _scanTime;
+  IMUState _imuStart, _imuCur;
+  Vector3 _imuPositionShift;
+  size_t _imuIdx = 0;
+  std::vector<IMUState> _imuHistory;  // bounded FIFO of imuHistorySize states
+  pcl::PointCloud<pcl::PointXYZ> _imuTrans = {4, 1};
+
+  b200::Context* _gpu;
+  std::vector<float> _packed, _lessFlatDS;
+  std::vector<int> _ringStart, _ringEnd, _sharpIdx, _lessSharpIdx, _flatIdx;
+  std::vector<signed char> _labels;
+};
+
+}  // namespace loam

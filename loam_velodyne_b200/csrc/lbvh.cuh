@@ -1,0 +1,392 @@
+// Morton-sorted linear BVH in HBM + exact k-NN walk.
+// Replaces nanoflann's k-d tree (include/loam_velodyne/nanoflann.hpp:916-1043 build, :1354-1412 search) with the
+// same observable semantics: exact k nearest neighbours, ascending squared distance, fp32 L2 accumulated
+// x -> y -> z (L2_Simple_Adaptor::evalMetric, nanoflann.hpp:372-379), a candidate only enters when strictly
+// closer than the current k-th (KNNResultSet::addPoint, :115-139; equal distances keep first-seen order).
+//
+// Build (per sweep, like the reference's per-sweep setInputCloud, BasicLaserMapping.cpp:636-637):
+//   bbox reduce -> 30-bit Morton key per point -> LSD radix sort (key, index) -> gather points in Morton order
+//   (xyz + original index in w) -> leaves of LEAF_SIZE consecutive points -> Karras topology over the leaves ->
+//   bottom-up box refit.  Nodes are 64 B (both child boxes + links): one aligned 64 B read per visit.
+#pragma once
+
+#include "ctx.cuh"
+
+namespace loamb {
+
+constexpr int LEAF_SIZE = 8;
+constexpr int KNN_MAX = 8;
+
+// ---------------------------------------------------------------- bbox
+__device__ __forceinline__ unsigned enc_f(float f) {  // order-preserving float -> uint
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float dec_f(unsigned u) {
+  unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(v);
+#else
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+#endif
+}
+
+__global__ void bbox_init_kernel(unsigned* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+__global__ void bbox_kernel(const float4* __restrict__ p, int m, unsigned* bb) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const float4 q = p[i];
+    mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
+    mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
+    mn[2] = fminf(mn[2], q.z); mx[2] = fmaxf(mx[2], q.z);
+  }
+  for (int a = 0; a < 3; a++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&bb[a], enc_f(mn[a]));
+      atomicMax(&bb[3 + a], enc_f(mx[a]));
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned expand10(unsigned v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void morton_kernel(const float4* __restrict__ p, int m, const unsigned* __restrict__ bb,
+                              unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float lx = dec_f(bb[0]), ly = dec_f(bb[1]), lz = dec_f(bb[2]);
+  const float ex = dec_f(bb[3]) - lx, ey = dec_f(bb[4]) - ly, ez = dec_f(bb[5]) - lz;
+  const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
+  const float sc = 1023.0f / ext;  // cubic cells
+  const float4 q = p[i];
+  const unsigned ix = (unsigned)fminf(fmaxf((q.x - lx) * sc, 0.f), 1023.f);
+  const unsigned iy = (unsigned)fminf(fmaxf((q.y - ly) * sc, 0.f), 1023.f);
+  const unsigned iz = (unsigned)fminf(fmaxf((q.z - lz) * sc, 0.f), 1023.f);
+  keys[i] = (expand10(ix) << 2) | (expand10(iy) << 1) | expand10(iz);
+  vals[i] = i;
+}
+
+// ---------------------------------------------------------------- LSD radix sort, 8 bits per pass, 4 passes
+// Per pass: (1) per-tile digit histogram, (2) exclusive scan over (digit, tile), (3) stable scatter.
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;                        // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // keys per CTA
+
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const unsigned* __restrict__ keys, int m, int shift, unsigned* __restrict__ hist, int n_tiles) {
+  __shared__ unsigned h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE;
+  for (int it = 0; it < RS_ITEMS; it++) {
+    const int i = base + it * RS_THREADS + threadIdx.x;
+    if (i < m) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];  // digit-major so one scan gives global offsets
+}
+
+// exclusive scan of 256 * n_tiles counters by a single CTA (n_tiles is small: m / 4096)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ hist, int total) {
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < total; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < total ? hist[i] : 0u;
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned w = warp_sums[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      warp_sums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const unsigned woff = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u;
+    const unsigned incl = x + woff + carry;
+    if (i < total) hist[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+}
+
+// stable scatter: each warp owns RS_ITEMS*32 consecutive keys of the tile and processes them 32 at a time;
+// rank within the CTA = (keys of the same digit in earlier warps) + (earlier keys of the same digit in this warp)
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int m, int shift,
+                     const unsigned* __restrict__ hist, int n_tiles, unsigned* __restrict__ keys_out,
+                     int* __restrict__ vals_out) {
+  constexpr int NW = RS_THREADS / 32;
+  __shared__ unsigned wcount[NW][256];   // per-warp digit counts, then exclusive prefix over warps
+  __shared__ unsigned gbase[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) wcount[warp][d] = 0;
+  gbase[threadIdx.x] = hist[threadIdx.x * n_tiles + blockIdx.x];
+  __syncwarp();
+  const int wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+  unsigned mykeys[RS_ITEMS];
+  unsigned short myrank[RS_ITEMS];
+  // pass A: per-warp counts and the in-warp rank of every key
+  for (int it = 0; it < RS_ITEMS; it++) {
+    const int i = wbase + it * 32 + lane;
+    const bool valid = i < m;
+    const unsigned k = valid ? keys_in[i] : 0xffffffffu;
+    mykeys[it] = k;
+    const unsigned d = (k >> shift) & 255u;
+    // peers with the same digit among valid lanes
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    for (int b = 0; b < 8; b++) {
+      const unsigned bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
+    const unsigned before = __popc(peers & ((1u << lane) - 1u));
+    unsigned prior = 0;
+    if (valid) prior = wcount[warp][d];
+    myrank[it] = (unsigned short)(prior + before);
+    __syncwarp();
+    if (valid && before == 0) wcount[warp][d] = prior + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix over warps for each digit
+  {
+    const int d = threadIdx.x;
+    unsigned acc = 0;
+    for (int wv = 0; wv < NW; wv++) {
+      const unsigned c = wcount[wv][d];
+      wcount[wv][d] = acc;
+      acc += c;
+    }
+  }
+  __syncthreads();
+  for (int it = 0; it < RS_ITEMS; it++) {
+    const int i = wbase + it * 32 + lane;
+    if (i < m) {
+      const unsigned k = mykeys[it];
+      const unsigned d = (k >> shift) & 255u;
+      const unsigned dst = gbase[d] + wcount[warp][d] + myrank[it];
+      keys_out[dst] = k;
+      vals_out[dst] = vals_in[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- gather + leaves
+__global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ order, int m,
+                                     float4* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int o = order[i];
+  float4 p = pts[o];
+  p.w = __int_as_float(o);
+  sorted[i] = p;
+}
+
+__global__ void leaf_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ keys, int m, int n_leaf,
+                            unsigned* __restrict__ leaf_key, float4* __restrict__ box_lo, float4* __restrict__ box_hi,
+                            int* __restrict__ flags) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaf) return;
+  const int b = l * LEAF_SIZE, e = min(b + LEAF_SIZE, m);
+  float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  for (int i = b; i < e; i++) {
+    const float4 p = sorted[i];
+    lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
+    hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
+  }
+  leaf_key[l] = keys[b];
+  // leaves live after the n_leaf-1 internal nodes in the box arrays
+  box_lo[n_leaf - 1 + l] = make_float4(lo.x, lo.y, lo.z, 0.f);
+  box_hi[n_leaf - 1 + l] = make_float4(hi.x, hi.y, hi.z, 0.f);
+  if (l < n_leaf - 1) flags[l] = 0;
+}
+
+// ---------------------------------------------------------------- Karras (2012) topology over leaf keys
+__device__ __forceinline__ int delta_fn(const unsigned* __restrict__ k, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const unsigned a = k[i], b = k[j];
+  if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);
+  return __clz(a ^ b);
+}
+
+__global__ void karras_kernel(const unsigned* __restrict__ leaf_key, int n_leaf, BvhNode* __restrict__ nodes,
+                              int* __restrict__ parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_leaf - 1) return;
+  const int d = (delta_fn(leaf_key, n_leaf, i, i + 1) - delta_fn(leaf_key, n_leaf, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta_fn(leaf_key, n_leaf, i, i - d);
+  int lmax = 2;
+  while (delta_fn(leaf_key, n_leaf, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta_fn(leaf_key, n_leaf, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = delta_fn(leaf_key, n_leaf, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta_fn(leaf_key, n_leaf, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const int c0 = (lo == gamma) ? ~gamma : gamma;            // leaf link = ~leaf id
+  const int c1 = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+  nodes[i].lo0.w = __int_as_float(c0);
+  nodes[i].hi0.w = __int_as_float(c1);
+  parent[(c0 < 0) ? (n_leaf - 1 + ~c0) : c0] = i;
+  parent[(c1 < 0) ? (n_leaf - 1 + ~c1) : c1] = i;
+  if (i == 0) parent[0] = -1;
+}
+
+// bottom-up refit: one thread per leaf climbs; the second arrival at a node merges the children
+__global__ void refit_kernel(int n_leaf, BvhNode* __restrict__ nodes, const int* __restrict__ parent,
+                             float4* __restrict__ box_lo, float4* __restrict__ box_hi, int* __restrict__ flags) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaf) return;
+  int cur = n_leaf - 1 + l;
+  int p = parent[cur];
+  while (p >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[p], 1) == 0) return;  // first arrival: sibling not ready yet
+    __threadfence();
+    const int c0 = __float_as_int(nodes[p].lo0.w), c1 = __float_as_int(nodes[p].hi0.w);
+    const int b0 = (c0 < 0) ? (n_leaf - 1 + ~c0) : c0, b1 = (c1 < 0) ? (n_leaf - 1 + ~c1) : c1;
+    const float4 l0 = __ldcg(&box_lo[b0]), h0 = __ldcg(&box_hi[b0]);
+    const float4 l1 = __ldcg(&box_lo[b1]), h1 = __ldcg(&box_hi[b1]);
+    nodes[p].lo0 = make_float4(l0.x, l0.y, l0.z, __int_as_float(c0));
+    nodes[p].hi0 = make_float4(h0.x, h0.y, h0.z, __int_as_float(c1));
+    nodes[p].lo1 = make_float4(l1.x, l1.y, l1.z, 0.f);
+    nodes[p].hi1 = make_float4(h1.x, h1.y, h1.z, 0.f);
+    __stcg(&box_lo[p], make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f));
+    __stcg(&box_hi[p], make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f));
+    cur = p;
+    p = parent[cur];
+  }
+}
+
+// ---------------------------------------------------------------- k-NN walk (one query per thread)
+struct TreeView {
+  const BvhNode* nodes;
+  const float4* sorted;
+  int m, n_leaf, root;
+};
+
+template <int K>
+struct KnnResult {
+  float d2[K];
+  float x[K], y[K], z[K];
+  int idx[K];
+};
+
+__device__ __forceinline__ float box_d2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
+  const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f);
+  const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f);
+  const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// Exact K nearest with d2 < max_d2.  Results ascending; unfilled slots keep idx = -1, d2 = max_d2 sentinel.
+template <int K>
+__device__ __forceinline__ void knn_walk(const TreeView& t, float qx, float qy, float qz, float max_d2,
+                                         KnnResult<K>& r) {
+#pragma unroll
+  for (int i = 0; i < K; i++) { r.d2[i] = max_d2; r.idx[i] = -1; r.x[i] = 0.f; r.y[i] = 0.f; r.z[i] = 0.f; }
+  if (t.m <= 0) return;
+  int stack_n[64];
+  float stack_d[64];
+  int sp = 0;
+  int node = t.root;
+  while (true) {
+    if (node < 0) {
+      const int leaf = ~node;
+      const int b = leaf * LEAF_SIZE;
+      const int cnt = min(LEAF_SIZE, t.m - b);
+#pragma unroll
+      for (int i = 0; i < LEAF_SIZE; i++) {
+        if (i < cnt) {
+          const float4 p = __ldg(&t.sorted[b + i]);
+          const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < r.d2[K - 1]) {
+            // insert after every entry with d2 <= d (first-seen order among equals)
+            float cd = d, cx = p.x, cy = p.y, cz = p.z;
+            int ci = __float_as_int(p.w);
+#pragma unroll
+            for (int s = 0; s < K; s++) {
+              if (cd < r.d2[s]) {
+                const float td = r.d2[s], tx = r.x[s], ty = r.y[s], tz = r.z[s];
+                const int ti = r.idx[s];
+                r.d2[s] = cd; r.x[s] = cx; r.y[s] = cy; r.z[s] = cz; r.idx[s] = ci;
+                cd = td; cx = tx; cy = ty; cz = tz; ci = ti;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      const BvhNode* nd = t.nodes + node;
+      const float4 lo0 = __ldg(&nd->lo0), hi0 = __ldg(&nd->hi0), lo1 = __ldg(&nd->lo1), hi1 = __ldg(&nd->hi1);
+      const float d0 = box_d2(qx, qy, qz, lo0, hi0), d1 = box_d2(qx, qy, qz, lo1, hi1);
+      const int c0 = __float_as_int(lo0.w), c1 = __float_as_int(hi0.w);
+      const bool first0 = d0 <= d1;
+      const float dn = first0 ? d0 : d1, df = first0 ? d1 : d0;
+      const int cn = first0 ? c0 : c1, cf = first0 ? c1 : c0;
+      const float worst = r.d2[K - 1];
+      if (df < worst && sp < 64) { stack_n[sp] = cf; stack_d[sp] = df; sp++; }
+      if (dn < worst) { node = cn; continue; }
+    }
+    // pop
+    bool found = false;
+    while (sp > 0) {
+      sp--;
+      if (stack_d[sp] < r.d2[K - 1]) { node = stack_n[sp]; found = true; break; }
+    }
+    if (!found) break;
+  }
+}
+
+template <int K>
+__global__ void knn_kernel(TreeView t, const float4* __restrict__ q, int nq, float max_d2, int* __restrict__ idx_out,
+                           float* __restrict__ d2_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const float4 p = q[i];
+  KnnResult<K> r;
+  knn_walk<K>(t, p.x, p.y, p.z, max_d2, r);
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    idx_out[i * K + j] = r.idx[j];
+    d2_out[i * K + j] = r.idx[j] >= 0 ? r.d2[j] : FLT_MAX;
+  }
+}
+
+}  // namespace loamb

@@ -1,0 +1,636 @@
+// libloam_b200.so -- extern "C" entry points (include/loam_b200.h) over the sm_100a kernels.
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point fails loudly.
+#include <cmath>
+
+#include "ctx.cuh"
+#include "features.cuh"
+#include "lbvh.cuh"
+#include "mapping_lm.cuh"
+#include "odometry_lm.cuh"
+#include "voxel.cuh"
+
+using namespace loamb;
+
+#define CHECK_CTX(c) \
+  if (!(c)) return LOAM_B200_ERR_ARG
+
+namespace {
+
+inline int blocks_for(long long n, int bs) { return (int)((n + bs - 1) / bs); }
+
+TreeView view_of(const Tree& t) {
+  TreeView v;
+  v.nodes = t.nodes.p;
+  v.sorted = t.sorted.p;
+  v.m = t.m;
+  v.n_leaf = t.n_leaf;
+  v.root = t.root;
+  return v;
+}
+
+// radix sort (keys, vals) of length m in ctx->sort; result ends in keys_a / vals_a (4 passes = even)
+int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits) {
+  SortScratch& s = c->sort;
+  const int n_tiles = blocks_for(m, RS_TILE);
+  LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles));
+  unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
+  int *va = s.vals_a.p, *vb = s.vals_b.p;
+  int passes = (key_bits + 7) / 8;
+  if (passes & 1) passes++;  // keep the result in buffer a
+  for (int p = 0; p < passes; p++) {
+    const int shift = p * 8;
+    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, shift, s.hist.p, n_tiles);
+    LB_LAUNCH_CHECK(c);
+    radix_scan_kernel<<<1, 1024, 0, c->stream>>>(s.hist.p, 256 * n_tiles);
+    LB_LAUNCH_CHECK(c);
+    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, m, shift, s.hist.p, n_tiles, kb, vb);
+    LB_LAUNCH_CHECK(c);
+    unsigned* tk = ka; ka = kb; kb = tk;
+    int* tv = va; va = vb; vb = tv;
+  }
+  return LOAM_B200_OK;
+}
+
+// build the BVH of tree t from t.pts (device, m points)
+int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
+  t.m = m;
+  t.n_leaf = 0;
+  t.root = 0;
+  if (m <= 0) return LOAM_B200_OK;
+  const int n_leaf = (m + LEAF_SIZE - 1) / LEAF_SIZE;
+  t.n_leaf = n_leaf;
+  SortScratch& s = c->sort;
+  LB_CUDA(c, s.keys_a.reserve(m));
+  LB_CUDA(c, s.keys_b.reserve(m));
+  LB_CUDA(c, s.vals_a.reserve(m));
+  LB_CUDA(c, s.vals_b.reserve(m));
+  LB_CUDA(c, c->bbox.reserve(8));
+  LB_CUDA(c, t.sorted.reserve(m));
+  LB_CUDA(c, t.nodes.reserve(n_leaf > 1 ? n_leaf - 1 : 1));
+  LB_CUDA(c, t.leaf_key.reserve(n_leaf));
+  LB_CUDA(c, t.parent.reserve(2 * (size_t)n_leaf));
+  LB_CUDA(c, t.flags.reserve(n_leaf));
+  LB_CUDA(c, t.box_lo.reserve(2 * (size_t)n_leaf));
+  LB_CUDA(c, t.box_hi.reserve(2 * (size_t)n_leaf));
+  unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
+  bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
+  LB_LAUNCH_CHECK(c);
+  const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 8);
+  bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(t.pts.p, m, bb);
+  LB_LAUNCH_CHECK(c);
+  morton_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.pts.p, m, bb, s.keys_a.p, s.vals_a.p);
+  LB_LAUNCH_CHECK(c);
+  int rc = radix_sort_pairs(c, m, 30);
+  if (rc) return rc;
+  gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.pts.p, s.vals_a.p, m, t.sorted.p);
+  LB_LAUNCH_CHECK(c);
+  leaf_kernel<<<blocks_for(n_leaf, 256), 256, 0, c->stream>>>(t.sorted.p, s.keys_a.p, m, n_leaf, t.leaf_key.p,
+                                                              t.box_lo.p, t.box_hi.p, t.flags.p);
+  LB_LAUNCH_CHECK(c);
+  if (n_leaf == 1) {
+    t.root = ~0;
+    return LOAM_B200_OK;
+  }
+  karras_kernel<<<blocks_for(n_leaf - 1, 256), 256, 0, c->stream>>>(t.leaf_key.p, n_leaf, t.nodes.p, t.parent.p);
+  LB_LAUNCH_CHECK(c);
+  refit_kernel<<<blocks_for(n_leaf, 256), 256, 0, c->stream>>>(n_leaf, t.nodes.p, t.parent.p, t.box_lo.p, t.box_hi.p,
+                                                               t.flags.p);
+  LB_LAUNCH_CHECK(c);
+  t.root = 0;
+  return LOAM_B200_OK;
+}
+
+int upload_points(loam_b200_ctx* c, DevBuf<float4>& dst, const float* src, int n) {
+  if (n <= 0) return LOAM_B200_OK;
+  LB_CUDA(c, dst.reserve(n));
+  LB_CUDA(c, cudaMemcpyAsync(dst.p, src, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  return LOAM_B200_OK;
+}
+
+void fill_map_args(const loam_b200_pose* p, MapIterArgs& a) {
+  const float srx = p->sin_[0], crx = p->cos_[0], sry = p->sin_[1], cry = p->cos_[1], srz = p->sin_[2],
+              crz = p->cos_[2];
+  a.srx = srx; a.crx = crx; a.sry = sry; a.cry = cry; a.srz = srz; a.crz = crz;
+  a.tx = p->pos[0]; a.ty = p->pos[1]; a.tz = p->pos[2];
+  // Jacobian coefficient products, formed left to right exactly like BasicLaserMapping.cpp:842-853
+  a.A[0] = crx * sry * srz;      a.A[1] = crx * crz * sry;        a.A[2] = -(srx * sry);
+  a.A[3] = -srx * srz;           a.A[4] = -(crz * srx);           a.A[5] = -crx;
+  a.A[6] = crx * cry * srz;      a.A[7] = crx * cry * crz;        a.A[8] = -(cry * srx);
+  a.B[0] = cry * srx * srz - crz * sry;
+  a.B[1] = sry * srz + cry * crz * srx;
+  a.B[2] = crx * cry;
+  a.B[3] = a.B[4] = a.B[5] = 0.f;
+  a.B[6] = -cry * crz - srx * sry * srz;
+  a.B[7] = cry * srz - crz * srx * sry;
+  a.B[8] = -(crx * sry);
+  a.C[0] = crz * srx * sry - cry * srz;
+  a.C[1] = -cry * crz - srx * sry * srz;
+  a.C[2] = 0.f;
+  a.C[3] = crx * crz;
+  a.C[4] = -(crx * srz);
+  a.C[5] = 0.f;
+  a.C[6] = sry * srz + cry * crz * srx;
+  a.C[7] = crz * sry - cry * srx * srz;
+  a.C[8] = 0.f;
+}
+
+void fill_odom_args(const loam_b200_odom_pose* p, OdomIterArgs& a) {
+  const float srx = p->sin_[0], crx = p->cos_[0], sry = p->sin_[1], cry = p->cos_[1], srz = p->sin_[2],
+              crz = p->cos_[2];
+  const float tx = p->pos[0], ty = p->pos[1], tz = p->pos[2];
+  a.rx = p->rot[0]; a.ry = p->rot[1]; a.rz = p->rot[2];
+  a.tx = tx; a.ty = ty; a.tz = tz;
+  a.inv_sp = p->inv_scan_period;
+  a.iter = p->iter;
+  // BasicLaserOdometry.cpp:514-543 with s = 1 (every `s *` is an exact multiplication by one)
+  a.g1a = -crx * sry * srz;  a.g1b = crx * crz * sry;  a.g1c = srx * sry;
+  a.k1 = tx * crx * sry * srz;  a.k2 = ty * crx * crz * sry;  a.k3 = tz * srx * sry;
+  a.t1 = srx * srz;  a.t2 = crz * srx;  a.t3 = crx;
+  a.k4 = ty * crz * srx;  a.k5 = tz * crx;  a.k6 = tx * srx * srz;
+  a.u1 = crx * cry * srz;  a.u2 = crx * cry * crz;  a.u3 = cry * srx;
+  a.k7 = tz * cry * srx;  a.k8 = ty * crx * cry * crz;  a.k9 = tx * crx * cry * srz;
+  a.e1 = -crz * sry - cry * srx * srz;
+  a.e2 = cry * crz * srx - sry * srz;
+  a.e3 = crx * cry;
+  a.e4 = crz * sry + cry * srx * srz;
+  a.e5 = sry * srz - cry * crz * srx;
+  a.k10 = tz * crx * cry;
+  a.f1 = cry * crz - srx * sry * srz;
+  a.f2 = cry * srz + crz * srx * sry;
+  a.f3 = crx * sry;
+  a.k11 = tz * crx * sry;
+  a.g1 = -cry * srz - crz * srx * sry;
+  a.h1 = -crx * crz;  a.h2 = crx * srz;
+  a.k12 = ty * crx * srz;  a.k13 = tx * crx * crz;
+  a.atx_y = crx * srz;  a.aty_y = crx * crz;
+  a.atz_x = crx * sry;  a.atz_y = srx;  a.atz_z = crx * cry;
+}
+
+int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
+  LB_CUDA(c, c->result_host.reserve(NEQ));
+  LB_CUDA(c, cudaMemcpyAsync(c->result_host.p, c->result.p, NEQ * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const float* r = c->result_host.p;
+  int k = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      out->AtA[i * 6 + j] = r[k];
+      out->AtA[j * 6 + i] = r[k];
+      k++;
+    }
+  for (int i = 0; i < 6; i++) out->AtB[i] = r[21 + i];
+  out->n_selected = (int)(r[27] + 0.5f);
+  out->n_corner_selected = (int)(r[28] + 0.5f);
+  return LOAM_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* loam_b200_strerror(int status) {
+  switch (status) {
+    case LOAM_B200_OK: return "ok";
+    case LOAM_B200_ERR_ARG: return "invalid argument";
+    case LOAM_B200_ERR_CUDA: return "CUDA error";
+    case LOAM_B200_ERR_NO_DEVICE: return "no usable CUDA device (libloam_b200 has no CPU fallback)";
+    case LOAM_B200_ERR_STATE: return "invalid call sequence";
+    case LOAM_B200_ERR_CAPACITY: return "output capacity too small";
+    case LOAM_B200_ERR_COMM: return "NCCL error";
+  }
+  return "unknown status";
+}
+
+const char* loam_b200_last_error(const loam_b200_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int loam_b200_version(void) { return 100; }
+
+int loam_b200_create(loam_b200_ctx** out, int device) {
+  if (!out || device < 0) return LOAM_B200_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device >= n) {
+    cudaGetLastError();
+    return LOAM_B200_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    return LOAM_B200_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaGetLastError();
+    return LOAM_B200_ERR_NO_DEVICE;
+  }
+  if (prop.major != 10) return LOAM_B200_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  loam_b200_ctx* c = new loam_b200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return LOAM_B200_ERR_CUDA;
+  }
+  cudaFuncSetAttribute(feature_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||
+      c->ticket.reserve(4) != cudaSuccess || c->result_host.reserve(NEQ) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return LOAM_B200_ERR_CUDA;
+  }
+  cudaMemsetAsync(c->ticket.p, 0, 4 * sizeof(unsigned), c->stream);
+  cudaStreamSynchronize(c->stream);
+  *out = c;
+  return LOAM_B200_OK;
+}
+
+int loam_b200_destroy(loam_b200_ctx* c) {
+  CHECK_CTX(c);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->reg_pts.release(); c->reg_ring_start.release(); c->reg_ring_end.release(); c->reg_picks.release();
+  c->reg_counts.release(); c->reg_label.release(); c->reg_lessflat.release(); c->stage.release(); c->stage2.release();
+  for (auto& t : c->tree) {
+    t.pts.release(); t.sorted.release(); t.nodes.release(); t.leaf_key.release(); t.parent.release();
+    t.flags.release(); t.box_lo.release(); t.box_hi.release();
+  }
+  c->sort.keys_a.release(); c->sort.keys_b.release(); c->sort.vals_a.release(); c->sort.vals_b.release();
+  c->sort.hist.release();
+  c->bbox.release(); c->knn_q.release(); c->knn_idx.release(); c->knn_d2.release();
+  c->map_q.release(); c->partials.release(); c->result.release(); c->ticket.release(); c->dbg_coeff.release();
+  c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return LOAM_B200_OK;
+}
+
+int loam_b200_sync(loam_b200_ctx* c) {
+  CHECK_CTX(c);
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
+void* loam_b200_stream(loam_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ features
+int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const int32_t* ring_start,
+                               const int32_t* ring_end, int n_rings, const loam_b200_reg_params* prm,
+                               loam_b200_features* out) {
+  CHECK_CTX(c);
+  if (!pts || n < 0 || !ring_start || !ring_end || n_rings <= 0 || n_rings > 256 || !prm || !out)
+    return LOAM_B200_ERR_ARG;
+  if (prm->curvatureRegion < 1 || prm->curvatureRegion > 15 || prm->nFeatureRegions < 1 || prm->maxCornerSharp < 0 ||
+      prm->maxCornerLessSharp < prm->maxCornerSharp || prm->maxSurfaceFlat < 0 || !(prm->lessFlatFilterSize > 0.f))
+    return LOAM_B200_ERR_ARG;
+  out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
+  int max_ring = 0;
+  for (int r = 0; r < n_rings; r++) {
+    const long long s = ring_start[r], e = ring_end[r];
+    if (s < 0 || e >= n || e < s - 1) {
+      if (!(n == 0 && s == 0 && e == 0)) return LOAM_B200_ERR_ARG;
+    }
+    if (e >= s) max_ring = std::max(max_ring, (int)(e - s + 1));
+  }
+  if (n == 0) return LOAM_B200_OK;
+  FeatParams fp;
+  fp.nFeatureRegions = prm->nFeatureRegions;
+  fp.curvatureRegion = prm->curvatureRegion;
+  fp.maxCornerSharp = prm->maxCornerSharp;
+  fp.maxCornerLessSharp = prm->maxCornerLessSharp;
+  fp.maxSurfaceFlat = prm->maxSurfaceFlat;
+  fp.lessFlatFilterSize = prm->lessFlatFilterSize;
+  fp.surfaceCurvatureThreshold = prm->surfaceCurvatureThreshold;
+  fp.cap_sharp = prm->nFeatureRegions * prm->maxCornerSharp;
+  fp.cap_less = prm->nFeatureRegions * prm->maxCornerLessSharp;
+  fp.cap_flat = prm->nFeatureRegions * prm->maxSurfaceFlat;
+  const int slots = fp.cap_sharp + fp.cap_less + fp.cap_flat;
+
+  int ncap = (max_ring + 31) & ~31;
+  if (ncap < 32) ncap = 32;
+  int n2cap = 1;
+  while (n2cap < ncap) n2cap <<= 1;
+  const size_t smem = (size_t)ncap * (16 + 4 + 4 + 2) + (size_t)n2cap * 8;
+  if (smem > 200 * 1024) return LOAM_B200_ERR_CAPACITY;  // ring longer than ~5.7 k points
+
+  LB_CUDA(c, c->reg_pts.reserve(n));
+  LB_CUDA(c, c->reg_ring_start.reserve(n_rings));
+  LB_CUDA(c, c->reg_ring_end.reserve(n_rings));
+  LB_CUDA(c, c->reg_picks.reserve((size_t)n_rings * slots * 2 + 16));
+  LB_CUDA(c, c->reg_counts.reserve((size_t)n_rings * 4 + 8));
+  LB_CUDA(c, c->reg_label.reserve(n));
+  LB_CUDA(c, c->reg_lessflat.reserve(n));
+  LB_CUDA(c, c->tmp_pts.reserve(n));
+  LB_CUDA(c, cudaMemcpyAsync(c->reg_pts.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_start.p, ring_start, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
+  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_end.p, ring_end, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
+
+  prof_begin(c, LOAM_B200_K_FEATURES);
+  feature_ring_kernel<<<n_rings, FEAT_THREADS, smem, c->stream>>>(c->reg_pts.p, c->reg_ring_start.p,
+                                                                  c->reg_ring_end.p, fp, ncap, n2cap, c->reg_picks.p,
+                                                                  c->reg_counts.p, c->reg_label.p, c->reg_lessflat.p);
+  LB_LAUNCH_CHECK(c);
+  // dense outputs: three pick lists live behind the per-ring slots, totals behind the counts
+  int* dense = c->reg_picks.p + (size_t)n_rings * slots;
+  int* totals = c->reg_counts.p + (size_t)n_rings * 4;
+  feature_pack_kernel<<<1, 256, 0, c->stream>>>(c->reg_counts.p, c->reg_picks.p, c->reg_ring_start.p,
+                                                c->reg_lessflat.p, n_rings, fp, dense,
+                                                dense + (size_t)n_rings * fp.cap_sharp,
+                                                dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less), c->tmp_pts.p,
+                                                totals);
+  LB_LAUNCH_CHECK(c);
+  prof_end(c);
+
+  int h_tot[4];
+  LB_CUDA(c, cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  out->n_sharp = h_tot[0];
+  out->n_less_sharp = h_tot[1];
+  out->n_flat = h_tot[2];
+  out->n_less_flat = h_tot[3];
+  if ((out->sharp_idx && h_tot[0] > out->sharp_cap) || (out->less_sharp_idx && h_tot[1] > out->less_sharp_cap) ||
+      (out->flat_idx && h_tot[2] > out->flat_cap) || (out->less_flat_ds && h_tot[3] > out->less_flat_cap))
+    return LOAM_B200_ERR_CAPACITY;
+  if (out->sharp_idx && h_tot[0])
+    LB_CUDA(c, cudaMemcpyAsync(out->sharp_idx, dense, h_tot[0] * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (out->less_sharp_idx && h_tot[1])
+    LB_CUDA(c, cudaMemcpyAsync(out->less_sharp_idx, dense + (size_t)n_rings * fp.cap_sharp, h_tot[1] * 4,
+                               cudaMemcpyDeviceToHost, c->stream));
+  if (out->flat_idx && h_tot[2])
+    LB_CUDA(c, cudaMemcpyAsync(out->flat_idx, dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less), h_tot[2] * 4,
+                               cudaMemcpyDeviceToHost, c->stream));
+  if (out->label) LB_CUDA(c, cudaMemcpyAsync(out->label, c->reg_label.p, n, cudaMemcpyDeviceToHost, c->stream));
+  if (out->less_flat_ds && h_tot[3])
+    LB_CUDA(c, cudaMemcpyAsync(out->less_flat_ds, c->tmp_pts.p, (size_t)h_tot[3] * 16, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trees
+int loam_b200_tree_build(loam_b200_ctx* c, int slot, const float* pts, int m) {
+  CHECK_CTX(c);
+  if (slot < 0 || slot >= LOAM_B200_NUM_TREES || m < 0 || (m > 0 && !pts)) return LOAM_B200_ERR_ARG;
+  Tree& t = c->tree[slot];
+  int rc = upload_points(c, t.pts, pts, m);
+  if (rc) return rc;
+  prof_begin(c, LOAM_B200_K_TREE_BUILD);
+  rc = tree_build_device(c, t, m);
+  prof_end(c);
+  if (rc) return rc;
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
+int loam_b200_tree_size(loam_b200_ctx* c, int slot) {
+  if (!c || slot < 0 || slot >= LOAM_B200_NUM_TREES) return LOAM_B200_ERR_ARG;
+  return c->tree[slot].m;
+}
+
+int loam_b200_tree_knn(loam_b200_ctx* c, int slot, const float* queries, int nq, int k, float max_d2,
+                       int32_t* idx_out, float* d2_out) {
+  CHECK_CTX(c);
+  if (slot < 0 || slot >= LOAM_B200_NUM_TREES || nq < 0 || (nq > 0 && (!queries || !idx_out || !d2_out)) || k < 1 ||
+      k > KNN_MAX)
+    return LOAM_B200_ERR_ARG;
+  if (nq == 0) return LOAM_B200_OK;
+  int rc = upload_points(c, c->knn_q, queries, nq);
+  if (rc) return rc;
+  LB_CUDA(c, c->knn_idx.reserve((size_t)nq * k));
+  LB_CUDA(c, c->knn_d2.reserve((size_t)nq * k));
+  const TreeView tv = view_of(c->tree[slot]);
+  const int bs = 128, nb = blocks_for(nq, bs);
+  prof_begin(c, LOAM_B200_K_KNN);
+  switch (k) {
+#define KNN_CASE(K)                                                                                              \
+  case K:                                                                                                        \
+    knn_kernel<K><<<nb, bs, 0, c->stream>>>(tv, c->knn_q.p, nq, max_d2, c->knn_idx.p, c->knn_d2.p);              \
+    break;
+    KNN_CASE(1) KNN_CASE(2) KNN_CASE(3) KNN_CASE(4) KNN_CASE(5) KNN_CASE(6) KNN_CASE(7) KNN_CASE(8)
+#undef KNN_CASE
+  }
+  LB_LAUNCH_CHECK(c);
+  prof_end(c);
+  LB_CUDA(c, cudaMemcpyAsync(idx_out, c->knn_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaMemcpyAsync(d2_out, c->knn_d2.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ mapping
+int loam_b200_map_set_queries(loam_b200_ctx* c, const float* corner, int n_corner, const float* surf, int n_surf) {
+  CHECK_CTX(c);
+  if (n_corner < 0 || n_surf < 0 || (n_corner > 0 && !corner) || (n_surf > 0 && !surf)) return LOAM_B200_ERR_ARG;
+  LB_CUDA(c, c->map_q.reserve((size_t)n_corner + n_surf + 1));
+  if (n_corner)
+    LB_CUDA(c, cudaMemcpyAsync(c->map_q.p, corner, (size_t)n_corner * 16, cudaMemcpyHostToDevice, c->stream));
+  if (n_surf)
+    LB_CUDA(c, cudaMemcpyAsync(c->map_q.p + n_corner, surf, (size_t)n_surf * 16, cudaMemcpyHostToDevice, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->map_nc = n_corner;
+  c->map_ns = n_surf;
+  return LOAM_B200_OK;
+}
+
+static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b200_normal_eq* out, float* coeff,
+                            int8_t* selected) {
+  CHECK_CTX(c);
+  if (!pose || !out) return LOAM_B200_ERR_ARG;
+  const int nc = c->map_nc, ns = c->map_ns;
+  memset(out, 0, sizeof *out);
+  if (nc + ns == 0) return LOAM_B200_OK;
+  MapIterArgs a;
+  fill_map_args(pose, a);
+  const int cb = blocks_for(nc, LM_THREADS), sb = blocks_for(ns, LM_THREADS);
+  const int nb = cb + sb;
+  LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
+  const bool dbg = coeff != nullptr;
+  if (dbg) {
+    LB_CUDA(c, c->dbg_coeff.reserve(nc + ns));
+    LB_CUDA(c, c->dbg_sel.reserve(nc + ns));
+  }
+  prof_begin(c, LOAM_B200_K_MAP_ITER);
+  map_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(c->tree[LOAM_B200_TREE_MAP_CORNER]),
+                                                       view_of(c->tree[LOAM_B200_TREE_MAP_SURF]), c->map_q.p, nc, ns,
+                                                       cb, a, c->partials.p, c->result.p, c->ticket.p,
+                                                       dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr);
+  LB_LAUNCH_CHECK(c);
+  prof_end(c);
+  int rc = fetch_normal_eq(c, out);
+  if (rc) return rc;
+  if (dbg) {
+    LB_CUDA(c, cudaMemcpyAsync(coeff, c->dbg_coeff.p, (size_t)(nc + ns) * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (selected)
+      LB_CUDA(c, cudaMemcpyAsync(selected, c->dbg_sel.p, (size_t)(nc + ns), cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return LOAM_B200_OK;
+}
+
+int loam_b200_map_iterate(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b200_normal_eq* out) {
+  return map_iterate_impl(c, pose, out, nullptr, nullptr);
+}
+int loam_b200_map_iterate_debug(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b200_normal_eq* out, float* coeff,
+                                int8_t* selected) {
+  if (!coeff) return LOAM_B200_ERR_ARG;
+  return map_iterate_impl(c, pose, out, coeff, selected);
+}
+
+// ------------------------------------------------------------------------------------------------ odometry
+int loam_b200_odom_set_last(loam_b200_ctx* c, const float* corner, int n_corner, const float* surf, int n_surf) {
+  CHECK_CTX(c);
+  int rc = loam_b200_tree_build(c, LOAM_B200_TREE_ODOM_CORNER, corner, n_corner);
+  if (rc) return rc;
+  rc = loam_b200_tree_build(c, LOAM_B200_TREE_ODOM_SURF, surf, n_surf);
+  if (rc) return rc;
+  c->od_last_set = true;
+  return LOAM_B200_OK;
+}
+
+int loam_b200_odom_set_current(loam_b200_ctx* c, const float* sharp, int n_sharp, const float* flat, int n_flat) {
+  CHECK_CTX(c);
+  if (n_sharp < 0 || n_flat < 0 || (n_sharp > 0 && !sharp) || (n_flat > 0 && !flat)) return LOAM_B200_ERR_ARG;
+  LB_CUDA(c, c->od_q.reserve((size_t)n_sharp + n_flat + 1));
+  LB_CUDA(c, c->od_ind.reserve(((size_t)n_sharp + n_flat + 1) * 3));
+  if (n_sharp) LB_CUDA(c, cudaMemcpyAsync(c->od_q.p, sharp, (size_t)n_sharp * 16, cudaMemcpyHostToDevice, c->stream));
+  if (n_flat)
+    LB_CUDA(c, cudaMemcpyAsync(c->od_q.p + n_sharp, flat, (size_t)n_flat * 16, cudaMemcpyHostToDevice, c->stream));
+  LB_CUDA(c, cudaMemsetAsync(c->od_ind.p, 0xff, ((size_t)n_sharp + n_flat + 1) * 3 * sizeof(int), c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->od_nsharp = n_sharp;
+  c->od_nflat = n_flat;
+  return LOAM_B200_OK;
+}
+
+static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, loam_b200_normal_eq* out,
+                             float* coeff, int8_t* selected, int32_t* ind) {
+  CHECK_CTX(c);
+  if (!pose || !out) return LOAM_B200_ERR_ARG;
+  if (!c->od_last_set) return LOAM_B200_ERR_STATE;
+  const int nsh = c->od_nsharp, nfl = c->od_nflat;
+  memset(out, 0, sizeof *out);
+  if (nsh + nfl == 0) return LOAM_B200_OK;
+  OdomIterArgs a;
+  fill_odom_args(pose, a);
+  const Tree& tc = c->tree[LOAM_B200_TREE_ODOM_CORNER];
+  const Tree& ts = c->tree[LOAM_B200_TREE_ODOM_SURF];
+  a.n_last_corner = tc.m;
+  a.n_last_surf = ts.m;
+  const int cb = blocks_for(nsh, LM_THREADS), sb = blocks_for(nfl, LM_THREADS);
+  const int nb = cb + sb;
+  LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
+  const bool dbg = coeff != nullptr;
+  if (dbg) {
+    LB_CUDA(c, c->dbg_coeff.reserve(nsh + nfl));
+    LB_CUDA(c, c->dbg_sel.reserve(nsh + nfl));
+  }
+  prof_begin(c, LOAM_B200_K_ODOM_ITER);
+  odom_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.pts.p, ts.pts.p, c->od_q.p, nsh,
+                                                        nfl, cb, a, c->od_ind.p, c->partials.p, c->result.p,
+                                                        c->ticket.p, dbg ? c->dbg_coeff.p : nullptr,
+                                                        dbg ? c->dbg_sel.p : nullptr);
+  LB_LAUNCH_CHECK(c);
+  prof_end(c);
+  int rc = fetch_normal_eq(c, out);
+  if (rc) return rc;
+  if (dbg) {
+    LB_CUDA(c, cudaMemcpyAsync(coeff, c->dbg_coeff.p, (size_t)(nsh + nfl) * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (selected)
+      LB_CUDA(c, cudaMemcpyAsync(selected, c->dbg_sel.p, (size_t)(nsh + nfl), cudaMemcpyDeviceToHost, c->stream));
+    if (ind)
+      LB_CUDA(c, cudaMemcpyAsync(ind, c->od_ind.p, (size_t)(nsh + nfl) * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return LOAM_B200_OK;
+}
+
+int loam_b200_odom_iterate(loam_b200_ctx* c, const loam_b200_odom_pose* pose, loam_b200_normal_eq* out) {
+  return odom_iterate_impl(c, pose, out, nullptr, nullptr, nullptr);
+}
+int loam_b200_odom_iterate_debug(loam_b200_ctx* c, const loam_b200_odom_pose* pose, loam_b200_normal_eq* out,
+                                 float* coeff, int8_t* selected, int32_t* ind) {
+  if (!coeff) return LOAM_B200_ERR_ARG;
+  return odom_iterate_impl(c, pose, out, coeff, selected, ind);
+}
+
+// ------------------------------------------------------------------------------------------------ bulk transforms
+int loam_b200_transform_to_end(loam_b200_ctx* c, float* pts, int n, const loam_b200_odom_pose* p) {
+  CHECK_CTX(c);
+  if (n < 0 || (n > 0 && !pts) || !p) return LOAM_B200_ERR_ARG;
+  if (n == 0) return LOAM_B200_OK;
+  int rc = upload_points(c, c->tmp_pts2, pts, n);
+  if (rc) return rc;
+  ToEndArgs a;
+  a.rx = p->rot[0]; a.ry = p->rot[1]; a.rz = p->rot[2];
+  a.tx = p->pos[0]; a.ty = p->pos[1]; a.tz = p->pos[2];
+  a.inv_sp = p->inv_scan_period;
+  a.srx = p->sin_[0]; a.crx = p->cos_[0]; a.sry = p->sin_[1]; a.cry = p->cos_[1]; a.srz = p->sin_[2]; a.crz = p->cos_[2];
+  prof_begin(c, LOAM_B200_K_TRANSFORM);
+  transform_to_end_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->tmp_pts2.p, n, a);
+  LB_LAUNCH_CHECK(c);
+  prof_end(c);
+  LB_CUDA(c, cudaMemcpyAsync(pts, c->tmp_pts2.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
+int loam_b200_transform_to_map(loam_b200_ctx* c, float* pts, int n, const loam_b200_pose* p) {
+  CHECK_CTX(c);
+  if (n < 0 || (n > 0 && !pts) || !p) return LOAM_B200_ERR_ARG;
+  if (n == 0) return LOAM_B200_OK;
+  int rc = upload_points(c, c->tmp_pts2, pts, n);
+  if (rc) return rc;
+  MapIterArgs a;
+  fill_map_args(p, a);
+  prof_begin(c, LOAM_B200_K_TRANSFORM);
+  transform_to_map_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->tmp_pts2.p, n, a);
+  LB_LAUNCH_CHECK(c);
+  prof_end(c);
+  LB_CUDA(c, cudaMemcpyAsync(pts, c->tmp_pts2.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ voxel grid
+int loam_b200_voxel_grid(loam_b200_ctx* c, const float* pts, int n, float leaf, float* out, int cap, int* n_out) {
+  CHECK_CTX(c);
+  if (n < 0 || (n > 0 && (!pts || !out)) || !n_out || !(leaf > 0.f)) return LOAM_B200_ERR_ARG;
+  *n_out = 0;
+  if (n == 0) return LOAM_B200_OK;
+  int rc = upload_points(c, c->tmp_pts, pts, n);
+  if (rc) return rc;
+  LB_CUDA(c, c->tmp_pts2.reserve(n));
+  int count = 0;
+  prof_begin(c, LOAM_B200_K_VOXEL);
+  rc = voxel_grid_device(c, c->tmp_pts.p, n, leaf, c->tmp_pts2.p, &count);
+  prof_end(c);
+  if (rc) return rc;
+  if (count > cap) return LOAM_B200_ERR_CAPACITY;
+  LB_CUDA(c, cudaMemcpyAsync(out, c->tmp_pts2.p, (size_t)count * 16, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_out = count;
+  return LOAM_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+int loam_b200_profile_enable(loam_b200_ctx* c, int on) {
+  CHECK_CTX(c);
+  c->prof_on = on != 0;
+  return LOAM_B200_OK;
+}
+int loam_b200_profile_reset(loam_b200_ctx* c) {
+  CHECK_CTX(c);
+  for (int i = 0; i < LOAM_B200_NUM_KERNEL_FAMILIES; i++) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; }
+  return LOAM_B200_OK;
+}
+int loam_b200_profile_get(loam_b200_ctx* c, int family, double* gpu_ms, long long* launches) {
+  CHECK_CTX(c);
+  if (family < 0 || family >= LOAM_B200_NUM_KERNEL_FAMILIES) return LOAM_B200_ERR_ARG;
+  if (gpu_ms) *gpu_ms = c->prof_ms[family];
+  if (launches) *launches = c->prof_launches[family];
+  return LOAM_B200_OK;
+}
+long long loam_b200_launch_count(loam_b200_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// Fused scan-to-map Gauss-Newton iteration.
+// One thread per stack point: pointAssociateToMap (BasicLaserMapping.cpp:207-219) -> 5-NN against the corner /
+// surface map BVH with the d5^2 < 1.0 gate folded into the walk (:669-671, :758-760) -> PCA line fit (:673-710) or
+// 5x3 least-squares plane fit (:762-791) -> residual weight (:712-749, :795-814) -> Jacobian row (:842-861) ->
+// warp-shuffle tree reduction of the 21 + 6 normal-equation accumulators (+ counts), one partial per CTA,
+// combined in fixed order by the last CTA to finish (deterministic run to run).
+#pragma once
+
+#include "lbvh.cuh"
+#include "linalg.cuh"
+
+namespace loamb {
+
+constexpr int LM_THREADS = 128;
+constexpr int NEQ = 32;  // 21 AtA (upper triangle, row-major) + 6 AtB + n_selected + n_corner_selected + 3 pad
+
+struct MapIterArgs {
+  float srx, crx, sry, cry, srz, crz;  // sin / cos of rot_x, rot_y, rot_z as cached by the host's Angle objects
+  float tx, ty, tz;
+  float A[9], B[9], C[9];              // Jacobian coefficient matrices, products formed on the host in reference order
+};
+
+__device__ __forceinline__ void associate_to_map(const MapIterArgs& a, const float4& pi, float& x, float& y, float& z) {
+  // rotateZXY(po, rot_z, rot_x, rot_y) then translate (math_utils.h:196-238)
+  const float x1 = a.crz * pi.x - a.srz * pi.y;
+  const float y1 = a.srz * pi.x + a.crz * pi.y;
+  const float y2 = a.crx * y1 - a.srx * pi.z;
+  const float z2 = a.srx * y1 + a.crx * pi.z;
+  const float x3 = a.cry * x1 + a.sry * z2;
+  const float z3 = a.cry * z2 - a.sry * x1;
+  x = x3 + a.tx;
+  y = y2 + a.ty;
+  z = z3 + a.tz;
+}
+
+// closed-form point-to-line residual shared by mapping (:712-730) and odometry (BasicLaserOdometry.cpp:319-337)
+__device__ __forceinline__ void line_residual(float x0, float y0, float z0, float x1, float y1, float z1, float x2,
+                                              float y2, float z2, float& la, float& lb, float& lc, float& ld2) {
+  const float m11 = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+  const float m12 = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+  const float m13 = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+  const float a012 = sqrtf(m11 * m11 + m12 * m12 + m13 * m13);
+  const float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+  la = ((y1 - y2) * m11 + (z1 - z2) * m12) / a012 / l12;
+  lb = -((x1 - x2) * m11 - (z1 - z2) * m13) / a012 / l12;
+  lc = -((x1 - x2) * m12 + (y1 - y2) * m13) / a012 / l12;
+  ld2 = a012 / l12;
+}
+
+// corner correspondence (:671-751). Returns true when the point is selected; coeff = (s*la, s*lb, s*lc, s*ld2)
+__device__ __forceinline__ bool corner_fit(const KnnResult<5>& nn, float sx, float sy, float sz, float4& coeff) {
+  if (nn.idx[4] < 0) return false;  // fewer than five map points with d2 < 1.0  <=>  pointSearchSqDis[4] >= 1.0
+  float vx = 0.f, vy = 0.f, vz = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) { vx += nn.x[j]; vy += nn.y[j]; vz += nn.z[j]; }
+  vx /= 5.0f; vy /= 5.0f; vz /= 5.0f;
+  float m[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) m[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const float ax = nn.x[j] - vx, ay = nn.y[j] - vy, az = nn.z[j] - vz;
+    m[0] += ax * ax;  // (0,0)
+    m[1] += ax * ay;  // (1,0)
+    m[2] += ax * az;  // (2,0)
+    m[4] += ay * ay;  // (1,1)
+    m[5] += ay * az;  // (2,1)
+    m[8] += az * az;  // (2,2)
+  }
+  m[0] /= 5.0f; m[1] /= 5.0f; m[2] /= 5.0f; m[4] /= 5.0f; m[5] /= 5.0f; m[8] /= 5.0f;
+  float ev[3], V[9];
+  sym_eigen<3>(m, ev, V);
+  if (!(ev[2] > 3.f * ev[1])) return false;
+  // end points vc +- 0.1 * v (the 0.1 literal is double in the reference, :705-710)
+  const float x1 = (float)((double)vx + 0.1 * (double)V[0 + 2 * 3]);
+  const float y1 = (float)((double)vy + 0.1 * (double)V[1 + 2 * 3]);
+  const float z1 = (float)((double)vz + 0.1 * (double)V[2 + 2 * 3]);
+  const float x2 = (float)((double)vx - 0.1 * (double)V[0 + 2 * 3]);
+  const float y2 = (float)((double)vy - 0.1 * (double)V[1 + 2 * 3]);
+  const float z2 = (float)((double)vz - 0.1 * (double)V[2 + 2 * 3]);
+  float la, lb, lc, ld2;
+  line_residual(sx, sy, sz, x1, y1, z1, x2, y2, z2, la, lb, lc, ld2);
+  const float s = 1.f - 0.9f * fabsf(ld2);
+  coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
+  return (double)s > 0.1;
+}
+
+// surface correspondence (:760-816)
+__device__ __forceinline__ bool surf_fit(const KnnResult<5>& nn, float sx, float sy, float sz, float4& coeff) {
+  if (nn.idx[4] < 0) return false;
+  float A[15], b[5], x[3];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    A[j + 0 * 5] = nn.x[j];
+    A[j + 1 * 5] = nn.y[j];
+    A[j + 2 * 5] = nn.z[j];
+    b[j] = -1.f;
+  }
+  colpiv_qr_solve<5, 3>(A, b, x);
+  float pa = x[0], pb = x[1], pc = x[2], pd = 1.f;
+  const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+#pragma unroll
+  for (int j = 0; j < 5; j++)
+    if ((double)fabsf(pa * nn.x[j] + pb * nn.y[j] + pc * nn.z[j] + pd) > 0.2) return false;
+  const float pd2 = pa * sx + pb * sy + pc * sz + pd;
+  const float s = 1.f - 0.9f * fabsf(pd2) / sqrtf(sqrtf(sx * sx + sy * sy + sz * sz));
+  coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+  return (double)s > 0.1;
+}
+
+// accumulate one Jacobian row into the 29 running sums
+__device__ __forceinline__ void accumulate_row(float* acc, const float* row, float b, bool is_corner) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = i; j < 6; j++) acc[k++] += row[i] * row[j];
+#pragma unroll
+  for (int i = 0; i < 6; i++) acc[21 + i] += row[i] * b;
+  acc[27] += 1.f;
+  if (is_corner) acc[28] += 1.f;
+}
+
+// block reduction of NEQ accumulators -> partials[block]; the last block to finish folds all partials in block
+// order (double accumulation) into result[NEQ] and resets the ticket for the next launch.
+__device__ __forceinline__ void reduce_normal_equations(float* acc, float* __restrict__ partials,
+                                                        float* __restrict__ result, unsigned int* ticket) {
+  __shared__ float s_part[LM_THREADS / 32][NEQ];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 29; k++) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NEQ) {
+    float v = 0.f;
+    if (threadIdx.x < 29)
+      for (int wv = 0; wv < LM_THREADS / 32; wv++) v += s_part[wv][threadIdx.x];
+    __stcg(&partials[(size_t)blockIdx.x * NEQ + threadIdx.x], v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < NEQ) {
+      double v = 0.0;
+      for (unsigned bk = 0; bk < gridDim.x; bk++) v += (double)__ldcg(&partials[(size_t)bk * NEQ + threadIdx.x]);
+      result[threadIdx.x] = (float)v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(LM_THREADS)
+map_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ queries, int n_corner,
+                   int n_surf, int corner_blocks, MapIterArgs a, float* __restrict__ partials,
+                   float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
+                   int8_t* __restrict__ dbg_sel) {
+  float acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; k++) acc[k] = 0.f;
+
+  const bool is_corner = (int)blockIdx.x < corner_blocks;
+  const int local = is_corner ? blockIdx.x * LM_THREADS + threadIdx.x
+                              : (blockIdx.x - corner_blocks) * LM_THREADS + threadIdx.x;
+  const int qi = is_corner ? local : n_corner + local;
+  const bool active = is_corner ? (local < n_corner) : (local < n_surf);
+  if (active) {
+    const float4 po = queries[qi];
+    float sx, sy, sz;
+    associate_to_map(a, po, sx, sy, sz);
+    KnnResult<5> nn;
+    knn_walk<5>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 1.0f, nn);
+    float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool sel = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
+    if (dbg_coeff) {
+      dbg_coeff[qi] = coeff;
+      dbg_sel[qi] = sel ? 1 : 0;
+    }
+    if (sel) {
+      float row[6];
+      row[0] = (a.A[0] * po.x + a.A[1] * po.y + a.A[2] * po.z) * coeff.x +
+               (a.A[3] * po.x + a.A[4] * po.y + a.A[5] * po.z) * coeff.y +
+               (a.A[6] * po.x + a.A[7] * po.y + a.A[8] * po.z) * coeff.z;
+      row[1] = (a.B[0] * po.x + a.B[1] * po.y + a.B[2] * po.z) * coeff.x +
+               (a.B[6] * po.x + a.B[7] * po.y + a.B[8] * po.z) * coeff.z;
+      row[2] = (a.C[0] * po.x + a.C[1] * po.y) * coeff.x + (a.C[3] * po.x + a.C[4] * po.y) * coeff.y +
+               (a.C[6] * po.x + a.C[7] * po.y) * coeff.z;
+      row[3] = coeff.x;
+      row[4] = coeff.y;
+      row[5] = coeff.z;
+      accumulate_row(acc, row, -coeff.w, is_corner);
+    }
+  }
+  reduce_normal_equations(acc, partials, result, ticket);
+}
+
+}  // namespace loamb

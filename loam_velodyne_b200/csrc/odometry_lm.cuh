@@ -1,0 +1,254 @@
+// Fused scan-to-scan Gauss-Newton iteration and the bulk transforms (O6, M1).
+// One thread per sharp / flat feature point: transformToStart (BasicLaserOdometry.cpp:40-53) -> on every 5th
+// iteration 1-NN in the last corner / surface cloud (BVH walk, d^2 < 25 gate) plus the +-2.5-ring linear scans in
+// the ring-ordered last cloud (:253-302, :370-435; loop bounds reproduce the reference) ->
+// point-to-line / point-to-plane residual and weight (:304-361, :437-481) -> Jacobian row (:497-553) -> the same
+// warp-shuffle / last-CTA reduction as the mapping kernel.
+#pragma once
+
+#include "mapping_lm.cuh"
+
+namespace loamb {
+
+struct OdomIterArgs {
+  float rx, ry, rz;     // _transform rotation (rad)
+  float tx, ty, tz;     // _transform translation
+  float inv_sp;         // 1.f / scanPeriod
+  int iter;
+  int n_last_corner, n_last_surf;
+  // Jacobian terms (BasicLaserOdometry.cpp:514-543), every product formed on the host in the reference's order
+  float g1a, g1b, g1c, k1, k2, k3;      // arx group multiplying coeff.x
+  float t1, t2, t3, k4, k5, k6;         // arx group multiplying coeff.y
+  float u1, u2, u3, k7, k8, k9;         // arx group multiplying coeff.z
+  float e1, e2, e3, e4, e5, k10;        // ary group multiplying coeff.x
+  float f1, f2, f3, k11;                // ary group multiplying coeff.z
+  float g1;                             // arz
+  float h1, h2, k12, k13;
+  float atx_y, aty_y, atz_x, atz_y, atz_z;  // crx*srz, crx*crz, crx*sry, srx, crx*cry
+};
+
+// cos / sin evaluated in double and rounded once: agrees with a correctly rounded float libm (the reference
+// calls std::cos / std::sin on float, Angle.h:23-26) except in rare double-rounding cases.
+__device__ __forceinline__ void sincos_f(float a, float& s, float& c) {
+  double sd, cd;
+  sincos((double)a, &sd, &cd);
+  s = (float)sd;
+  c = (float)cd;
+}
+
+__device__ __forceinline__ void rot_zxy(float& x, float& y, float& z, float sz, float cz, float sx, float cx,
+                                        float sy, float cy) {
+  const float x1 = cz * x - sz * y;
+  const float y1 = sz * x + cz * y;
+  const float y2 = cx * y1 - sx * z;
+  const float z2 = sx * y1 + cx * z;
+  const float x3 = cy * x1 + sy * z2;
+  const float z3 = cy * z2 - sy * x1;
+  x = x3; y = y2; z = z3;
+}
+__device__ __forceinline__ void rot_yxz(float& x, float& y, float& z, float sy, float cy, float sx, float cx,
+                                        float sz, float cz) {
+  const float x1 = cy * x + sy * z;
+  const float z1 = cy * z - sy * x;
+  const float y2 = cx * y - sx * z1;
+  const float z2 = sx * y + cx * z1;
+  const float x3 = cz * x1 - sz * y2;
+  const float y3 = sz * x1 + cz * y2;
+  x = x3; y = y3; z = z2;
+}
+
+__device__ __forceinline__ void transform_to_start(const OdomIterArgs& a, const float4& pi, float& x, float& y,
+                                                   float& z) {
+  const float s = a.inv_sp * (pi.w - (float)(int)pi.w);
+  x = pi.x - s * a.tx;
+  y = pi.y - s * a.ty;
+  z = pi.z - s * a.tz;
+  float sx, cx, sy, cy, sz, cz;
+  sincos_f(-s * a.rx, sx, cx);
+  sincos_f(-s * a.ry, sy, cy);
+  sincos_f(-s * a.rz, sz, cz);
+  rot_zxy(x, y, z, sz, cz, sx, cx, sy, cy);
+}
+
+__device__ __forceinline__ float sqdiff3(const float4& a, float bx, float by, float bz) {
+  const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(LM_THREADS)
+odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
+                    const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
+                    int sharp_blocks, OdomIterArgs a, int* __restrict__ ind, float* __restrict__ partials,
+                    float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
+                    int8_t* __restrict__ dbg_sel) {
+  float acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; k++) acc[k] = 0.f;
+
+  const bool is_corner = (int)blockIdx.x < sharp_blocks;
+  const int local = is_corner ? blockIdx.x * LM_THREADS + threadIdx.x
+                              : (blockIdx.x - sharp_blocks) * LM_THREADS + threadIdx.x;
+  const int qi = is_corner ? local : n_sharp + local;
+  const bool active = is_corner ? (local < n_sharp) : (local < n_flat);
+  if (active) {
+    const float4 po = queries[qi];
+    float sx, sy, sz;
+    transform_to_start(a, po, sx, sy, sz);
+    int i1, i2, i3 = -1;
+    if (a.iter % 5 == 0) {
+      KnnResult<1> nn;
+      knn_walk<1>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 25.0f, nn);
+      i1 = nn.idx[0];
+      i2 = -1;
+      if (is_corner) {
+        if (i1 >= 0) {
+          const int scan = (int)last_corner[i1].w;
+          float min2 = 25.f;
+          // forward scan bounded by the CURRENT sharp count (BasicLaserOdometry.cpp:262), clamped to the cloud
+          const int fend = min(n_sharp, a.n_last_corner);
+          for (int j = i1 + 1; j < fend; j++) {
+            const float4 p = last_corner[j];
+            const int r = (int)p.w;
+            if ((double)r > (double)scan + 2.5) break;
+            const float d = sqdiff3(p, sx, sy, sz);
+            if (r > scan && d < min2) { min2 = d; i2 = j; }
+          }
+          for (int j = i1 - 1; j >= 0; j--) {
+            const float4 p = last_corner[j];
+            const int r = (int)p.w;
+            if ((double)r < (double)scan - 2.5) break;
+            const float d = sqdiff3(p, sx, sy, sz);
+            if (r < scan && d < min2) { min2 = d; i2 = j; }
+          }
+        }
+      } else {
+        if (i1 >= 0) {
+          const int scan = (int)last_surf[i1].w;
+          float min2 = 25.f, min3 = 25.f;
+          const int fend = min(n_flat, a.n_last_surf);  // :378
+          for (int j = i1 + 1; j < fend; j++) {
+            const float4 p = last_surf[j];
+            const int r = (int)p.w;
+            if ((double)r > (double)scan + 2.5) break;
+            const float d = sqdiff3(p, sx, sy, sz);
+            if (r <= scan) {
+              if (d < min2) { min2 = d; i2 = j; }
+            } else {
+              if (d < min3) { min3 = d; i3 = j; }
+            }
+          }
+          for (int j = i1 - 1; j >= 0; j--) {
+            const float4 p = last_surf[j];
+            const int r = (int)p.w;
+            if ((double)r < (double)scan - 2.5) break;
+            const float d = sqdiff3(p, sx, sy, sz);
+            if (r >= scan) {
+              if (d < min2) { min2 = d; i2 = j; }
+            } else {
+              if (d < min3) { min3 = d; i3 = j; }
+            }
+          }
+        }
+      }
+      ind[qi * 3 + 0] = i1;
+      ind[qi * 3 + 1] = i2;
+      ind[qi * 3 + 2] = i3;
+    } else {
+      i1 = ind[qi * 3 + 0];
+      i2 = ind[qi * 3 + 1];
+      i3 = ind[qi * 3 + 2];
+    }
+
+    float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool sel = false;
+    if (is_corner) {
+      if (i2 >= 0) {
+        const float4 t1 = last_corner[i1], t2 = last_corner[i2];
+        float la, lb, lc, ld2;
+        line_residual(sx, sy, sz, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, la, lb, lc, ld2);
+        float s = 1.f;
+        if (a.iter >= 5) s = 1.f - 1.8f * fabsf(ld2);
+        coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
+        sel = (double)s > 0.1 && ld2 != 0.f;
+      }
+    } else {
+      if (i2 >= 0 && i3 >= 0) {
+        const float4 t1 = last_surf[i1], t2 = last_surf[i2], t3 = last_surf[i3];
+        float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
+        float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
+        float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
+        float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
+        const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+        pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+        const float pd2 = pa * sx + pb * sy + pc * sz + pd;
+        float s = 1.f;
+        if (a.iter >= 5) s = 1.f - 1.8f * fabsf(pd2) / sqrtf(sqrtf(sx * sx + sy * sy + sz * sz));
+        coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+        sel = (double)s > 0.1 && pd2 != 0.f;
+      }
+    }
+    if (dbg_coeff) {
+      dbg_coeff[qi] = coeff;
+      dbg_sel[qi] = sel ? 1 : 0;
+    }
+    if (sel) {
+      const float px = po.x, py = po.y, pz = po.z;
+      const float G1 = a.g1a * px + a.g1b * py + a.g1c * pz + a.k1 - a.k2 - a.k3;
+      const float G2 = a.t1 * px - a.t2 * py + a.t3 * pz + a.k4 - a.k5 - a.k6;
+      const float G3 = a.u1 * px - a.u2 * py - a.u3 * pz + a.k7 + a.k8 - a.k9;
+      const float H1 = a.e1 * px + a.e2 * py - a.e3 * pz + a.tx * a.e4 + a.ty * a.e5 + a.k10;
+      const float H2 = a.f1 * px + a.f2 * py - a.f3 * pz + a.k11 - a.ty * a.f2 - a.tx * a.f1;
+      const float I1 = a.g1 * px + a.f1 * py + a.tx * a.f2 - a.ty * a.f1;
+      const float I2 = a.h1 * px - a.h2 * py + a.k12 + a.k13;
+      const float I3 = a.e2 * px + a.e4 * py + a.tx * a.e5 - a.ty * a.e4;
+      float row[6];
+      row[0] = G1 * coeff.x + G2 * coeff.y + G3 * coeff.z;
+      row[1] = H1 * coeff.x + H2 * coeff.z;
+      row[2] = I1 * coeff.x + I2 * coeff.y + I3 * coeff.z;
+      row[3] = (-a.f1) * coeff.x + a.atx_y * coeff.y - a.e4 * coeff.z;
+      row[4] = (-a.f2) * coeff.x - a.aty_y * coeff.y - a.e5 * coeff.z;
+      row[5] = a.atz_x * coeff.x - a.atz_y * coeff.y - a.atz_z * coeff.z;
+      const float b = (float)(-0.05 * (double)coeff.w);
+      accumulate_row(acc, row, b, is_corner);
+    }
+  }
+  reduce_normal_equations(acc, partials, result, ticket);
+}
+
+// BasicLaserOdometry::transformToEnd without IMU terms (BasicLaserOdometry.cpp:57-87): in place on a device cloud.
+// sy,cy,... are the host-cached sin/cos of the full transform.
+struct ToEndArgs {
+  float rx, ry, rz, tx, ty, tz, inv_sp;
+  float srx, crx, sry, cry, srz, crz;
+};
+__global__ void transform_to_end_kernel(float4* __restrict__ p, int n, ToEndArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = p[i];
+  const float s = a.inv_sp * (q.w - (float)(int)q.w);
+  float x = q.x - s * a.tx, y = q.y - s * a.ty, z = q.z - s * a.tz;
+  q.w = (float)(int)q.w;
+  float sx, cx, sy, cy, sz, cz;
+  sincos_f(-s * a.rx, sx, cx);
+  sincos_f(-s * a.ry, sy, cy);
+  sincos_f(-s * a.rz, sz, cz);
+  rot_zxy(x, y, z, sz, cz, sx, cx, sy, cy);
+  rot_yxz(x, y, z, a.sry, a.cry, a.srx, a.crx, a.srz, a.crz);
+  // += pos - imuShiftFromStart (zero without IMU); the two IMU rotations are identities (Angle(): cos 1, sin 0)
+  q.x = x + a.tx;
+  q.y = y + a.ty;
+  q.z = z + a.tz;
+  p[i] = q;
+}
+
+__global__ void transform_to_map_kernel(float4* __restrict__ p, int n, MapIterArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = p[i];
+  float x, y, z;
+  associate_to_map(a, q, x, y, z);
+  q.x = x; q.y = y; q.z = z;
+  p[i] = q;
+}
+
+}  // namespace loamb
