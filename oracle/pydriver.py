@@ -108,6 +108,17 @@ class Driver:
             fn.restype = res
             fn.argtypes = args
         self.kind = L.loamdrv_kind().decode()
+        if self.kind == "restatement":
+            # per-iteration hooks only the restatement offers (the reference classes cannot be paused mid-process)
+            _S = C.POINTER(C.c_int8)
+            L.loamorc_odom_iteration.restype = C.c_int
+            L.loamorc_odom_iteration.argtypes = [vp, C.c_int, _F, _F, _S, _F, _F]
+            L.loamorc_odom_set_last.restype = None
+            L.loamorc_odom_set_last.argtypes = [vp, _F, C.c_int, _F, C.c_int]
+            L.loamorc_map_set.restype = None
+            L.loamorc_map_set.argtypes = [vp, _F, C.c_int, _F, C.c_int, _F, C.c_int, _F, C.c_int]
+            L.loamorc_map_iteration.restype = C.c_int
+            L.loamorc_map_iteration.argtypes = [vp, _F, _F, _S, _F, _F]
 
     # ---- generic cloud getter
     def _cloud(self, size_fn, copy_fn, h, which):
@@ -272,6 +283,45 @@ class Mapping:
     def cloud(self, name):
         return self.d._cloud(self.d.L.loamdrv_map_cloud_size, self.d.L.loamdrv_map_cloud_copy, self.h,
                              self.NAMES[name])
+
+
+def map_iteration(drv, corner_map, surf_map, corner_q, surf_q, tobe6):
+    """One correspondence + normal-equation pass of the scan-to-map loop at pose tobe6 (restatement only)."""
+    m = drv.mapping()
+    a = [_pts(x) for x in (corner_map, surf_map, corner_q, surf_q)]
+    drv.L.loamorc_map_set(m.h, _fp(a[0]), a[0].shape[0], _fp(a[1]), a[1].shape[0], _fp(a[2]), a[2].shape[0], _fp(a[3]),
+                          a[3].shape[0])
+    nq = a[2].shape[0] + a[3].shape[0]
+    coeff = np.zeros((nq, 4), np.float32)
+    sel = np.zeros(nq, np.int8)
+    AtA = np.zeros((6, 6), np.float32)
+    AtB = np.zeros(6, np.float32)
+    t = np.ascontiguousarray(tobe6, dtype=np.float32)
+    n = drv.L.loamorc_map_iteration(m.h, _fp(t), _fp(coeff), sel.ctypes.data_as(C.POINTER(C.c_int8)), _fp(AtA), _fp(AtB))
+    return {"n_selected": n, "coeff": coeff, "selected": sel, "AtA": AtA, "AtB": AtB}
+
+
+class OdomIterator:
+    """Steps the scan-to-scan loop one iteration at a time (restatement only)."""
+
+    def __init__(self, drv, last_corner, last_surf, sharp, flat, scan_period=0.1):
+        self.d = drv
+        self.o = drv.odom(scan_period, 25)
+        lc, ls = _pts(last_corner), _pts(last_surf)
+        drv.L.loamorc_odom_set_last(self.o.h, _fp(lc), lc.shape[0], _fp(ls), ls.shape[0])
+        empty = np.zeros((0, 4), np.float32)
+        self.o.set_inputs(sharp, empty, flat, empty, empty)
+        self.nq = _pts(sharp).shape[0] + _pts(flat).shape[0]
+
+    def iterate(self, it, transform6):
+        coeff = np.zeros((self.nq, 4), np.float32)
+        sel = np.zeros(self.nq, np.int8)
+        AtA = np.zeros((6, 6), np.float32)
+        AtB = np.zeros(6, np.float32)
+        t = np.ascontiguousarray(transform6, dtype=np.float32)
+        n = self.d.L.loamorc_odom_iteration(self.o.h, it, _fp(t), _fp(coeff), sel.ctypes.data_as(C.POINTER(C.c_int8)),
+                                            _fp(AtA), _fp(AtB))
+        return {"n_selected": n, "coeff": coeff, "selected": sel, "AtA": AtA, "AtB": AtB}
 
 
 class Pipeline:
