@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- sweeps/sec of the scan-to-map cycle (registration -> odometry -> mapping) on synthetic ring-ordered
+sweeps, BASELINE.json's metric, at N GPUs of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W            # CUDA arm (this repo)
+    python bench.py --impl reference --gpus 1 ...            # the reference's own CPU implementation, same workload
+
+A "step" is one full pass of the hot path over one sweep.  The default workload is BASELINE config 3: HDL-64E
+64 x 2048 sweeps against a 1 M-point surrounding map.  One JSON line is printed by rank 0 (contract in the task
+statement): metric / value / e2e / roofline / cpu_baseline / clocks / gpu_launches.
+
+Multi-GPU (see DESIGN.md "Multi-GPU"): the path shards by map cubes / queries with one 36-float all-reduce per LM
+iteration; that mode is strong-scaling of a single stream and latency-bound, so the default N > 1 run is
+"replicas": every rank registers its own independent sweep stream against its own map (weak scaling, no data-path
+collective), which is how a fleet of sensors would use an 8-GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (lidar factory name, map points, description)
+    "vlp16_200k": ("vlp16", 200_000, "VLP-16 16x1800 sweeps, 200k-pt map (BASELINE config 2)"),
+    "hdl64_1m": ("hdl64", 1_000_000, "HDL-64E 64x2048 sweeps, 1M-pt surrounding map (BASELINE config 3)"),
+    "hdl64_10m": ("hdl64", 10_000_000, "HDL-64E 64x2048 sweeps, 10M-pt map (BASELINE config 4, single-GPU variant)"),
+}
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.gpu_index = gpu_index
+        self.t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_workload(name, n_sweeps, rank=0):
+    from loam_velodyne_b200 import synth
+    lidar_name, m, _ = WORKLOADS[name]
+    scene = synth.make_scene()
+    lidar = getattr(synth.Lidar, lidar_name)()
+    corner, surf = synth.make_map(scene, m)
+    # every rank drives its own stream: same world, different heading rate so the sweeps differ
+    yaw_rate = math.radians(5.0 + 0.5 * rank)
+    sweeps = [synth.make_sweep(scene, lidar, i, yaw_rate=yaw_rate) for i in range(n_sweeps)]
+    return lidar, corner, surf, sweeps
+
+
+def measure_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_cuda(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from loam_velodyne_b200 import api
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    api.set_device(local_rank)
+    n_total = args.warmup + args.steps
+    lidar, corner, surf, sweeps = make_workload(args.workload, n_total, rank)
+
+    pipe = api.Pipeline()
+    pipe.seed_map(corner, surf)
+    L = api.lib()
+    # kernel-family timing through the three contexts the drop-in classes own is reported by a dedicated pass below;
+    # the timed region itself runs without event brackets.
+    h2d = d2h = 0
+    for i in range(args.warmup):
+        pipe.sweep(*sweeps[i])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    stage = np.zeros(5)
+    iters_o = iters_m = 0
+    for i in range(args.warmup, n_total):
+        ok, odom, aft, st = pipe.sweep(*sweeps[i])
+        stage += st
+        iters_o += pipe.odom.last_iterations()
+        iters_m += pipe.mapping.last_iterations()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    elapsed = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = float(elapsed.item())
+    e2e_value = world * args.steps / elapsed
+
+    # ---- kernel-level pass (rank 0, N = 1 semantics): north-star kernel roofline through the kernel ABI
+    roof = None
+    value = e2e_value
+    launches = 0
+    if rank == 0:
+        roof, launches_per_sweep = kernel_roofline(args, api, corner, surf, sweeps[args.warmup], pipe)
+        launches = int(launches_per_sweep * args.steps)
+    out = None
+    if rank == 0:
+        n_pts = int(sweeps[0][0].shape[0])
+        h2d = n_pts * 16  # sweep upload (further intermediate copies are accounted in DESIGN.md, not claimed here)
+        d2h = 2 * 6 * 4
+        out = {
+            "metric": "sweeps/sec scan-to-map", "value": round(value, 3), "unit": "sweeps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * elapsed / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": n_pts,
+                       "map_points": int(corner.shape[0] + surf.shape[0]), "mode": "replicas" if world > 1 else "single",
+                       "l2_note": "inputs change every step (new sweep, rebuilt map BVH); 1M-pt map (16 MB) is L2-resident by construction",
+                       "odom_iters_per_sweep": round(iters_o / args.steps, 2), "map_iters_per_sweep": round(iters_m / args.steps, 2),
+                       "stage_ms": {k: round(1e3 * v / args.steps, 3) for k, v in zip(["registration", "odometry", "full_to_end", "mapping", "total"], stage)}},
+            "e2e": {"value": round(e2e_value, 3), "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, corner, surf, sweeps)
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def kernel_roofline(args, api, corner, surf, sweep, pipe):
+    """North-star kernel (fused 5-NN + fit + Jacobian + reduction = map_iterate_kernel) timed with CUDA events on its
+    own stream through the kernel ABI, on the same queries / map the pipeline uses."""
+    ctx = api.Ctx(int(os.environ.get("LOCAL_RANK", "0")))
+    cq = pipe.mapping.cloud("corner_stack_ds")
+    sq = pipe.mapping.cloud("surf_stack_ds")
+    cm = pipe.mapping.cloud("corner_from_map")
+    sm = pipe.mapping.cloud("surf_from_map")
+    twist = pipe.mapping.twist("aft")
+    ctx.tree_build(api.TREE_MAP_CORNER, cm)
+    ctx.tree_build(api.TREE_MAP_SURF, sm)
+    ctx.map_set_queries(cq, sq)
+    _, nodes, leaves = ctx.map_iterate_stats(twist)
+    nq = cq.shape[0] + sq.shape[0]
+    for _ in range(5):
+        ctx.map_iterate(twist)
+    ctx.profile(True)
+    reps = 50
+    for _ in range(reps):
+        ctx.map_iterate(twist)
+    ms, n = ctx.profile_get()["map_iter"]
+    ctx.profile(False)
+    # algorithmic bytes per launch: Q * 16 + nodes * 64 + leaves * LEAF(8) * 16 + 36 * 4
+    alg_bytes = nq * 16 + nodes * 64 + leaves * 8 * 16 + 36 * 4
+    dur_s = ms / n * 1e-3
+    peak, how = measure_peaks()
+    achieved = alg_bytes / dur_s / 1e9
+    # launches per sweep of the whole pipeline: count through a separate profiled pipeline pass is not possible from
+    # here (three private contexts); the kernel ABI context exposes its own launch counter instead
+    launches_per_sweep = estimate_launches(api, pipe)
+    ctx.close()
+    return ({"bound": "hbm", "kernel": "map_iterate_kernel (fused 5-NN walk + line/plane fit + Jacobian + 6x6 reduction)",
+             "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+             "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes),
+             "avg_launch_us": round(dur_s * 1e6, 2), "queries": int(nq), "nodes_per_query": round(nodes / max(nq, 1), 2),
+             "leaves_per_query": round(leaves / max(nq, 1), 2),
+             "note": "1M-pt map + nodes fit in the 126 MB L2, so DRAM traffic is structurally far below the algorithmic bytes"},
+            launches_per_sweep)
+
+
+def estimate_launches(api, pipe):
+    """Kernels launched per sweep: 2 (features) + trees (4 builds x ~19) + iterations + transforms + voxel calls."""
+    it_o = max(pipe.odom.last_iterations(), 1)
+    it_m = max(pipe.mapping.last_iterations(), 1)
+    per_tree = 3 + 4 * 3 + 4
+    return 2 + 4 * per_tree + it_o + it_m + 4
+
+
+def cpu_baseline(args, corner, surf, sweeps):
+    """The reference's CPU path (compiled reference when oracle/_ref travelled, else the restatement), -O3 build,
+    one thread (every reference node is single-threaded), on a bounded sample of the same workload."""
+    from oracle import pydriver
+    drv = pydriver.best(fast=True)
+    pipe = drv.pipeline()
+    pipe.seed_map(corner, surf)
+    n = min(len(sweeps), 2 + args.cpu_sweeps)
+    times = []
+    stage = np.zeros(5)
+    for i in range(n):
+        ok, _, _, st = pipe.sweep(*sweeps[i])
+        if i >= 2:
+            times.append(st[4])
+            stage += st
+    v = len(times) / sum(times)
+    return {"value": round(v, 3), "unit": "sweeps/s", "cores": 1, "host_cores_available": os.cpu_count(),
+            "kind": "reference" if drv.kind == "reference" else "port",
+            "sample": f"{len(times)} sweeps of the same workload after 2 warm-up sweeps, wall time inside the C++ pipeline driver",
+            "stage_ms": {k: round(1e3 * s / len(times), 2) for k, s in zip(["registration", "odometry", "full_to_end", "mapping", "total"], stage)}}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
+    if rank != 0:
+        return None
+    from oracle import pydriver
+    drv = pydriver.best(fast=True)
+    n_total = args.warmup + args.steps
+    lidar, corner, surf, sweeps = make_workload(args.workload, n_total, 0)
+    pipe = drv.pipeline()
+    pipe.seed_map(corner, surf)
+    for i in range(args.warmup):
+        pipe.sweep(*sweeps[i])
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_total):
+        pipe.sweep(*sweeps[i])
+    el = time.perf_counter() - t0
+    v = args.steps / el
+    kind = "reference" if drv.kind == "reference" else "port"
+    return {"impl": "reference", "metric": "sweeps/sec scan-to-map", "value": round(v, 3), "unit": "sweeps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * el / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": int(sweeps[0][0].shape[0]),
+                       "map_points": int(corner.shape[0] + surf.shape[0])},
+            "cpu_baseline": {"value": round(v, 3), "unit": "sweeps/s", "cores": 1, "kind": kind,
+                             "sample": f"{args.steps} sweeps, single thread (the reference nodes are single-threaded), "
+                                       f"{os.cpu_count()} host cores present"},
+            "e2e": {"value": round(v, 3), "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="hdl64_1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sweeps", type=int, default=12, help="sweeps timed for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank, world, local_rank = rank_world()
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40  # bounded sample: ~0.3 s per sweep on one core
+        out = run_reference(args, rank, world)
+    else:
+        import __graft_entry__ as ge
+        if rank == 0:
+            ge.build()
+        out = run_cuda(args, rank, world, local_rank)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,11 @@ int loam_b200_map_iterate(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b
 int loam_b200_map_iterate_debug(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b200_normal_eq* out,
                                 float* coeff, int8_t* selected);
 
+/* instrumented variant: same result plus the number of BVH nodes / leaves the 5-NN walks visited in this launch
+ * (feeds the algorithmic-bytes figure of the roofline); slower, never used on the timed path */
+int loam_b200_map_iterate_stats(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b200_normal_eq* out,
+                                unsigned long long* nodes_visited, unsigned long long* leaves_visited);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Scan-to-scan Gauss-Newton iteration: replaces the body of the iteration loop of BasicLaserOdometry::process up to
  * AtA / AtB (BasicLaserOdometry.cpp:246-557: transformToStart, 1-NN + adjacent-ring search every 5th iteration,

@@ -93,6 +93,8 @@ def lib():
         "loam_b200_map_set_queries": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
         "loam_b200_map_iterate": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(NormalEq)]),
         "loam_b200_map_iterate_debug": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(NormalEq), _F, _B]),
+        "loam_b200_map_iterate_stats": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(NormalEq), C.POINTER(C.c_ulonglong),
+                                          C.POINTER(C.c_ulonglong)]),
         "loam_b200_odom_set_last": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
         "loam_b200_odom_set_current": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
         "loam_b200_odom_iterate": (C.c_int, [vp, C.POINTER(OdomPose), C.POINTER(NormalEq)]),
@@ -270,6 +272,16 @@ class Ctx:
             return _ne(ne), coeff, sel
         self._ck(self.L.loam_b200_map_iterate(self.h, C.byref(p), C.byref(ne)), "map_iterate")
         return _ne(ne)
+
+    def map_iterate_stats(self, twist6):
+        """(normal equations, BVH nodes visited, leaves visited) of one instrumented launch."""
+        p = make_pose(twist6)
+        ne = NormalEq()
+        nodes = C.c_ulonglong(0)
+        leaves = C.c_ulonglong(0)
+        self._ck(self.L.loam_b200_map_iterate_stats(self.h, C.byref(p), C.byref(ne), C.byref(nodes), C.byref(leaves)),
+                 "map_iterate_stats")
+        return _ne(ne), nodes.value, leaves.value
 
     def odom_set_last(self, corner, surf):
         c, s = _pts(corner), _pts(surf)

@@ -131,6 +131,7 @@ struct loam_b200_ctx {
   loamb::DevBuf<float> partials;   // per-block partial normal equations
   loamb::DevBuf<float> result;     // 36 floats
   loamb::DevBuf<unsigned int> ticket;
+  loamb::DevBuf<unsigned long long> walk_totals;
   loamb::DevBuf<float4> dbg_coeff;
   loamb::DevBuf<int8_t> dbg_sel;
   loamb::PinBuf<float> result_host;

@@ -315,9 +315,11 @@ __device__ __forceinline__ float box_d2(float qx, float qy, float qz, const floa
 }
 
 // Exact K nearest with d2 < max_d2.  Results ascending; unfilled slots keep idx = -1, d2 = max_d2 sentinel.
-template <int K>
+// STATS = true additionally counts visited internal nodes / leaves (walk_stats[0], walk_stats[1]) for the roofline's
+// algorithmic-bytes figure (Q * [16 + D*64 + V*L*16]).
+template <int K, bool STATS = false>
 __device__ __forceinline__ void knn_walk(const TreeView& t, float qx, float qy, float qz, float max_d2,
-                                         KnnResult<K>& r) {
+                                         KnnResult<K>& r, unsigned* walk_stats = nullptr) {
 #pragma unroll
   for (int i = 0; i < K; i++) { r.d2[i] = max_d2; r.idx[i] = -1; r.x[i] = 0.f; r.y[i] = 0.f; r.z[i] = 0.f; }
   if (t.m <= 0) return;
@@ -327,6 +329,7 @@ __device__ __forceinline__ void knn_walk(const TreeView& t, float qx, float qy, 
   int node = t.root;
   while (true) {
     if (node < 0) {
+      if (STATS) walk_stats[1]++;
       const int leaf = ~node;
       const int b = leaf * LEAF_SIZE;
       const int cnt = min(LEAF_SIZE, t.m - b);
@@ -353,6 +356,7 @@ __device__ __forceinline__ void knn_walk(const TreeView& t, float qx, float qy, 
         }
       }
     } else {
+      if (STATS) walk_stats[0]++;
       const BvhNode* nd = t.nodes + node;
       const float4 lo0 = __ldg(&nd->lo0), hi0 = __ldg(&nd->hi0), lo1 = __ldg(&nd->lo1), hi1 = __ldg(&nd->hi1);
       const float d0 = box_d2(qx, qy, qz, lo0, hi0), d1 = box_d2(qx, qy, qz, lo1, hi1);

@@ -257,7 +257,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   c->sort.keys_a.release(); c->sort.keys_b.release(); c->sort.vals_a.release(); c->sort.vals_b.release();
   c->sort.hist.release();
   c->bbox.release(); c->knn_q.release(); c->knn_idx.release(); c->knn_d2.release();
-  c->map_q.release(); c->partials.release(); c->result.release(); c->ticket.release(); c->dbg_coeff.release();
+  c->map_q.release(); c->partials.release(); c->result.release(); c->ticket.release(); c->walk_totals.release(); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -434,7 +434,7 @@ int loam_b200_map_set_queries(loam_b200_ctx* c, const float* corner, int n_corne
 }
 
 static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b200_normal_eq* out, float* coeff,
-                            int8_t* selected) {
+                            int8_t* selected, unsigned long long* walk_totals_host = nullptr) {
   CHECK_CTX(c);
   if (!pose || !out) return LOAM_B200_ERR_ARG;
   const int nc = c->map_nc, ns = c->map_ns;
@@ -450,13 +450,24 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     LB_CUDA(c, c->dbg_coeff.reserve(nc + ns));
     LB_CUDA(c, c->dbg_sel.reserve(nc + ns));
   }
-  prof_begin(c, LOAM_B200_K_MAP_ITER);
-  map_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(c->tree[LOAM_B200_TREE_MAP_CORNER]),
-                                                       view_of(c->tree[LOAM_B200_TREE_MAP_SURF]), c->map_q.p, nc, ns,
-                                                       cb, a, c->partials.p, c->result.p, c->ticket.p,
-                                                       dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr);
-  LB_LAUNCH_CHECK(c);
-  prof_end(c);
+  if (walk_totals_host) {
+    LB_CUDA(c, c->walk_totals.reserve(2));
+    LB_CUDA(c, cudaMemsetAsync(c->walk_totals.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    map_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(
+        view_of(c->tree[LOAM_B200_TREE_MAP_CORNER]), view_of(c->tree[LOAM_B200_TREE_MAP_SURF]), c->map_q.p, nc, ns, cb,
+        a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
+    LB_LAUNCH_CHECK(c);
+    LB_CUDA(c, cudaMemcpyAsync(walk_totals_host, c->walk_totals.p, 2 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    prof_begin(c, LOAM_B200_K_MAP_ITER);
+    map_iterate_kernel<false><<<nb, LM_THREADS, 0, c->stream>>>(
+        view_of(c->tree[LOAM_B200_TREE_MAP_CORNER]), view_of(c->tree[LOAM_B200_TREE_MAP_SURF]), c->map_q.p, nc, ns, cb,
+        a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
+        nullptr);
+    LB_LAUNCH_CHECK(c);
+    prof_end(c);
+  }
   int rc = fetch_normal_eq(c, out);
   if (rc) return rc;
   if (dbg) {
@@ -475,6 +486,15 @@ int loam_b200_map_iterate_debug(loam_b200_ctx* c, const loam_b200_pose* pose, lo
                                 int8_t* selected) {
   if (!coeff) return LOAM_B200_ERR_ARG;
   return map_iterate_impl(c, pose, out, coeff, selected);
+}
+int loam_b200_map_iterate_stats(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b200_normal_eq* out,
+                                unsigned long long* nodes_visited, unsigned long long* leaves_visited) {
+  if (!nodes_visited || !leaves_visited) return LOAM_B200_ERR_ARG;
+  unsigned long long tot[2] = {0, 0};
+  int rc = map_iterate_impl(c, pose, out, nullptr, nullptr, tot);
+  *nodes_visited = tot[0];
+  *leaves_visited = tot[1];
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ odometry

@@ -158,11 +158,12 @@ __device__ __forceinline__ void reduce_normal_equations(float* acc, float* __res
   }
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(LM_THREADS)
 map_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ queries, int n_corner,
                    int n_surf, int corner_blocks, MapIterArgs a, float* __restrict__ partials,
                    float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
-                   int8_t* __restrict__ dbg_sel) {
+                   int8_t* __restrict__ dbg_sel, unsigned long long* __restrict__ walk_totals) {
   float acc[29];
 #pragma unroll
   for (int k = 0; k < 29; k++) acc[k] = 0.f;
@@ -177,7 +178,12 @@ map_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
     float sx, sy, sz;
     associate_to_map(a, po, sx, sy, sz);
     KnnResult<5> nn;
-    knn_walk<5>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 1.0f, nn);
+    unsigned ws[2] = {0u, 0u};
+    knn_walk<5, STATS>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 1.0f, nn, ws);
+    if (STATS) {
+      atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
+      atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
+    }
     float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool sel = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
     if (dbg_coeff) {
