@@ -167,6 +167,72 @@ int loam_b200_transform_to_map(loam_b200_ctx* ctx, float* pts, int n, const loam
 int loam_b200_voxel_grid(loam_b200_ctx* ctx, const float* pts, int n, float leaf, float* out, int cap, int* n_out);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Device-resident stage API.  The Basic* drop-in classes keep their clouds in HBM between calls and only
+ * materialise a pcl::PointCloud on the host when an accessor is used; these are the entry points they call.  Clouds
+ * live in numbered slots of a context; each class owns a disjoint range of slots.
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum {
+  /* BasicScanRegistration outputs (BasicScanRegistration.h:156-163) */
+  LOAM_B200_C_REG_FULL = 0, LOAM_B200_C_REG_SHARP, LOAM_B200_C_REG_LESS_SHARP, LOAM_B200_C_REG_FLAT, LOAM_B200_C_REG_LESS_FLAT,
+  /* BasicLaserOdometry inputs / outputs (BasicLaserOdometry.h:22-31) */
+  LOAM_B200_C_ODOM_SHARP, LOAM_B200_C_ODOM_LESS_SHARP, LOAM_B200_C_ODOM_FLAT, LOAM_B200_C_ODOM_LESS_FLAT, LOAM_B200_C_ODOM_FULL,
+  LOAM_B200_C_ODOM_LAST_CORNER, LOAM_B200_C_ODOM_LAST_SURF,
+  /* BasicLaserMapping inputs / internals / outputs (BasicLaserMapping.h:88-90,150-162) */
+  LOAM_B200_C_MAP_CORNER_LAST, LOAM_B200_C_MAP_SURF_LAST, LOAM_B200_C_MAP_FULL, LOAM_B200_C_MAP_CORNER_STACK_DS,
+  LOAM_B200_C_MAP_SURF_STACK_DS, LOAM_B200_C_MAP_CORNER_FROM_MAP, LOAM_B200_C_MAP_SURF_FROM_MAP, LOAM_B200_C_MAP_SURROUND_DS,
+  LOAM_B200_C_MAP_CORNER_POOL, LOAM_B200_C_MAP_SURF_POOL,
+  LOAM_B200_NUM_CLOUDS
+};
+
+int loam_b200_cloud_upload(loam_b200_ctx* ctx, int slot, const float* pts, int n);
+/* d_pts: DEVICE pointer to n packed points (e.g. a torch tensor); device-to-device copy on the context's stream */
+int loam_b200_cloud_upload_device(loam_b200_ctx* ctx, int slot, const void* d_pts, int n);
+int loam_b200_cloud_download(loam_b200_ctx* ctx, int slot, float* out, int cap, int* n_out);
+int loam_b200_cloud_size(loam_b200_ctx* ctx, int slot);
+int loam_b200_cloud_swap(loam_b200_ctx* ctx, int slot_a, int slot_b);
+/* copy a cloud between slots, possibly of two different contexts on the same device (stream-ordered, no host hop) */
+int loam_b200_cloud_copy(loam_b200_ctx* dst_ctx, int dst_slot, loam_b200_ctx* src_ctx, int src_slot);
+
+/* Scan registration on the cloud in LOAM_B200_C_REG_FULL (already uploaded): fills the REG_SHARP / LESS_SHARP / FLAT /
+ * LESS_FLAT slots; counts_out[4] = their sizes.  Index lists and labels of this sweep stay readable until the next run. */
+int loam_b200_reg_run(loam_b200_ctx* ctx, const int32_t* ring_start, const int32_t* ring_end, int n_rings,
+                      const loam_b200_reg_params* params, int counts_out[4]);
+/* which: 1 sharp, 2 less sharp, 3 flat */
+int loam_b200_reg_indices(loam_b200_ctx* ctx, int which, int32_t* out, int cap, int* n_out);
+int loam_b200_reg_labels(loam_b200_ctx* ctx, int8_t* out, int n);
+
+/* Odometry stage on the ODOM_* slots: prepare = take ODOM_SHARP + ODOM_FLAT as this sweep's queries;
+ * rebuild_last = BVHs over ODOM_LAST_CORNER / ODOM_LAST_SURF (setInputCloud, BasicLaserOdometry.cpp:203-204,662-663);
+ * loam_b200_odom_iterate (above) then works on them. */
+int loam_b200_odom_prepare(loam_b200_ctx* ctx);
+int loam_b200_odom_rebuild_last(loam_b200_ctx* ctx);
+/* transformToEnd / pointAssociateToMap in place on a device cloud */
+int loam_b200_cloud_transform_to_end(loam_b200_ctx* ctx, int slot, const loam_b200_odom_pose* pose);
+int loam_b200_cloud_transform_to_map(loam_b200_ctx* ctx, int slot, const loam_b200_pose* pose);
+
+/* Mapping stage.  The surrounding map is a flat point pool per kind (MAP_CORNER_POOL / MAP_SURF_POOL); the 21x11x21
+ * cube grid of the reference is implicit (a point's cube follows from its position and the grid centre). */
+typedef struct {
+  int cen[3];                 /* _laserCloudCenWidth / Height / Depth after rolling (BasicLaserMapping.cpp:311-441) */
+  const int32_t* valid_cubes; /* _laserCloudValidInd, cube index i + 21 j + 231 k (BasicLaserMapping.h:126-127) */
+  int n_valid;                /* <= 125 */
+  float corner_leaf, surf_leaf;
+} loam_b200_map_window;
+
+/* append points (map frame) to the pool of kind 0 corner / 1 surface */
+int loam_b200_map_pool_append(loam_b200_ctx* ctx, int kind, const float* pts, int n);
+/* stacks: MAP_CORNER_LAST / MAP_SURF_LAST -> to map -> back to sensor (predicted pose) -> VoxelGrid -> *_STACK_DS;
+ * from-map clouds: pool points in valid cubes -> *_FROM_MAP + BVHs; queries set for loam_b200_map_iterate.
+ * sizes_out[4] = corner_from_map, surf_from_map, corner_stack_ds, surf_stack_ds */
+int loam_b200_map_begin_sweep(loam_b200_ctx* ctx, const loam_b200_pose* predicted, const loam_b200_map_window* win,
+                              int sizes_out[4]);
+/* insert the stack points with the optimised pose, voxel-filter every valid cube (BasicLaserMapping.cpp:536-593) and
+ * move MAP_FULL into the map frame (:595) */
+int loam_b200_map_end_sweep(loam_b200_ctx* ctx, const loam_b200_pose* optimised);
+/* createDownsizedMap (:242-264): VoxelGrid(leaf) over the corner + surface points of the surround cubes -> MAP_SURROUND_DS */
+int loam_b200_map_surround(loam_b200_ctx* ctx, const int cen[3], const int32_t* surround_cubes, int n, float leaf);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Kernel timing (CUDA events on the context's stream) for bench.py's roofline: accumulated GPU milliseconds and
  * launch counts per kernel family since the last reset.
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -1,5 +1,5 @@
 /* loam_b200_host.h -- C handles over the C++ drop-in classes loam::BasicScanRegistration / BasicLaserOdometry /
- * BasicLaserMapping (loam_velodyne_b200/csrc/host/loam_velodyne/*.h), for callers that cannot include C++ headers
+ * BasicLaserMapping (the headers under loam_velodyne_b200/csrc/host/loam_velodyne/), for callers that cannot include C++ headers
  * (the Python package, bench.py, ctypes tests).  C++ callers -- including the reference's ROS adapters, which derive
  * from the Basic* classes (ScanRegistration.h:55, LaserOdometry.h:56, LaserMapping.h:54 upstream) -- use the classes
  * directly.
@@ -71,6 +71,13 @@ int loam_b200_pipeline_seed_map(void* h, const float* corner, int n_corner, cons
 /* stage_seconds[5]: registration, odometry, full->end, mapping, total (steady_clock, host wall time) */
 int loam_b200_pipeline_sweep(void* h, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
                              float* map_aft6, double* stage_seconds);
+/* same, the sweep already resident in GPU memory (d_pts: device pointer to the packed points) */
+int loam_b200_pipeline_sweep_device(void* h, const void* d_pts, const int* ring_sizes, int n_rings, float* odom_sum6,
+                                    float* map_aft6, double* stage_seconds);
+/* same chain, but every hand-off goes through host pcl clouds and the reference's own entry points
+ * (processScanlines(vector<PointCloud>) / cloud Ptr accessors), as separate ROS nodes would use the classes */
+int loam_b200_pipeline_sweep_hostclouds(void* h, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
+                                        float* map_aft6, double* stage_seconds);
 void* loam_b200_pipeline_scanreg(void* h);
 void* loam_b200_pipeline_odom(void* h);
 void* loam_b200_pipeline_map(void* h);

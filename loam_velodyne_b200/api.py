@@ -60,6 +60,11 @@ class NormalEq(C.Structure):
                 ("n_corner_selected", C.c_int)]
 
 
+class MapWindow(C.Structure):
+    _fields_ = [("cen", C.c_int * 3), ("valid_cubes", _I), ("n_valid", C.c_int), ("corner_leaf", C.c_float),
+                ("surf_leaf", C.c_float)]
+
+
 TREE_ODOM_CORNER, TREE_ODOM_SURF, TREE_MAP_CORNER, TREE_MAP_SURF = range(4)
 K_FEATURES, K_TREE_BUILD, K_KNN, K_MAP_ITER, K_ODOM_ITER, K_TRANSFORM, K_VOXEL = range(7)
 KERNEL_FAMILIES = ["features", "tree_build", "knn", "map_iter", "odom_iter", "transform", "voxel"]
@@ -102,6 +107,23 @@ def lib():
         "loam_b200_transform_to_end": (C.c_int, [vp, _F, C.c_int, C.POINTER(OdomPose)]),
         "loam_b200_transform_to_map": (C.c_int, [vp, _F, C.c_int, C.POINTER(Pose)]),
         "loam_b200_voxel_grid": (C.c_int, [vp, _F, C.c_int, C.c_float, _F, C.c_int, _I]),
+        "loam_b200_cloud_upload": (C.c_int, [vp, C.c_int, _F, C.c_int]),
+        "loam_b200_cloud_upload_device": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "loam_b200_cloud_download": (C.c_int, [vp, C.c_int, _F, C.c_int, _I]),
+        "loam_b200_cloud_size": (C.c_int, [vp, C.c_int]),
+        "loam_b200_cloud_swap": (C.c_int, [vp, C.c_int, C.c_int]),
+        "loam_b200_cloud_copy": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "loam_b200_reg_run": (C.c_int, [vp, _I, _I, C.c_int, C.POINTER(RegParams), _I]),
+        "loam_b200_reg_indices": (C.c_int, [vp, C.c_int, _I, C.c_int, _I]),
+        "loam_b200_reg_labels": (C.c_int, [vp, _B, C.c_int]),
+        "loam_b200_odom_prepare": (C.c_int, [vp]),
+        "loam_b200_odom_rebuild_last": (C.c_int, [vp]),
+        "loam_b200_cloud_transform_to_end": (C.c_int, [vp, C.c_int, C.POINTER(OdomPose)]),
+        "loam_b200_cloud_transform_to_map": (C.c_int, [vp, C.c_int, C.POINTER(Pose)]),
+        "loam_b200_map_pool_append": (C.c_int, [vp, C.c_int, _F, C.c_int]),
+        "loam_b200_map_begin_sweep": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(MapWindow), _I]),
+        "loam_b200_map_end_sweep": (C.c_int, [vp, C.POINTER(Pose)]),
+        "loam_b200_map_surround": (C.c_int, [vp, _I, _I, C.c_int, C.c_float]),
         "loam_b200_profile_enable": (C.c_int, [vp, C.c_int]),
         "loam_b200_profile_reset": (C.c_int, [vp]),
         "loam_b200_profile_get": (C.c_int, [vp, C.c_int, _D, C.POINTER(C.c_longlong)]),
@@ -140,6 +162,8 @@ def lib():
         "loam_b200_pipeline_destroy": (None, [vp]),
         "loam_b200_pipeline_seed_map": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
         "loam_b200_pipeline_sweep": (C.c_int, [vp, _F, _I, C.c_int, _F, _F, _D]),
+        "loam_b200_pipeline_sweep_device": (C.c_int, [vp, vp, _I, C.c_int, _F, _F, _D]),
+        "loam_b200_pipeline_sweep_hostclouds": (C.c_int, [vp, _F, _I, C.c_int, _F, _F, _D]),
         "loam_b200_pipeline_scanreg": (vp, [vp]),
         "loam_b200_pipeline_odom": (vp, [vp]),
         "loam_b200_pipeline_map": (vp, [vp]),
@@ -499,14 +523,28 @@ class Pipeline(_Handle):
         c, s = _pts(corner), _pts(surf)
         self._ck(self.L.loam_b200_pipeline_seed_map(self.h, _fp(c), c.shape[0], _fp(s), s.shape[0]), "seed_map")
 
-    def sweep(self, pts, ring_sizes):
+    def sweep(self, pts, ring_sizes, mode="fused"):
+        """mode "fused": clouds stay in HBM between the three stages; "hostclouds": every hand-off goes through the
+        reference's own entry points and host pcl clouds (as separate ROS nodes would use the classes)."""
         pts = _pts(pts)
         rs = np.ascontiguousarray(ring_sizes, dtype=np.int32)
         odom = np.empty(6, np.float32)
         aft = np.empty(6, np.float32)
         st = np.zeros(5, np.float64)
-        ok = self._ck(self.L.loam_b200_pipeline_sweep(self.h, _fp(pts), _ip(rs), rs.shape[0], _fp(odom), _fp(aft),
-                                                      st.ctypes.data_as(_D)), "pipeline_sweep")
+        fn = self.L.loam_b200_pipeline_sweep if mode == "fused" else self.L.loam_b200_pipeline_sweep_hostclouds
+        ok = self._ck(fn(self.h, _fp(pts), _ip(rs), rs.shape[0], _fp(odom), _fp(aft), st.ctypes.data_as(_D)),
+                      "pipeline_sweep")
+        return bool(ok), odom, aft, st
+
+    def sweep_device(self, device_ptr, ring_sizes):
+        """Sweep already resident in GPU memory (device_ptr: address of n x 4 float32, e.g. tensor.data_ptr())."""
+        rs = np.ascontiguousarray(ring_sizes, dtype=np.int32)
+        odom = np.empty(6, np.float32)
+        aft = np.empty(6, np.float32)
+        st = np.zeros(5, np.float64)
+        ok = self._ck(self.L.loam_b200_pipeline_sweep_device(self.h, C.c_void_p(device_ptr), _ip(rs), rs.shape[0],
+                                                             _fp(odom), _fp(aft), st.ctypes.data_as(_D)),
+                      "pipeline_sweep_device")
         return bool(ok), odom, aft, st
 
 

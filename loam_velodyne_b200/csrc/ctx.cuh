@@ -32,6 +32,24 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
+  // grow while preserving the first `keep` elements (stream-ordered device copy)
+  cudaError_t reserve_keep(size_t n, size_t keep, cudaStream_t st) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = cap ? cap : 256;
+    while (want < n) want = want + want / 2 + 256;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) {
+      e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) { cudaFree(q); return e; }
+      cudaStreamSynchronize(st);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -75,7 +93,9 @@ struct Tree {
   int m = 0;        // points
   int n_leaf = 0;   // leaves (LEAF_SIZE consecutive Morton-sorted points each)
   int root = 0;     // root link (>= 0 internal node, < 0 leaf)
-  DevBuf<float4> pts;      // original order (xyz, intensity)
+  DevBuf<float4> pts;      // original order (xyz, intensity) when the tree owns its points
+  const float4* ext_pts = nullptr;  // ... or a cloud slot's buffer (device-resident stage API)
+  const float4* points() const { return ext_pts ? ext_pts : pts.p; }
   DevBuf<float4> sorted;   // Morton order (xyz, original index as int bits)
   DevBuf<BvhNode> nodes;   // n_leaf - 1 internal nodes
   DevBuf<uint32_t> leaf_key;
@@ -83,6 +103,9 @@ struct Tree {
   DevBuf<int> flags;
   DevBuf<float4> box_lo, box_hi;  // per-node total boxes during refit (internal then leaves)
 };
+
+struct FeatSlots { int cap_sharp = 0, cap_less = 0, cap_flat = 0; };
+struct CubeGridHost { int cen_w = 10, cen_h = 5, cen_d = 10; };
 
 struct SortScratch {
   DevBuf<uint32_t> keys_a, keys_b;
@@ -141,6 +164,23 @@ struct loam_b200_ctx {
   int od_nsharp = 0, od_nflat = 0;
   loamb::DevBuf<int> od_ind;   // (n_sharp + n_flat) x 3 persisted correspondence indices
   bool od_last_set = false;
+
+  // device-resident clouds of the stage API
+  loamb::DevBuf<float4> cloud[LOAM_B200_NUM_CLOUDS];
+  int cloud_n[LOAM_B200_NUM_CLOUDS] = {0};
+  int reg_totals[4] = {0, 0, 0, 0};
+  int reg_n_rings = 0, reg_n = 0;
+  loamb::FeatSlots reg_slots;
+  // map pools: class per point, cube tables, scratch
+  loamb::DevBuf<unsigned char> pool_cls[2];
+  loamb::DevBuf<unsigned char> rank_of_cube;
+  loamb::DevBuf<float4> pool_tmp;
+  loamb::DevBuf<unsigned char> pool_tmp_cls;
+  loamb::DevBuf<unsigned> cmp_pos, cmp_bsum;
+  loamb::CubeGridHost map_grid;
+  int map_n_valid = 0;
+  float map_leaf[2] = {0.2f, 0.4f};
+  cudaEvent_t ev_xfer = nullptr;
 
   // generic scratch
   loamb::DevBuf<float4> tmp_pts;

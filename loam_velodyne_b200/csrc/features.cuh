@@ -361,33 +361,52 @@ feature_ring_kernel(const float4* __restrict__ pts, const int* __restrict__ ring
   (void)s_misc;
 }
 
-// pack per-ring results densely: picks (three lists) and the less-flat DS cloud, ring-major
-__global__ void feature_pack_kernel(const int* __restrict__ counts, const int* __restrict__ picks,
-                                    const int* __restrict__ ring_start, const float4* __restrict__ lessflat_slots,
-                                    int n_rings, FeatParams prm, int* __restrict__ sharp, int* __restrict__ less,
-                                    int* __restrict__ flat, float4* __restrict__ lessflat, int* __restrict__ totals) {
-  __shared__ int off[4][257];
-  const int tid = threadIdx.x;
-  if (tid < 4) {
-    int acc = 0;
-    for (int r = 0; r < n_rings; r++) {
-      off[tid][r] = acc;
-      acc += counts[r * 4 + tid];
+// pack per-ring results densely, one CTA per ring: three pick lists (indices + gathered points) and the less-flat DS
+// cloud, ring-major.  Offsets are exclusive sums of the per-ring counts (R <= 256, one block-wide reduction each).
+__global__ void __launch_bounds__(256)
+feature_pack_kernel(const int* __restrict__ counts, const int* __restrict__ picks, const int* __restrict__ ring_start,
+                    const float4* __restrict__ pts, const float4* __restrict__ lessflat_slots, int n_rings,
+                    FeatParams prm, int* __restrict__ sharp, int* __restrict__ less, int* __restrict__ flat,
+                    float4* __restrict__ sharp_pts, float4* __restrict__ less_pts, float4* __restrict__ flat_pts,
+                    float4* __restrict__ lessflat, int* __restrict__ totals) {
+  __shared__ int s_off[4], s_tot[4];
+  __shared__ int s_w[8][8];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int before[4] = {0, 0, 0, 0}, all[4] = {0, 0, 0, 0};
+  if (tid < n_rings) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = counts[tid * 4 + k];
+      all[k] = c;
+      before[k] = tid < r ? c : 0;
     }
-    off[tid][n_rings] = acc;
-    totals[tid] = acc;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int b = before[k], a = all[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    if (lane == 0) { s_w[warp][k] = b; s_w[warp][4 + k] = a; }
+  }
+  __syncthreads();
+  if (tid < 4) {
+    int b = 0, a = 0;
+    for (int w = 0; w < 8; w++) { b += s_w[w][tid]; a += s_w[w][4 + tid]; }
+    s_off[tid] = b;
+    s_tot[tid] = a;
+    if (r == 0) totals[tid] = a;
   }
   __syncthreads();
   const int slots = prm.cap_sharp + prm.cap_less + prm.cap_flat;
-  for (int r = 0; r < n_rings; r++) {
-    const int* pk = picks + (size_t)r * slots;
-    const int ns = counts[r * 4 + 0], nl = counts[r * 4 + 1], nf = counts[r * 4 + 2], nd = counts[r * 4 + 3];
-    for (int i = tid; i < ns; i += blockDim.x) sharp[off[0][r] + i] = pk[i];
-    for (int i = tid; i < nl; i += blockDim.x) less[off[1][r] + i] = pk[prm.cap_sharp + i];
-    for (int i = tid; i < nf; i += blockDim.x) flat[off[2][r] + i] = pk[prm.cap_sharp + prm.cap_less + i];
-    const float4* src = lessflat_slots + ring_start[r];
-    for (int i = tid; i < nd; i += blockDim.x) lessflat[off[3][r] + i] = src[i];
-  }
+  const int* pk = picks + (size_t)r * slots;
+  const int ns = counts[r * 4 + 0], nl = counts[r * 4 + 1], nf = counts[r * 4 + 2], nd = counts[r * 4 + 3];
+  for (int i = tid; i < ns; i += blockDim.x) { const int ix = pk[i]; sharp[s_off[0] + i] = ix; sharp_pts[s_off[0] + i] = pts[ix]; }
+  for (int i = tid; i < nl; i += blockDim.x) { const int ix = pk[prm.cap_sharp + i]; less[s_off[1] + i] = ix; less_pts[s_off[1] + i] = pts[ix]; }
+  for (int i = tid; i < nf; i += blockDim.x) { const int ix = pk[prm.cap_sharp + prm.cap_less + i]; flat[s_off[2] + i] = ix; flat_pts[s_off[2] + i] = pts[ix]; }
+  const float4* src = lessflat_slots + ring_start[r];
+  for (int i = tid; i < nd; i += blockDim.x) lessflat[s_off[3] + i] = src[i];
 }
 
 }  // namespace loamb

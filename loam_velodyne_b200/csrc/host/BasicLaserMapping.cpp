@@ -9,40 +9,57 @@
 
 #include "b200_runtime.h"
 #include "host_math.h"
+#include "loam_velodyne/BasicLaserOdometry.h"
 
 namespace loam {
 
 using hostmath::rad2deg;
+
+enum { M_CORNER_LAST = 0, M_SURF_LAST, M_FULL, M_CORNER_STACK_DS, M_SURF_STACK_DS, M_CORNER_FROM_MAP, M_SURF_FROM_MAP,
+       M_SURROUND_DS, M_NUM };
 
 BasicLaserMapping::BasicLaserMapping(const float& scanPeriod, const size_t& maxIterations)
     : _scanPeriod(scanPeriod), _stackFrameNum(1), _mapFrameNum(5), _frameCount(0), _mapFrameCount(0),
       _maxIterations(maxIterations), _deltaTAbort(0.05), _deltaRAbort(0.05), _laserCloudCenWidth(10),
       _laserCloudCenHeight(5), _laserCloudCenDepth(10), _laserCloudWidth(21), _laserCloudHeight(11),
       _laserCloudDepth(21), _laserCloudNum(_laserCloudWidth * _laserCloudHeight * _laserCloudDepth),
-      _laserCloudCornerLast(new Cloud()), _laserCloudSurfLast(new Cloud()), _laserCloudFullRes(new Cloud()),
-      _laserCloudCornerStack(new Cloud()), _laserCloudSurfStack(new Cloud()), _laserCloudCornerStackDS(new Cloud()),
-      _laserCloudSurfStackDS(new Cloud()), _laserCloudSurround(new Cloud()), _laserCloudSurroundDS(new Cloud()),
-      _laserCloudCornerFromMap(new Cloud()), _laserCloudSurfFromMap(new Cloud()), _gpu(new b200::Context()),
-      _solver(new b200::GaussNewtonSolver()) {
+      _c(new b200::DualCloud[M_NUM]), _gpu(new b200::Context()), _solver(new b200::GaussNewtonSolver()) {
+  static const int slots[M_NUM] = {LOAM_B200_C_MAP_CORNER_LAST, LOAM_B200_C_MAP_SURF_LAST, LOAM_B200_C_MAP_FULL,
+                                   LOAM_B200_C_MAP_CORNER_STACK_DS, LOAM_B200_C_MAP_SURF_STACK_DS,
+                                   LOAM_B200_C_MAP_CORNER_FROM_MAP, LOAM_B200_C_MAP_SURF_FROM_MAP,
+                                   LOAM_B200_C_MAP_SURROUND_DS};
+  for (int i = 0; i < M_NUM; i++) _c[i].bind(_gpu, slots[i]);
   _frameCount = _stackFrameNum - 1;
   _mapFrameCount = _mapFrameNum - 1;
-  _laserCloudCornerArray.resize(_laserCloudNum);
-  _laserCloudSurfArray.resize(_laserCloudNum);
-  _laserCloudCornerDSArray.resize(_laserCloudNum);
-  _laserCloudSurfDSArray.resize(_laserCloudNum);
-  for (size_t i = 0; i < _laserCloudNum; i++) {
-    _laserCloudCornerArray[i].reset(new Cloud());
-    _laserCloudSurfArray[i].reset(new Cloud());
-    _laserCloudCornerDSArray[i].reset(new Cloud());
-    _laserCloudSurfDSArray[i].reset(new Cloud());
-  }
   _downSizeFilterCorner.setLeafSize(0.2, 0.2, 0.2);
   _downSizeFilterSurf.setLeafSize(0.4, 0.4, 0.4);
 }
 
 BasicLaserMapping::~BasicLaserMapping() {
   delete _solver;
+  delete[] _c;
   delete _gpu;
+}
+
+pcl::PointCloud<pcl::PointXYZI>& BasicLaserMapping::laserCloud() { return _c[M_FULL].hostMutable(); }
+pcl::PointCloud<pcl::PointXYZI>& BasicLaserMapping::laserCloudCornerLast() { return _c[M_CORNER_LAST].hostMutable(); }
+pcl::PointCloud<pcl::PointXYZI>& BasicLaserMapping::laserCloudSurfLast() { return _c[M_SURF_LAST].hostMutable(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::laserCloudSurroundDS() const { return _c[M_SURROUND_DS].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::cornerStackDS() const { return _c[M_CORNER_STACK_DS].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::surfStackDS() const { return _c[M_SURF_STACK_DS].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::cornerFromMap() const { return _c[M_CORNER_FROM_MAP].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::surfFromMap() const { return _c[M_SURF_FROM_MAP].host(); }
+
+void BasicLaserMapping::adopt(BasicLaserOdometry& odom) {
+  static const int to[3] = {M_CORNER_LAST, M_SURF_LAST, M_FULL};
+  for (int i = 0; i < 3; i++) {
+    b200::DualCloud& src = odom.deviceCloud(i);
+    src.ensureDevice();
+    _gpu->check(loam_b200_cloud_copy(_gpu->get(), _c[to[i]].slot(), odom.deviceContext()->get(), src.slot()),
+                "loam_b200_cloud_copy");
+    _c[to[i]].deviceWritten((int)src.size());
+  }
+  updateOdometry(odom.transformSum());
 }
 
 // Pose prediction: compose (Sum, BefMapped, AftMapped) into TobeMapped, closed-form ZXY Euler algebra as published
@@ -138,91 +155,18 @@ void BasicLaserMapping::pointAssociateToMap(const pcl::PointXYZI& pi, pcl::Point
   po.z += _transformTobeMapped.pos.z();
 }
 
-void BasicLaserMapping::pointAssociateTobeMapped(const pcl::PointXYZI& pi, pcl::PointXYZI& po) {
-  po.x = pi.x - _transformTobeMapped.pos.x();
-  po.y = pi.y - _transformTobeMapped.pos.y();
-  po.z = pi.z - _transformTobeMapped.pos.z();
-  po.intensity = pi.intensity;
-  hostmath::rotateYXZ(po, -_transformTobeMapped.rot_y, -_transformTobeMapped.rot_x, -_transformTobeMapped.rot_z);
-}
-
-void BasicLaserMapping::transformFullResToMap() {
-  const size_t n = _laserCloudFullRes->size();
-  if (n == 0) return;
-  b200::pack(*_laserCloudFullRes, _bufA);
-  loam_b200_pose p;
-  b200::fillPose(_transformTobeMapped, p);
-  _gpu->check(loam_b200_transform_to_map(_gpu->get(), _bufA.data(), (int)n, &p), "loam_b200_transform_to_map");
-  b200::unpack(_bufA.data(), n, *_laserCloudFullRes);
-}
-
 bool BasicLaserMapping::createDownsizedMap() {
   _mapFrameCount++;
   if (_mapFrameCount < _mapFrameNum) return false;
   _mapFrameCount = 0;
-  _laserCloudSurround->clear();
-  for (auto ind : _laserCloudSurroundInd) {
-    *_laserCloudSurround += *_laserCloudCornerArray[ind];
-    *_laserCloudSurround += *_laserCloudSurfArray[ind];
-  }
-  // upstream filters the surround map with the CORNER filter (:261-262); _downSizeFilterMap is never used
-  b200::voxelFilter(*_gpu, *_laserCloudSurround, b200::leafOf(_downSizeFilterCorner), *_laserCloudSurroundDS, _bufA, _bufB);
+  // corner + surface points of the 5 x 5 x 5 surround cubes, filtered with the CORNER filter (upstream :251-262;
+  // _downSizeFilterMap is configurable but never used there either)
+  std::vector<int32_t> cubes(_laserCloudSurroundInd.begin(), _laserCloudSurroundInd.end());
+  const int cen[3] = {_laserCloudCenWidth, _laserCloudCenHeight, _laserCloudCenDepth};
+  _gpu->check(loam_b200_map_surround(_gpu->get(), cen, cubes.data(), (int)cubes.size(), b200::leafOf(_downSizeFilterCorner)),
+              "loam_b200_map_surround");
+  _c[M_SURROUND_DS].deviceWritten(loam_b200_cloud_size(_gpu->get(), LOAM_B200_C_MAP_SURROUND_DS));
   return true;
-}
-
-// cube index of a map-frame point: truncation toward zero plus the negative-side correction (upstream :540-553)
-bool BasicLaserMapping::cubeIndexOf(const pcl::PointXYZI& p, size_t& index) const {
-  const double CUBE_SIZE = 50.0, CUBE_HALF = CUBE_SIZE / 2;
-  int cubeI = int((p.x + CUBE_HALF) / CUBE_SIZE) + _laserCloudCenWidth;
-  int cubeJ = int((p.y + CUBE_HALF) / CUBE_SIZE) + _laserCloudCenHeight;
-  int cubeK = int((p.z + CUBE_HALF) / CUBE_SIZE) + _laserCloudCenDepth;
-  if (p.x + CUBE_HALF < 0) cubeI--;
-  if (p.y + CUBE_HALF < 0) cubeJ--;
-  if (p.z + CUBE_HALF < 0) cubeK--;
-  if (cubeI >= 0 && cubeI < (int)_laserCloudWidth && cubeJ >= 0 && cubeJ < (int)_laserCloudHeight && cubeK >= 0 &&
-      cubeK < (int)_laserCloudDepth) {
-    index = cubeI + _laserCloudWidth * cubeJ + _laserCloudWidth * _laserCloudHeight * cubeK;
-    return true;
-  }
-  return false;
-}
-
-// Roll the cube grid by one cell along `axis` (0 = width, 1 = height, 2 = depth).  direction +1 moves every cube
-// to the next higher index and empties the lowest slab (the map centre index grows); -1 the opposite
-// (upstream :311-441 spells the six cases out).
-void BasicLaserMapping::shiftCubes(int axis, int direction) {
-  const int dims[3] = {(int)_laserCloudWidth, (int)_laserCloudHeight, (int)_laserCloudDepth};
-  const int n = dims[axis];
-  const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
-  int ijk[3];
-  for (ijk[a1] = 0; ijk[a1] < dims[a1]; ijk[a1]++) {
-    for (ijk[a2] = 0; ijk[a2] < dims[a2]; ijk[a2]++) {
-      if (direction > 0) {
-        for (int t = n - 1; t >= 1; t--) {
-          ijk[axis] = t;
-          const size_t a = toIndex(ijk[0], ijk[1], ijk[2]);
-          ijk[axis] = t - 1;
-          const size_t b = toIndex(ijk[0], ijk[1], ijk[2]);
-          std::swap(_laserCloudCornerArray[a], _laserCloudCornerArray[b]);
-          std::swap(_laserCloudSurfArray[a], _laserCloudSurfArray[b]);
-        }
-        ijk[axis] = 0;
-      } else {
-        for (int t = 0; t < n - 1; t++) {
-          ijk[axis] = t;
-          const size_t a = toIndex(ijk[0], ijk[1], ijk[2]);
-          ijk[axis] = t + 1;
-          const size_t b = toIndex(ijk[0], ijk[1], ijk[2]);
-          std::swap(_laserCloudCornerArray[a], _laserCloudCornerArray[b]);
-          std::swap(_laserCloudSurfArray[a], _laserCloudSurfArray[b]);
-        }
-        ijk[axis] = n - 1;
-      }
-      const size_t c = toIndex(ijk[0], ijk[1], ijk[2]);
-      _laserCloudCornerArray[c]->clear();
-      _laserCloudSurfArray[c]->clear();
-    }
-  }
 }
 
 bool BasicLaserMapping::process(Time const& laserOdometryTime) {
@@ -231,17 +175,7 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   _frameCount = 0;
   _laserOdometryTime = laserOdometryTime;
 
-  pcl::PointXYZI pointSel;
   transformAssociateToMap();
-
-  for (auto const& pt : _laserCloudCornerLast->points) {
-    pointAssociateToMap(pt, pointSel);
-    _laserCloudCornerStack->push_back(pointSel);
-  }
-  for (auto const& pt : _laserCloudSurfLast->points) {
-    pointAssociateToMap(pt, pointSel);
-    _laserCloudSurfStack->push_back(pointSel);
-  }
 
   pcl::PointXYZI pointOnYAxis;
   pointOnYAxis.x = 0.0;
@@ -257,13 +191,15 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   if (_transformTobeMapped.pos.y() + CUBE_HALF < 0) centerCubeJ--;
   if (_transformTobeMapped.pos.z() + CUBE_HALF < 0) centerCubeK--;
 
-  // keep the sensor at least 3 cubes away from every face of the grid
-  while (centerCubeI < 3) { shiftCubes(0, +1); centerCubeI++; _laserCloudCenWidth++; }
-  while (centerCubeI >= (int)_laserCloudWidth - 3) { shiftCubes(0, -1); centerCubeI--; _laserCloudCenWidth--; }
-  while (centerCubeJ < 3) { shiftCubes(1, +1); centerCubeJ++; _laserCloudCenHeight++; }
-  while (centerCubeJ >= (int)_laserCloudHeight - 3) { shiftCubes(1, -1); centerCubeJ--; _laserCloudCenHeight--; }
-  while (centerCubeK < 3) { shiftCubes(2, +1); centerCubeK++; _laserCloudCenDepth++; }
-  while (centerCubeK >= (int)_laserCloudDepth - 3) { shiftCubes(2, -1); centerCubeK--; _laserCloudCenDepth--; }
+  // Rolling the grid (upstream :311-441 moves cube pointers and clears the slab that wraps around): with the flat
+  // GPU pools a point's cube follows from its position and these centre offsets, so only the offsets move; points
+  // whose cube leaves the grid are dropped by the next end-of-sweep pass.
+  while (centerCubeI < 3) { centerCubeI++; _laserCloudCenWidth++; }
+  while (centerCubeI >= (int)_laserCloudWidth - 3) { centerCubeI--; _laserCloudCenWidth--; }
+  while (centerCubeJ < 3) { centerCubeJ++; _laserCloudCenHeight++; }
+  while (centerCubeJ >= (int)_laserCloudHeight - 3) { centerCubeJ--; _laserCloudCenHeight--; }
+  while (centerCubeK < 3) { centerCubeK++; _laserCloudCenDepth++; }
+  while (centerCubeK >= (int)_laserCloudDepth - 3) { centerCubeK--; _laserCloudCenDepth--; }
 
   // 5 x 5 x 5 neighbourhood; a cube is "valid" when one of its corners lies within 30..150 degrees of the sensor's
   // up axis (law-of-cosines test against a point 10 m up the y axis, upstream :456-489)
@@ -301,47 +237,37 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
     }
   }
 
-  // surrounding-map clouds for the optimisation
-  _laserCloudCornerFromMap->clear();
-  _laserCloudSurfFromMap->clear();
-  for (auto const& ind : _laserCloudValidInd) {
-    *_laserCloudCornerFromMap += *_laserCloudCornerArray[ind];
-    *_laserCloudSurfFromMap += *_laserCloudSurfArray[ind];
-  }
-
-  // feature stacks back into the (predicted) sensor frame, then voxel-filtered
-  for (auto& pt : *_laserCloudCornerStack) pointAssociateTobeMapped(pt, pt);
-  for (auto& pt : *_laserCloudSurfStack) pointAssociateTobeMapped(pt, pt);
-  b200::voxelFilter(*_gpu, *_laserCloudCornerStack, b200::leafOf(_downSizeFilterCorner), *_laserCloudCornerStackDS, _bufA, _bufB);
-  const size_t laserCloudCornerStackNum = _laserCloudCornerStackDS->size();
-  b200::voxelFilter(*_gpu, *_laserCloudSurfStack, b200::leafOf(_downSizeFilterSurf), *_laserCloudSurfStackDS, _bufA, _bufB);
-  const size_t laserCloudSurfStackNum = _laserCloudSurfStackDS->size();
-  _laserCloudCornerStack->clear();
-  _laserCloudSurfStack->clear();
+  // GPU: feature stacks (to map and back with the predicted pose, voxel filters), surrounding-map clouds of the valid
+  // cubes and their BVHs (upstream :282-292, :503-527, :636-637)
+  _c[M_CORNER_LAST].ensureDevice();
+  _c[M_SURF_LAST].ensureDevice();
+  _c[M_FULL].ensureDevice();
+  std::vector<int32_t> valid(_laserCloudValidInd.begin(), _laserCloudValidInd.end());
+  loam_b200_map_window win;
+  win.cen[0] = _laserCloudCenWidth;
+  win.cen[1] = _laserCloudCenHeight;
+  win.cen[2] = _laserCloudCenDepth;
+  win.valid_cubes = valid.data();
+  win.n_valid = (int)valid.size();
+  win.corner_leaf = b200::leafOf(_downSizeFilterCorner);
+  win.surf_leaf = b200::leafOf(_downSizeFilterSurf);
+  loam_b200_pose predicted;
+  b200::fillPose(_transformTobeMapped, predicted);
+  _gpu->check(loam_b200_map_begin_sweep(_gpu->get(), &predicted, &win, _mapSizes), "loam_b200_map_begin_sweep");
+  _c[M_CORNER_FROM_MAP].deviceWritten(_mapSizes[0]);
+  _c[M_SURF_FROM_MAP].deviceWritten(_mapSizes[1]);
+  _c[M_CORNER_STACK_DS].deviceWritten(_mapSizes[2]);
+  _c[M_SURF_STACK_DS].deviceWritten(_mapSizes[3]);
 
   optimizeTransformTobeMapped();
 
-  // insert the down-sized stack points into their cubes with the optimised pose
-  for (size_t i = 0; i < laserCloudCornerStackNum; i++) {
-    pointAssociateToMap(_laserCloudCornerStackDS->points[i], pointSel);
-    size_t cubeInd;
-    if (cubeIndexOf(pointSel, cubeInd)) _laserCloudCornerArray[cubeInd]->push_back(pointSel);
-  }
-  for (size_t i = 0; i < laserCloudSurfStackNum; i++) {
-    pointAssociateToMap(_laserCloudSurfStackDS->points[i], pointSel);
-    size_t cubeInd;
-    if (cubeIndexOf(pointSel, cubeInd)) _laserCloudSurfArray[cubeInd]->push_back(pointSel);
-  }
+  // GPU: insert the down-sized stack points with the optimised pose, voxel-filter every valid cube, move the
+  // full-resolution cloud into the map frame (upstream :536-595)
+  loam_b200_pose optimised;
+  b200::fillPose(_transformTobeMapped, optimised);
+  _gpu->check(loam_b200_map_end_sweep(_gpu->get(), &optimised), "loam_b200_map_end_sweep");
+  _c[M_FULL].deviceWritten((int)_c[M_FULL].size());
 
-  // down-size every cube in the field of view
-  for (auto const& ind : _laserCloudValidInd) {
-    b200::voxelFilter(*_gpu, *_laserCloudCornerArray[ind], b200::leafOf(_downSizeFilterCorner), *_laserCloudCornerDSArray[ind], _bufA, _bufB);
-    b200::voxelFilter(*_gpu, *_laserCloudSurfArray[ind], b200::leafOf(_downSizeFilterSurf), *_laserCloudSurfDSArray[ind], _bufA, _bufB);
-    _laserCloudCornerArray[ind].swap(_laserCloudCornerDSArray[ind]);
-    _laserCloudSurfArray[ind].swap(_laserCloudSurfDSArray[ind]);
-  }
-
-  transformFullResToMap();
   _downsizedMapCreated = createDownsizedMap();
   return true;
 }
@@ -364,20 +290,9 @@ void BasicLaserMapping::updateOdometry(Twist const& twist) { _transformSum = twi
 
 void BasicLaserMapping::optimizeTransformTobeMapped() {
   _lastIterations = 0;
-  if (_laserCloudCornerFromMap->size() <= 10 || _laserCloudSurfFromMap->size() <= 100) return;
-
-  // the reference rebuilds both k-d trees over the concatenated surrounding map every sweep (:636-637)
-  b200::pack(*_laserCloudCornerFromMap, _bufA);
-  _gpu->check(loam_b200_tree_build(_gpu->get(), LOAM_B200_TREE_MAP_CORNER, _bufA.data(), (int)_laserCloudCornerFromMap->size()),
-              "loam_b200_tree_build(corner map)");
-  b200::pack(*_laserCloudSurfFromMap, _bufA);
-  _gpu->check(loam_b200_tree_build(_gpu->get(), LOAM_B200_TREE_MAP_SURF, _bufA.data(), (int)_laserCloudSurfFromMap->size()),
-              "loam_b200_tree_build(surf map)");
-  b200::pack(*_laserCloudCornerStackDS, _bufA);
-  b200::pack(*_laserCloudSurfStackDS, _bufB);
-  _gpu->check(loam_b200_map_set_queries(_gpu->get(), _bufA.data(), (int)_laserCloudCornerStackDS->size(), _bufB.data(),
-                                        (int)_laserCloudSurfStackDS->size()),
-              "loam_b200_map_set_queries");
+  // _laserCloudCornerFromMap->size() <= 10 || _laserCloudSurfFromMap->size() <= 100 (upstream :628-629); the trees
+  // and the query stacks were prepared by loam_b200_map_begin_sweep
+  if (_mapSizes[0] <= 10 || _mapSizes[1] <= 100) return;
 
   for (size_t iterCount = 0; iterCount < _maxIterations; iterCount++) {
     _lastIterations = iterCount + 1;
@@ -405,18 +320,25 @@ void BasicLaserMapping::optimizeTransformTobeMapped() {
 }
 
 void BasicLaserMapping::seedMap(Cloud const& cornerPoints, Cloud const& surfPoints) {
-  size_t idx;
-  for (auto const& p : cornerPoints.points)
-    if (cubeIndexOf(p, idx)) _laserCloudCornerArray[idx]->push_back(p);
-  for (auto const& p : surfPoints.points)
-    if (cubeIndexOf(p, idx)) _laserCloudSurfArray[idx]->push_back(p);
+  // points outside the 21 x 11 x 21 grid are dropped by the first end-of-sweep pass, like upstream's insertion
+  // (:548-554) would never have stored them
+  b200::pack(cornerPoints, _bufA);
+  _gpu->check(loam_b200_map_pool_append(_gpu->get(), 0, _bufA.data(), (int)cornerPoints.size()), "loam_b200_map_pool_append");
+  b200::pack(surfPoints, _bufA);
+  _gpu->check(loam_b200_map_pool_append(_gpu->get(), 1, _bufA.data(), (int)surfPoints.size()), "loam_b200_map_pool_append");
 }
 
 void BasicLaserMapping::collectMap(Cloud& corner, Cloud& surf) const {
-  corner.clear();
-  surf.clear();
-  for (auto const& c : _laserCloudCornerArray) corner += *c;
-  for (auto const& c : _laserCloudSurfArray) surf += *c;
+  Cloud* out[2] = {&corner, &surf};
+  const int slot[2] = {LOAM_B200_C_MAP_CORNER_POOL, LOAM_B200_C_MAP_SURF_POOL};
+  std::vector<float> buf;
+  for (int k = 0; k < 2; k++) {
+    const int n = _gpu->created() ? loam_b200_cloud_size(_gpu->get(), slot[k]) : 0;
+    buf.resize((size_t)n * 4 + 4);
+    int got = 0;
+    if (n > 0) _gpu->check(loam_b200_cloud_download(_gpu->get(), slot[k], buf.data(), n, &got), "loam_b200_cloud_download");
+    b200::unpack(buf.data(), (size_t)got, *out[k]);
+  }
 }
 
 }  // namespace loam

@@ -7,21 +7,74 @@
 
 #include "b200_runtime.h"
 #include "host_math.h"
+#include "loam_velodyne/BasicScanRegistration.h"
 
 namespace loam {
 
 using hostmath::rad2deg;
 
+static void fillOdomPoseOf(const Twist& t, float scanPeriod, int iter, loam_b200_odom_pose& p) {
+  p.rot[0] = t.rot_x.rad(); p.rot[1] = t.rot_y.rad(); p.rot[2] = t.rot_z.rad();
+  // upstream re-evaluates std::sin / std::cos of the float angle per Jacobian row (:504-509): same values as the
+  // Angle caches
+  p.sin_[0] = t.rot_x.sin(); p.sin_[1] = t.rot_y.sin(); p.sin_[2] = t.rot_z.sin();
+  p.cos_[0] = t.rot_x.cos(); p.cos_[1] = t.rot_y.cos(); p.cos_[2] = t.rot_z.cos();
+  p.pos[0] = t.pos.x(); p.pos[1] = t.pos.y(); p.pos[2] = t.pos.z();
+  p.inv_scan_period = 1.f / scanPeriod;
+  p.iter = iter;
+}
+
+enum { C_SHARP = 0, C_LESS_SHARP, C_FLAT, C_LESS_FLAT, C_FULL, C_LAST_CORNER, C_LAST_SURF, C_NUM };
+
 BasicLaserOdometry::BasicLaserOdometry(float scanPeriod, size_t maxIterations)
     : _scanPeriod(scanPeriod), _frameCount(0), _maxIterations(maxIterations), _systemInited(false), _deltaTAbort(0.1),
-      _deltaRAbort(0.1), _lastCornerCloud(new b200::Cloud()), _lastSurfaceCloud(new b200::Cloud()),
-      _cornerPointsSharp(new b200::Cloud()), _cornerPointsLessSharp(new b200::Cloud()),
-      _surfPointsFlat(new b200::Cloud()), _surfPointsLessFlat(new b200::Cloud()), _laserCloud(new b200::Cloud()),
-      _gpu(new b200::Context()), _solver(new b200::GaussNewtonSolver()) {}
+      _deltaRAbort(0.1), _c(new b200::DualCloud[C_NUM]), _gpu(new b200::Context()),
+      _solver(new b200::GaussNewtonSolver()) {
+  static const int slots[C_NUM] = {LOAM_B200_C_ODOM_SHARP, LOAM_B200_C_ODOM_LESS_SHARP, LOAM_B200_C_ODOM_FLAT,
+                                   LOAM_B200_C_ODOM_LESS_FLAT, LOAM_B200_C_ODOM_FULL, LOAM_B200_C_ODOM_LAST_CORNER,
+                                   LOAM_B200_C_ODOM_LAST_SURF};
+  for (int i = 0; i < C_NUM; i++) _c[i].bind(_gpu, slots[i]);
+}
 
 BasicLaserOdometry::~BasicLaserOdometry() {
   delete _solver;
+  delete[] _c;
   delete _gpu;
+}
+
+pcl::PointCloud<pcl::PointXYZI>::Ptr& BasicLaserOdometry::cornerPointsSharp() { return _c[C_SHARP].hostPtrMutable(); }
+pcl::PointCloud<pcl::PointXYZI>::Ptr& BasicLaserOdometry::cornerPointsLessSharp() { return _c[C_LESS_SHARP].hostPtrMutable(); }
+pcl::PointCloud<pcl::PointXYZI>::Ptr& BasicLaserOdometry::surfPointsFlat() { return _c[C_FLAT].hostPtrMutable(); }
+pcl::PointCloud<pcl::PointXYZI>::Ptr& BasicLaserOdometry::surfPointsLessFlat() { return _c[C_LESS_FLAT].hostPtrMutable(); }
+pcl::PointCloud<pcl::PointXYZI>::Ptr& BasicLaserOdometry::laserCloud() { return _c[C_FULL].hostPtrMutable(); }
+pcl::PointCloud<pcl::PointXYZI>::Ptr const& BasicLaserOdometry::lastCornerCloud() { return _c[C_LAST_CORNER].hostPtr(); }
+pcl::PointCloud<pcl::PointXYZI>::Ptr const& BasicLaserOdometry::lastSurfaceCloud() { return _c[C_LAST_SURF].hostPtr(); }
+b200::DualCloud& BasicLaserOdometry::deviceCloud(int which) {
+  return _c[which == 0 ? C_LAST_CORNER : which == 1 ? C_LAST_SURF : C_FULL];
+}
+
+void BasicLaserOdometry::adopt(BasicScanRegistration& reg) {
+  // reg clouds: 0 full, 1 sharp, 2 less sharp, 3 flat, 4 less flat
+  static const int from[5] = {1, 2, 3, 4, 0};
+  static const int to[5] = {C_SHARP, C_LESS_SHARP, C_FLAT, C_LESS_FLAT, C_FULL};
+  for (int i = 0; i < 5; i++) {
+    b200::DualCloud& src = reg.deviceCloud(from[i]);
+    src.ensureDevice();
+    _gpu->check(loam_b200_cloud_copy(_gpu->get(), _c[to[i]].slot(), reg.deviceContext()->get(), src.slot()),
+                "loam_b200_cloud_copy");
+    _c[to[i]].deviceWritten((int)src.size());
+  }
+  updateIMU(reg.imuTransform());
+}
+
+void BasicLaserOdometry::transformLaserCloudToEnd() {
+  if (_c[C_FULL].size() == 0) return;
+  _c[C_FULL].ensureDevice();
+  loam_b200_odom_pose p;
+  fillOdomPoseOf(_transform, _scanPeriod, 0, p);
+  _gpu->check(loam_b200_cloud_transform_to_end(_gpu->get(), _c[C_FULL].slot(), &p), "loam_b200_cloud_transform_to_end");
+  _c[C_FULL].deviceWritten((int)_c[C_FULL].size());
+  if (hasIMU()) applyImuToEnd(_c[C_FULL].hostMutable());
 }
 
 bool BasicLaserOdometry::hasIMU() const {
@@ -42,50 +95,40 @@ void BasicLaserOdometry::updateIMU(pcl::PointCloud<pcl::PointXYZ> const& imuTran
   _imuVeloFromStart = imuTrans.points[3];
 }
 
-static void fillOdomPose(const Twist& t, float scanPeriod, int iter, loam_b200_odom_pose& p) {
-  p.rot[0] = t.rot_x.rad(); p.rot[1] = t.rot_y.rad(); p.rot[2] = t.rot_z.rad();
-  // upstream re-evaluates std::sin/std::cos of the float angle per Jacobian row (:504-509): same values as the
-  // Angle caches
-  p.sin_[0] = t.rot_x.sin(); p.sin_[1] = t.rot_y.sin(); p.sin_[2] = t.rot_z.sin();
-  p.cos_[0] = t.rot_x.cos(); p.cos_[1] = t.rot_y.cos(); p.cos_[2] = t.rot_z.cos();
-  p.pos[0] = t.pos.x(); p.pos[1] = t.pos.y(); p.pos[2] = t.pos.z();
-  p.inv_scan_period = 1.f / scanPeriod;
-  p.iter = iter;
-}
-
 size_t BasicLaserOdometry::transformToEnd(pcl::PointCloud<pcl::PointXYZI>::Ptr& cloud) {
   const size_t n = cloud->points.size();
   if (n == 0) return 0;
+  // an arbitrary caller-owned cloud: host buffer in, host buffer out
   b200::pack(*cloud, _bufA);
   loam_b200_odom_pose p;
-  fillOdomPose(_transform, _scanPeriod, 0, p);
+  fillOdomPoseOf(_transform, _scanPeriod, 0, p);
   _gpu->check(loam_b200_transform_to_end(_gpu->get(), _bufA.data(), (int)n, &p), "loam_b200_transform_to_end");
   b200::unpack(_bufA.data(), n, *cloud);
-  if (hasIMU()) {
-    // IMU terms of upstream :78-83 (identity when no IMU): undo the plain "+ pos", redo with the shift, then rotate
-    for (auto& pt : cloud->points) {
-      pt.x += -_imuShiftFromStart.x();
-      pt.y += -_imuShiftFromStart.y();
-      pt.z += -_imuShiftFromStart.z();
-      hostmath::rotateZXY(pt, _imuRollStart, _imuPitchStart, _imuYawStart);
-      hostmath::rotateYXZ(pt, -_imuYawEnd, -_imuPitchEnd, -_imuRollEnd);
-    }
-  }
+  if (hasIMU()) applyImuToEnd(*cloud);
   return n;
 }
 
+// IMU terms of upstream :78-83 (all identities without IMU data)
+void BasicLaserOdometry::applyImuToEnd(pcl::PointCloud<pcl::PointXYZI>& cloud) {
+  for (auto& pt : cloud.points) {
+    pt.x += -_imuShiftFromStart.x();
+    pt.y += -_imuShiftFromStart.y();
+    pt.z += -_imuShiftFromStart.z();
+    hostmath::rotateZXY(pt, _imuRollStart, _imuPitchStart, _imuYawStart);
+    hostmath::rotateYXZ(pt, -_imuYawEnd, -_imuPitchEnd, -_imuRollEnd);
+  }
+}
+
 void BasicLaserOdometry::uploadLast() {
-  b200::pack(*_lastCornerCloud, _bufA);
-  b200::pack(*_lastSurfaceCloud, _bufB);
-  _gpu->check(loam_b200_odom_set_last(_gpu->get(), _bufA.data(), (int)_lastCornerCloud->size(), _bufB.data(),
-                                      (int)_lastSurfaceCloud->size()),
-              "loam_b200_odom_set_last");
+  _c[C_LAST_CORNER].ensureDevice();
+  _c[C_LAST_SURF].ensureDevice();
+  _gpu->check(loam_b200_odom_rebuild_last(_gpu->get()), "loam_b200_odom_rebuild_last");
 }
 
 void BasicLaserOdometry::process() {
   if (!_systemInited) {
-    _cornerPointsLessSharp.swap(_lastCornerCloud);
-    _surfPointsLessFlat.swap(_lastSurfaceCloud);
+    _c[C_LESS_SHARP].swap(_c[C_LAST_CORNER]);
+    _c[C_LESS_FLAT].swap(_c[C_LAST_SURF]);
     uploadLast();
     _transformSum.rot_x += _imuPitchStart;
     _transformSum.rot_z += _imuRollStart;
@@ -97,21 +140,19 @@ void BasicLaserOdometry::process() {
   _transform.pos -= _imuVeloFromStart * _scanPeriod;
   _lastIterations = 0;
 
-  size_t lastCornerCloudSize = _lastCornerCloud->points.size();
-  size_t lastSurfaceCloudSize = _lastSurfaceCloud->points.size();
+  size_t lastCornerCloudSize = _c[C_LAST_CORNER].size();
+  size_t lastSurfaceCloudSize = _c[C_LAST_SURF].size();
 
   if (lastCornerCloudSize > 10 && lastSurfaceCloudSize > 100) {
     // non-finite feature points would be dropped here upstream (removeNaNFromPointCloud, :230); inputs are dense
-    b200::pack(*_cornerPointsSharp, _bufA);
-    b200::pack(*_surfPointsFlat, _bufB);
-    _gpu->check(loam_b200_odom_set_current(_gpu->get(), _bufA.data(), (int)_cornerPointsSharp->size(), _bufB.data(),
-                                           (int)_surfPointsFlat->size()),
-                "loam_b200_odom_set_current");
+    _c[C_SHARP].ensureDevice();
+    _c[C_FLAT].ensureDevice();
+    _gpu->check(loam_b200_odom_prepare(_gpu->get()), "loam_b200_odom_prepare");
 
     for (size_t iterCount = 0; iterCount < _maxIterations; iterCount++) {
       _lastIterations = iterCount + 1;
       loam_b200_odom_pose pose;
-      fillOdomPose(_transform, _scanPeriod, (int)iterCount, pose);
+      fillOdomPoseOf(_transform, _scanPeriod, (int)iterCount, pose);
       loam_b200_normal_eq ne;
       _gpu->check(loam_b200_odom_iterate(_gpu->get(), &pose, &ne), "loam_b200_odom_iterate");
       if (ne.n_selected < 10) continue;
@@ -156,14 +197,21 @@ void BasicLaserOdometry::process() {
   _transformSum.rot_z = rz;
   _transformSum.pos = trans;
 
-  transformToEnd(_cornerPointsLessSharp);
-  transformToEnd(_surfPointsLessFlat);
+  // transformToEnd(less sharp / less flat) in HBM, then they become the "last" clouds (:651-655)
+  loam_b200_odom_pose endPose;
+  fillOdomPoseOf(_transform, _scanPeriod, 0, endPose);
+  for (int which : {C_LESS_SHARP, C_LESS_FLAT}) {
+    if (_c[which].size() == 0) continue;
+    _c[which].ensureDevice();
+    _gpu->check(loam_b200_cloud_transform_to_end(_gpu->get(), _c[which].slot(), &endPose), "loam_b200_cloud_transform_to_end");
+    _c[which].deviceWritten((int)_c[which].size());
+    if (hasIMU()) applyImuToEnd(_c[which].hostMutable());
+  }
+  _c[C_LESS_SHARP].swap(_c[C_LAST_CORNER]);
+  _c[C_LESS_FLAT].swap(_c[C_LAST_SURF]);
 
-  _cornerPointsLessSharp.swap(_lastCornerCloud);
-  _surfPointsLessFlat.swap(_lastSurfaceCloud);
-
-  lastCornerCloudSize = _lastCornerCloud->points.size();
-  lastSurfaceCloudSize = _lastSurfaceCloud->points.size();
+  lastCornerCloudSize = _c[C_LAST_CORNER].size();
+  lastSurfaceCloudSize = _c[C_LAST_SURF].size();
   if (lastCornerCloudSize > 10 && lastSurfaceCloudSize > 100) uploadLast();
 }
 

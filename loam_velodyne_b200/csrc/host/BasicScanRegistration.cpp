@@ -29,8 +29,15 @@ void IMUState::interpolate(const IMUState& start, const IMUState& end, const flo
   result.position = start.position * inv + end.position * ratio;
 }
 
-BasicScanRegistration::BasicScanRegistration() : _gpu(new b200::Context()) {}
-BasicScanRegistration::~BasicScanRegistration() { delete _gpu; }
+BasicScanRegistration::BasicScanRegistration() : _clouds(new b200::DualCloud[5]), _gpu(new b200::Context()) {
+  static const int slots[5] = {LOAM_B200_C_REG_FULL, LOAM_B200_C_REG_SHARP, LOAM_B200_C_REG_LESS_SHARP,
+                               LOAM_B200_C_REG_FLAT, LOAM_B200_C_REG_LESS_FLAT};
+  for (int i = 0; i < 5; i++) _clouds[i].bind(_gpu, slots[i]);
+}
+BasicScanRegistration::~BasicScanRegistration() {
+  delete[] _clouds;
+  delete _gpu;
+}
 
 bool BasicScanRegistration::configure(const RegistrationParams& config) {
   _config = config;
@@ -42,77 +49,118 @@ void BasicScanRegistration::reset(const Time& scanTime) {
   _imuIdx = 0;
   if (hasIMUData()) interpolateIMUStateFor(0, _imuStart);
   _sweepStart = scanTime;
-  _laserCloud.clear();
-  _cornerPointsSharp.clear();
-  _cornerPointsLessSharp.clear();
-  _surfacePointsFlat.clear();
-  _surfacePointsLessFlat.clear();
+  for (int i = 0; i < 5; i++) _clouds[i].clear();
   _scanIndices.clear();
+  _indicesFetched = _labelsFetched = false;
+  _sharpIdx.clear();
+  _lessSharpIdx.clear();
+  _flatIdx.clear();
+  _labels.clear();
+}
+
+b200::DualCloud& BasicScanRegistration::deviceCloud(int which) { return _clouds[which]; }
+pcl::PointCloud<pcl::PointXYZI> const& BasicScanRegistration::laserCloud() { return _clouds[0].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicScanRegistration::cornerPointsSharp() { return _clouds[1].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicScanRegistration::cornerPointsLessSharp() { return _clouds[2].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicScanRegistration::surfacePointsFlat() { return _clouds[3].host(); }
+pcl::PointCloud<pcl::PointXYZI> const& BasicScanRegistration::surfacePointsLessFlat() { return _clouds[4].host(); }
+
+// ring ranges exactly as upstream builds _scanIndices (BasicScanRegistration.cpp:35-42): inclusive (first, last),
+// an empty ring in the middle is (c, c - 1), an empty leading ring (0, 0)
+static void appendRange(std::vector<IndexRange>& ranges, size_t& cloudSize, size_t ringSize) {
+  IndexRange range(cloudSize, 0);
+  cloudSize += ringSize;
+  range.second = cloudSize > 0 ? cloudSize - 1 : 0;
+  ranges.push_back(range);
 }
 
 void BasicScanRegistration::processScanlines(const Time& scanTime,
                                              std::vector<pcl::PointCloud<pcl::PointXYZI>> const& laserCloudScans) {
   reset(scanTime);
-
-  // ring-ordered full-resolution cloud + inclusive index range per ring (upstream BasicScanRegistration.cpp:35-42)
   size_t cloudSize = 0;
-  for (size_t i = 0; i < laserCloudScans.size(); i++) {
-    _laserCloud += laserCloudScans[i];
-    IndexRange range(cloudSize, 0);
-    cloudSize += laserCloudScans[i].size();
-    range.second = cloudSize > 0 ? cloudSize - 1 : 0;
-    _scanIndices.push_back(range);
-  }
-
-  const int n = (int)_laserCloud.size();
-  const int nRings = (int)_scanIndices.size();
-  if (nRings > 0) {
-    b200::pack(_laserCloud, _packed);
-    _ringStart.resize(nRings);
-    _ringEnd.resize(nRings);
-    for (int r = 0; r < nRings; r++) {
-      _ringStart[r] = (int)_scanIndices[r].first;
-      // an empty ring in the middle has second = first - 1 (size_t arithmetic upstream never underflows because
-      // cloudSize > 0 there); an empty leading ring is (0, 0)
-      _ringEnd[r] = (int)_scanIndices[r].second;
+  for (size_t i = 0; i < laserCloudScans.size(); i++) appendRange(_scanIndices, cloudSize, laserCloudScans[i].size());
+  // pack the rings straight into the upload buffer; the host-side concatenated cloud is rebuilt lazily by laserCloud()
+  _packed.resize(cloudSize * 4 + 4);
+  size_t o = 0;
+  for (auto const& ring : laserCloudScans)
+    for (auto const& p : ring.points) {
+      _packed[o++] = p.x; _packed[o++] = p.y; _packed[o++] = p.z; _packed[o++] = p.intensity;
     }
-    loam_b200_reg_params prm;
-    prm.nFeatureRegions = _config.nFeatureRegions;
-    prm.curvatureRegion = _config.curvatureRegion;
-    prm.maxCornerSharp = _config.maxCornerSharp;
-    prm.maxCornerLessSharp = _config.maxCornerLessSharp;
-    prm.maxSurfaceFlat = _config.maxSurfaceFlat;
-    prm.lessFlatFilterSize = _config.lessFlatFilterSize;
-    prm.surfaceCurvatureThreshold = _config.surfaceCurvatureThreshold;
-
-    const size_t capSharp = (size_t)nRings * prm.nFeatureRegions * prm.maxCornerSharp;
-    const size_t capLess = (size_t)nRings * prm.nFeatureRegions * prm.maxCornerLessSharp;
-    const size_t capFlat = (size_t)nRings * prm.nFeatureRegions * prm.maxSurfaceFlat;
-    _sharpIdx.resize(capSharp + 1);
-    _lessSharpIdx.resize(capLess + 1);
-    _flatIdx.resize(capFlat + 1);
-    _labels.resize((size_t)n + 1);
-    _lessFlatDS.resize((size_t)n * 4 + 4);
-    loam_b200_features out;
-    out.sharp_idx = _sharpIdx.data();           out.sharp_cap = (int)capSharp;
-    out.less_sharp_idx = _lessSharpIdx.data();  out.less_sharp_cap = (int)capLess;
-    out.flat_idx = _flatIdx.data();             out.flat_cap = (int)capFlat;
-    out.label = reinterpret_cast<int8_t*>(_labels.data());
-    out.less_flat_ds = _lessFlatDS.data();      out.less_flat_cap = n;
-    out.n_sharp = out.n_less_sharp = out.n_flat = out.n_less_flat = 0;
-    _gpu->check(loam_b200_extract_features(_gpu->get(), _packed.data(), n, _ringStart.data(), _ringEnd.data(), nRings,
-                                           &prm, &out),
-                "loam_b200_extract_features");
-    _sharpIdx.resize(out.n_sharp);
-    _lessSharpIdx.resize(out.n_less_sharp);
-    _flatIdx.resize(out.n_flat);
-    _labels.resize(n);
-    for (int idx : _sharpIdx) _cornerPointsSharp.push_back(_laserCloud[idx]);
-    for (int idx : _lessSharpIdx) _cornerPointsLessSharp.push_back(_laserCloud[idx]);
-    for (int idx : _flatIdx) _surfacePointsFlat.push_back(_laserCloud[idx]);
-    b200::unpack(_lessFlatDS.data(), (size_t)out.n_less_flat, _surfacePointsLessFlat);
-  }
+  if (cloudSize > 0)
+    _gpu->check(loam_b200_cloud_upload(_gpu->get(), LOAM_B200_C_REG_FULL, _packed.data(), (int)cloudSize), "loam_b200_cloud_upload");
+  runExtraction((int)cloudSize);
   updateIMUTransform();
+}
+
+void BasicScanRegistration::processPackedSweep(const Time& scanTime, const float* xyzi, const int* ringSizes, int nRings) {
+  reset(scanTime);
+  size_t cloudSize = 0;
+  for (int i = 0; i < nRings; i++) appendRange(_scanIndices, cloudSize, (size_t)ringSizes[i]);
+  if (cloudSize > 0)
+    _gpu->check(loam_b200_cloud_upload(_gpu->get(), LOAM_B200_C_REG_FULL, xyzi, (int)cloudSize), "loam_b200_cloud_upload");
+  runExtraction((int)cloudSize);
+  updateIMUTransform();
+}
+
+void BasicScanRegistration::processDeviceSweep(const Time& scanTime, const void* deviceXyzi, const int* ringSizes, int nRings) {
+  reset(scanTime);
+  size_t cloudSize = 0;
+  for (int i = 0; i < nRings; i++) appendRange(_scanIndices, cloudSize, (size_t)ringSizes[i]);
+  if (cloudSize > 0)
+    _gpu->check(loam_b200_cloud_upload_device(_gpu->get(), LOAM_B200_C_REG_FULL, deviceXyzi, (int)cloudSize),
+                "loam_b200_cloud_upload_device");
+  runExtraction((int)cloudSize);
+  updateIMUTransform();
+}
+
+void BasicScanRegistration::runExtraction(int n) {
+  _lastN = n;
+  const int nRings = (int)_scanIndices.size();
+  if (nRings == 0 || n == 0) return;
+  _clouds[0].deviceWritten(n);
+  _ringStart.resize(nRings);
+  _ringEnd.resize(nRings);
+  for (int r = 0; r < nRings; r++) {
+    _ringStart[r] = (int)_scanIndices[r].first;
+    _ringEnd[r] = (int)_scanIndices[r].second;
+  }
+  loam_b200_reg_params prm;
+  prm.nFeatureRegions = _config.nFeatureRegions;
+  prm.curvatureRegion = _config.curvatureRegion;
+  prm.maxCornerSharp = _config.maxCornerSharp;
+  prm.maxCornerLessSharp = _config.maxCornerLessSharp;
+  prm.maxSurfaceFlat = _config.maxSurfaceFlat;
+  prm.lessFlatFilterSize = _config.lessFlatFilterSize;
+  prm.surfaceCurvatureThreshold = _config.surfaceCurvatureThreshold;
+  int counts[4] = {0, 0, 0, 0};
+  _gpu->check(loam_b200_reg_run(_gpu->get(), _ringStart.data(), _ringEnd.data(), nRings, &prm, counts), "loam_b200_reg_run");
+  for (int k = 0; k < 4; k++) _clouds[1 + k].deviceWritten(counts[k]);
+}
+
+void BasicScanRegistration::fetchIndices() {
+  if (_indicesFetched) return;
+  _indicesFetched = true;
+  if (_lastN == 0 || !_gpu->created()) return;
+  std::vector<int>* dst[3] = {&_sharpIdx, &_lessSharpIdx, &_flatIdx};
+  for (int w = 1; w <= 3; w++) {
+    const int n = (int)_clouds[w].size();
+    dst[w - 1]->resize(n + 1);
+    int got = 0;
+    _gpu->check(loam_b200_reg_indices(_gpu->get(), w, dst[w - 1]->data(), n, &got), "loam_b200_reg_indices");
+    dst[w - 1]->resize(got);
+  }
+}
+std::vector<int> const& BasicScanRegistration::sharpIndices() { fetchIndices(); return _sharpIdx; }
+std::vector<int> const& BasicScanRegistration::lessSharpIndices() { fetchIndices(); return _lessSharpIdx; }
+std::vector<int> const& BasicScanRegistration::flatIndices() { fetchIndices(); return _flatIdx; }
+std::vector<signed char> const& BasicScanRegistration::pointLabels() {
+  if (!_labelsFetched) {
+    _labelsFetched = true;
+    _labels.resize(_lastN);
+    if (_lastN > 0 && _gpu->created())
+      _gpu->check(loam_b200_reg_labels(_gpu->get(), reinterpret_cast<int8_t*>(_labels.data()), _lastN), "loam_b200_reg_labels");
+  }
+  return _labels;
 }
 
 // ---- IMU plumbing (host scalar code; upstream BasicScanRegistration.cpp:82-152,258-281).  The hot path's configs

@@ -39,6 +39,33 @@ void Context::check(int status, const char* what) {
   throw std::runtime_error(msg);
 }
 
+void DualCloud::ensureDevice() {
+  if (devValid_) return;
+  pack(*host_, buf_);
+  ctx_->check(loam_b200_cloud_upload(ctx_->get(), slot_, buf_.data(), (int)host_->points.size()), "loam_b200_cloud_upload");
+  devValid_ = true;
+  devN_ = (int)host_->points.size();
+}
+
+void DualCloud::materialise() {
+  if (hostValid_) return;
+  buf_.resize((std::size_t)devN_ * 4 + 4);
+  int n = 0;
+  ctx_->check(loam_b200_cloud_download(ctx_->get(), slot_, buf_.data(), devN_, &n), "loam_b200_cloud_download");
+  unpack(buf_.data(), (std::size_t)n, *host_);
+  hostValid_ = true;
+}
+
+void DualCloud::swap(DualCloud& o) {
+  host_.swap(o.host_);
+  std::swap(hostValid_, o.hostValid_);
+  std::swap(devValid_, o.devValid_);
+  std::swap(devN_, o.devN_);
+  // the device buffers trade places so each slot keeps meaning "this member"
+  if (ctx_ && ctx_ == o.ctx_ && ctx_->created())
+    ctx_->check(loam_b200_cloud_swap(ctx_->get(), slot_, o.slot_), "loam_b200_cloud_swap");
+}
+
 void GaussNewtonSolver::solve(const loam_b200_normal_eq& ne, bool firstIteration, float eigenThreshold, float x[6]) {
   // column-major copies for the dense kernels
   float A[36], b[6];

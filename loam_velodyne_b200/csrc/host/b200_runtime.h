@@ -28,6 +28,7 @@ class Context {
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   loam_b200_ctx* get();  // created on first use; throws when no GPU is usable
+  bool created() const { return ctx_ != nullptr; }
   void check(int status, const char* what);
 
  private:
@@ -35,6 +36,40 @@ class Context {
 };
 
 typedef pcl::PointCloud<pcl::PointXYZI> Cloud;
+
+// A pcl cloud of the drop-in API whose authoritative copy may live in a cloud slot of a context (HBM).  The host
+// pcl::PointCloud is only materialised when an accessor needs it; a mutable accessor marks the device copy stale so
+// the next stage call re-uploads.  This is what lets registration -> odometry -> mapping chain without host hops
+// while the reference's cloud accessors keep working.
+class DualCloud {
+ public:
+  DualCloud() : host_(new Cloud()), ctx_(nullptr), slot_(-1), hostValid_(true), devValid_(false), devN_(0) {}
+  void bind(Context* ctx, int slot) { ctx_ = ctx; slot_ = slot; }
+  int slot() const { return slot_; }
+  Context* context() const { return ctx_; }
+
+  // the reference hands out `Ptr&` / `Cloud&`; callers may modify through them
+  Cloud::Ptr& hostPtrMutable() { materialise(); devValid_ = false; return host_; }
+  Cloud& hostMutable() { materialise(); devValid_ = false; return *host_; }
+  const Cloud::Ptr& hostPtr() const { const_cast<DualCloud*>(this)->materialise(); return host_; }
+  const Cloud& host() const { const_cast<DualCloud*>(this)->materialise(); return *host_; }
+
+  std::size_t size() const { return hostValid_ ? host_->points.size() : (std::size_t)devN_; }
+  void deviceWritten(int n) { devValid_ = true; hostValid_ = false; devN_ = n; }
+  void ensureDevice();   // upload when the device copy is stale
+  void materialise();    // download when the host copy is stale
+  void clear() { host_->clear(); hostValid_ = true; devValid_ = false; devN_ = 0; }
+  // exchange contents with another cloud of the same context (the reference swaps cloud pointers)
+  void swap(DualCloud& o);
+
+ private:
+  Cloud::Ptr host_;
+  Context* ctx_;
+  int slot_;
+  bool hostValid_, devValid_;
+  int devN_;
+  std::vector<float> buf_;
+};
 
 // pcl::PointXYZI (32 B) <-> packed float4 (16 B)
 inline void pack(const Cloud& c, std::vector<float>& out) {

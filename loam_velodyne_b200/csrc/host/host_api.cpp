@@ -62,6 +62,7 @@ struct RegH {
   const std::vector<int>& index(int which) {
     return which == 1 ? r.sharpIndices() : which == 2 ? r.lessSharpIndices() : r.flatIndices();
   }
+  // the reference entry point: one pcl cloud per ring (BasicScanRegistration.h:142)
   void process(const float* pts, const int* ring_sizes, int n_rings) {
     rings.resize(n_rings);
     int off = 0;
@@ -76,7 +77,7 @@ struct OdomH {
   loam::BasicLaserOdometry o;
   OdomH(float sp, int it) : o(sp, it) {}
   const Cloud& cloud(int which) {
-    return which == 0 ? *o.lastCornerCloud() : which == 1 ? *o.lastSurfaceCloud() : *o.laserCloud();
+    return which == 0 ? *o.lastCornerCloud() : which == 1 ? *o.lastSurfaceCloud() : o.deviceCloud(2).host();
   }
 };
 struct MapH {
@@ -211,14 +212,51 @@ void* loam_b200_pipeline_scanreg(void* h) { return &((PipeH*)h)->reg; }
 void* loam_b200_pipeline_odom(void* h) { return &((PipeH*)h)->odom; }
 void* loam_b200_pipeline_map(void* h) { return &((PipeH*)h)->map; }
 
+static int pipeline_sweep_impl(PipeH* h, const float* pts, const void* d_pts, const int* ring_sizes, int n_rings,
+                               float* odom_sum6, float* map_aft6, double* st) {
+  const double t0 = now();
+  if (d_pts)
+    h->reg.r.processDeviceSweep(loam::Time(), d_pts, ring_sizes, n_rings);
+  else
+    h->reg.r.processPackedSweep(loam::Time(), pts, ring_sizes, n_rings);
+  const double t1 = now();
+  // ScanRegistration::publishResult -> LaserOdometry::*Handler upstream (five clouds + imuTrans over ROS topics):
+  // here a device-to-device hand-off
+  auto& o = h->odom.o;
+  o.adopt(h->reg.r);
+  o.process();
+  const double t2 = now();
+  o.transformLaserCloudToEnd();  // LaserOdometry::publishResult, LaserOdometry.cpp:326 upstream
+  const double t3 = now();
+  auto& m = h->map.m;
+  m.adopt(o);                    // LaserOdometry::publishResult -> LaserMapping::*Handler upstream
+  const int ok = m.process(loam::Time()) ? 1 : 0;
+  const double t4 = now();
+  twist6(o.transformSum(), odom_sum6);
+  twist6(m.transformAftMapped(), map_aft6);
+  if (st) { st[0] = t1 - t0; st[1] = t2 - t1; st[2] = t3 - t2; st[3] = t4 - t3; st[4] = t4 - t0; }
+  return ok;
+}
+
 int loam_b200_pipeline_sweep(void* hh, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
                              float* map_aft6, double* st) {
+  return guarded([&] { return pipeline_sweep_impl((PipeH*)hh, pts, nullptr, ring_sizes, n_rings, odom_sum6, map_aft6, st); });
+}
+
+int loam_b200_pipeline_sweep_device(void* hh, const void* d_pts, const int* ring_sizes, int n_rings, float* odom_sum6,
+                                    float* map_aft6, double* st) {
+  return guarded([&] { return pipeline_sweep_impl((PipeH*)hh, nullptr, d_pts, ring_sizes, n_rings, odom_sum6, map_aft6, st); });
+}
+
+// the same chain through the reference's own entry points and host clouds only (what separate ROS nodes would do):
+// processScanlines(vector<PointCloud>) -> host cloud copies -> process() -> host cloud copies -> process(Time)
+int loam_b200_pipeline_sweep_hostclouds(void* hh, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
+                                        float* map_aft6, double* st) {
   return guarded([&] {
     PipeH* h = (PipeH*)hh;
     const double t0 = now();
     h->reg.process(pts, ring_sizes, n_rings);
     const double t1 = now();
-    // the hop ScanRegistration::publishResult -> LaserOdometry::*Handler (plain cloud copies upstream)
     auto& o = h->odom.o;
     *o.cornerPointsSharp() = h->reg.r.cornerPointsSharp();
     *o.cornerPointsLessSharp() = h->reg.r.cornerPointsLessSharp();

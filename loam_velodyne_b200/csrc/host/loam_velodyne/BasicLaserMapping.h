@@ -18,7 +18,8 @@
 
 namespace loam {
 
-namespace b200 { class Context; struct GaussNewtonSolver; }
+namespace b200 { class Context; class DualCloud; struct GaussNewtonSolver; }
+class BasicLaserOdometry;
 
 typedef struct IMUState2 {
   Time stamp;
@@ -43,9 +44,11 @@ class BasicLaserMapping {
   void updateOdometry(double pitch, double yaw, double roll, double x, double y, double z);
   void updateOdometry(Twist const& twist);
 
-  auto& laserCloud() { return *_laserCloudFullRes; }
-  auto& laserCloudCornerLast() { return *_laserCloudCornerLast; }
-  auto& laserCloudSurfLast() { return *_laserCloudSurfLast; }
+  // input clouds (filled by the caller, LaserMapping.cpp:177-200 upstream) / registered full-resolution output;
+  // the authoritative copies live in HBM, these handles download on first use and mark the GPU copy stale
+  pcl::PointCloud<pcl::PointXYZI>& laserCloud();
+  pcl::PointCloud<pcl::PointXYZI>& laserCloudCornerLast();
+  pcl::PointCloud<pcl::PointXYZI>& laserCloudSurfLast();
 
   void setScanPeriod(float val) { _scanPeriod = val; }
   void setMaxIterations(size_t val) { _maxIterations = val; }
@@ -64,7 +67,7 @@ class BasicLaserMapping {
 
   auto const& transformAftMapped() const { return _transformAftMapped; }
   auto const& transformBefMapped() const { return _transformBefMapped; }
-  auto const& laserCloudSurroundDS() const { return *_laserCloudSurroundDS; }
+  pcl::PointCloud<pcl::PointXYZI> const& laserCloudSurroundDS() const;
 
   bool hasFreshMap() const { return _downsizedMapCreated; }
 
@@ -73,11 +76,15 @@ class BasicLaserMapping {
   void seedMap(pcl::PointCloud<pcl::PointXYZI> const& cornerPoints, pcl::PointCloud<pcl::PointXYZI> const& surfPoints);
   size_t lastIterationCount() const { return _lastIterations; }
   auto const& transformTobeMapped() const { return _transformTobeMapped; }
-  auto const& cornerStackDS() const { return *_laserCloudCornerStackDS; }
-  auto const& surfStackDS() const { return *_laserCloudSurfStackDS; }
-  auto const& cornerFromMap() const { return *_laserCloudCornerFromMap; }
-  auto const& surfFromMap() const { return *_laserCloudSurfFromMap; }
+  pcl::PointCloud<pcl::PointXYZI> const& cornerStackDS() const;
+  pcl::PointCloud<pcl::PointXYZI> const& surfStackDS() const;
+  pcl::PointCloud<pcl::PointXYZI> const& cornerFromMap() const;
+  pcl::PointCloud<pcl::PointXYZI> const& surfFromMap() const;
   void collectMap(pcl::PointCloud<pcl::PointXYZI>& corner, pcl::PointCloud<pcl::PointXYZI>& surf) const;
+  // take last corner / last surface / full-resolution clouds and transformSum from an odometry object without a
+  // host round trip (LaserOdometry::publishResult -> LaserMapping::*Handler upstream)
+  void adopt(BasicLaserOdometry& odom);
+  b200::Context* deviceContext() { return _gpu; }
 
  private:
   typedef pcl::PointCloud<pcl::PointXYZI> Cloud;
@@ -85,12 +92,7 @@ class BasicLaserMapping {
   void transformAssociateToMap();
   void transformUpdate();
   void pointAssociateToMap(const pcl::PointXYZI& pi, pcl::PointXYZI& po);
-  void pointAssociateTobeMapped(const pcl::PointXYZI& pi, pcl::PointXYZI& po);
-  void transformFullResToMap();
   bool createDownsizedMap();
-  size_t toIndex(int i, int j, int k) const { return i + _laserCloudWidth * j + _laserCloudWidth * _laserCloudHeight * k; }
-  bool cubeIndexOf(const pcl::PointXYZI& p, size_t& index) const;
-  void shiftCubes(int axis, int direction);
 
   Time _laserOdometryTime;
   float _scanPeriod;
@@ -104,12 +106,11 @@ class BasicLaserMapping {
   int _laserCloudCenWidth, _laserCloudCenHeight, _laserCloudCenDepth;
   const size_t _laserCloudWidth, _laserCloudHeight, _laserCloudDepth, _laserCloudNum;
 
-  Cloud::Ptr _laserCloudCornerLast, _laserCloudSurfLast, _laserCloudFullRes;
-  Cloud::Ptr _laserCloudCornerStack, _laserCloudSurfStack, _laserCloudCornerStackDS, _laserCloudSurfStackDS;
-  Cloud::Ptr _laserCloudSurround, _laserCloudSurroundDS, _laserCloudCornerFromMap, _laserCloudSurfFromMap;
-
-  std::vector<Cloud::Ptr> _laserCloudCornerArray, _laserCloudSurfArray, _laserCloudCornerDSArray, _laserCloudSurfDSArray;
+  // clouds in HBM slots: corner last, surf last, full res, corner / surf stack DS, corner / surf from map, surround DS;
+  // the 21 x 11 x 21 cube arrays of the reference are two flat point pools on the GPU (see csrc/mappool.cuh)
+  b200::DualCloud* _c;
   std::vector<size_t> _laserCloudValidInd, _laserCloudSurroundInd;
+  int _mapSizes[4] = {0, 0, 0, 0};
 
   Twist _transformSum, _transformIncre, _transformTobeMapped, _transformBefMapped, _transformAftMapped;
   std::vector<IMUState2> _imuHistory;

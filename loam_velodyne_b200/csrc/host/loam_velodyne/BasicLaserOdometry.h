@@ -12,7 +12,8 @@
 
 namespace loam {
 
-namespace b200 { class Context; struct GaussNewtonSolver; }
+namespace b200 { class Context; class DualCloud; struct GaussNewtonSolver; }
+class BasicScanRegistration;
 
 class BasicLaserOdometry {
  public:
@@ -24,16 +25,19 @@ class BasicLaserOdometry {
   void process();
   void updateIMU(pcl::PointCloud<pcl::PointXYZ> const& imuTrans);
 
-  auto& cornerPointsSharp() { return _cornerPointsSharp; }
-  auto& cornerPointsLessSharp() { return _cornerPointsLessSharp; }
-  auto& surfPointsFlat() { return _surfPointsFlat; }
-  auto& surfPointsLessFlat() { return _surfPointsLessFlat; }
-  auto& laserCloud() { return _laserCloud; }
+  // input clouds: the caller fills them through these handles (LaserOdometry.cpp:182-238 upstream); handing one
+  // out marks the GPU copy stale, so process() uploads it again
+  pcl::PointCloud<pcl::PointXYZI>::Ptr& cornerPointsSharp();
+  pcl::PointCloud<pcl::PointXYZI>::Ptr& cornerPointsLessSharp();
+  pcl::PointCloud<pcl::PointXYZI>::Ptr& surfPointsFlat();
+  pcl::PointCloud<pcl::PointXYZI>::Ptr& surfPointsLessFlat();
+  pcl::PointCloud<pcl::PointXYZI>::Ptr& laserCloud();
 
   auto const& transformSum() { return _transformSum; }
   auto const& transform() { return _transform; }
-  auto const& lastCornerCloud() { return _lastCornerCloud; }
-  auto const& lastSurfaceCloud() { return _lastSurfaceCloud; }
+  // result clouds live in HBM; downloaded on first use
+  pcl::PointCloud<pcl::PointXYZI>::Ptr const& lastCornerCloud();
+  pcl::PointCloud<pcl::PointXYZI>::Ptr const& lastSurfaceCloud();
 
   void setScanPeriod(float val) { _scanPeriod = val; }
   void setMaxIterations(size_t val) { _maxIterations = val; }
@@ -48,8 +52,16 @@ class BasicLaserOdometry {
 
   size_t transformToEnd(pcl::PointCloud<pcl::PointXYZI>::Ptr& cloud);
 
-  // extension: iterations executed by the last process() call
+  // ---- extensions (not part of the reference API) ----
+  // iterations executed by the last process() call
   size_t lastIterationCount() const { return _lastIterations; }
+  // take this sweep's five clouds + imuTransform from a scan registration object without a host round trip
+  // (what ScanRegistration::publishResult -> LaserOdometry::*Handler moves over ROS topics upstream)
+  void adopt(BasicScanRegistration& reg);
+  // transformToEnd(laserCloud()) on the GPU copy (LaserOdometry::publishResult, LaserOdometry.cpp:326 upstream)
+  void transformLaserCloudToEnd();
+  b200::Context* deviceContext() { return _gpu; }
+  b200::DualCloud& deviceCloud(int which);  // 0 last corner, 1 last surface, 2 laserCloud
 
  private:
   void pluginIMURotation(const Angle& bcx, const Angle& bcy, const Angle& bcz, const Angle& blx, const Angle& bly,
@@ -58,6 +70,7 @@ class BasicLaserOdometry {
   void accumulateRotation(Angle cx, Angle cy, Angle cz, Angle lx, Angle ly, Angle lz, Angle& ox, Angle& oy, Angle& oz);
   bool hasIMU() const;
   void uploadLast();
+  void applyImuToEnd(pcl::PointCloud<pcl::PointXYZI>& cloud);
 
   float _scanPeriod;
   long _frameCount;
@@ -65,9 +78,7 @@ class BasicLaserOdometry {
   bool _systemInited;
   float _deltaTAbort, _deltaRAbort;
 
-  pcl::PointCloud<pcl::PointXYZI>::Ptr _lastCornerCloud, _lastSurfaceCloud;
-  pcl::PointCloud<pcl::PointXYZI>::Ptr _cornerPointsSharp, _cornerPointsLessSharp, _surfPointsFlat, _surfPointsLessFlat,
-      _laserCloud;
+  b200::DualCloud* _c;  // [7]: sharp, less sharp, flat, less flat, full, last corner, last surface
 
   Twist _transform, _transformSum;
   Angle _imuRollStart, _imuPitchStart, _imuYawStart, _imuRollEnd, _imuPitchEnd, _imuYawEnd;

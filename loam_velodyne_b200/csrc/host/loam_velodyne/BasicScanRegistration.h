@@ -16,7 +16,7 @@
 
 namespace loam {
 
-namespace b200 { class Context; }
+namespace b200 { class Context; class DualCloud; }
 
 typedef std::pair<size_t, size_t> IndexRange;
 
@@ -68,18 +68,28 @@ class BasicScanRegistration {
 
   auto const& imuTransform() { return _imuTrans; }
   auto const& sweepStart() { return _sweepStart; }
-  auto const& laserCloud() { return _laserCloud; }
-  auto const& cornerPointsSharp() { return _cornerPointsSharp; }
-  auto const& cornerPointsLessSharp() { return _cornerPointsLessSharp; }
-  auto const& surfacePointsFlat() { return _surfacePointsFlat; }
-  auto const& surfacePointsLessFlat() { return _surfacePointsLessFlat; }
+  // The clouds live in HBM after processScanlines; these accessors download them on first use (then cache).
+  pcl::PointCloud<pcl::PointXYZI> const& laserCloud();
+  pcl::PointCloud<pcl::PointXYZI> const& cornerPointsSharp();
+  pcl::PointCloud<pcl::PointXYZI> const& cornerPointsLessSharp();
+  pcl::PointCloud<pcl::PointXYZI> const& surfacePointsFlat();
+  pcl::PointCloud<pcl::PointXYZI> const& surfacePointsLessFlat();
   auto const& config() { return _config; }
 
-  // extension: indices (into laserCloud()) of the picked features and the per-point labels of the last sweep
-  std::vector<int> const& sharpIndices() const { return _sharpIdx; }
-  std::vector<int> const& lessSharpIndices() const { return _lessSharpIdx; }
-  std::vector<int> const& flatIndices() const { return _flatIdx; }
-  std::vector<signed char> const& pointLabels() const { return _labels; }
+  // ---- extensions (not part of the reference API) ----
+  // same as processScanlines for a sweep that is already packed: n_rings rings of ring_sizes[r] consecutive
+  // (x, y, z, intensity) float quadruples; skips the per-ring pcl clouds
+  void processPackedSweep(const Time& scanTime, const float* xyzi, const int* ringSizes, int nRings);
+  // ... or already resident in GPU memory (device pointer to the packed points)
+  void processDeviceSweep(const Time& scanTime, const void* deviceXyzi, const int* ringSizes, int nRings);
+  // indices (into laserCloud()) of the picked features and the per-point labels of the last sweep
+  std::vector<int> const& sharpIndices();
+  std::vector<int> const& lessSharpIndices();
+  std::vector<int> const& flatIndices();
+  std::vector<signed char> const& pointLabels();
+  // device-side hand-off to BasicLaserOdometry::adopt
+  b200::Context* deviceContext() { return _gpu; }
+  b200::DualCloud& deviceCloud(int which);  // 0 full, 1 sharp, 2 less sharp, 3 flat, 4 less flat
 
  private:
   bool hasIMUData() const { return !_imuHistory.empty(); }
@@ -89,10 +99,12 @@ class BasicScanRegistration {
   void transformToStartIMU(pcl::PointXYZI& point);
   void updateIMUTransform();
 
+  void runExtraction(int n);
+  void fetchIndices();
+
   RegistrationParams _config;
-  pcl::PointCloud<pcl::PointXYZI> _laserCloud;
   std::vector<IndexRange> _scanIndices;
-  pcl::PointCloud<pcl::PointXYZI> _cornerPointsSharp, _cornerPointsLessSharp, _surfacePointsFlat, _surfacePointsLessFlat;
+  b200::DualCloud* _clouds;  // [5]: full, sharp, less sharp, flat, less flat
 
   Time _sweepStart, _scanTime;
   IMUState _imuStart, _imuCur;
@@ -102,9 +114,11 @@ class BasicScanRegistration {
   pcl::PointCloud<pcl::PointXYZ> _imuTrans = {4, 1};
 
   b200::Context* _gpu;
-  std::vector<float> _packed, _lessFlatDS;
+  std::vector<float> _packed;
   std::vector<int> _ringStart, _ringEnd, _sharpIdx, _lessSharpIdx, _flatIdx;
   std::vector<signed char> _labels;
+  bool _indicesFetched = false, _labelsFetched = false;
+  int _lastN = 0;
 };
 
 }  // namespace loam

@@ -8,6 +8,7 @@
 #include "mapping_lm.cuh"
 #include "odometry_lm.cuh"
 #include "voxel.cuh"
+#include "mappool.cuh"
 
 using namespace loamb;
 
@@ -76,13 +77,13 @@ int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
   const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 8);
-  bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(t.pts.p, m, bb);
+  bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(t.points(), m, bb);
   LB_LAUNCH_CHECK(c);
-  morton_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.pts.p, m, bb, s.keys_a.p, s.vals_a.p);
+  morton_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.points(), m, bb, s.keys_a.p, s.vals_a.p);
   LB_LAUNCH_CHECK(c);
   int rc = radix_sort_pairs(c, m, 30);
   if (rc) return rc;
-  gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.pts.p, s.vals_a.p, m, t.sorted.p);
+  gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.points(), s.vals_a.p, m, t.sorted.p);
   LB_LAUNCH_CHECK(c);
   leaf_kernel<<<blocks_for(n_leaf, 256), 256, 0, c->stream>>>(t.sorted.p, s.keys_a.p, m, n_leaf, t.leaf_key.p,
                                                               t.box_lo.p, t.box_hi.p, t.flags.p);
@@ -226,7 +227,8 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_xfer, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
     delete c;
     return LOAM_B200_ERR_CUDA;
@@ -257,7 +259,11 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   c->sort.keys_a.release(); c->sort.keys_b.release(); c->sort.vals_a.release(); c->sort.vals_b.release();
   c->sort.hist.release();
   c->bbox.release(); c->knn_q.release(); c->knn_idx.release(); c->knn_d2.release();
-  c->map_q.release(); c->partials.release(); c->result.release(); c->ticket.release(); c->walk_totals.release(); c->dbg_coeff.release();
+  c->map_q.release(); c->partials.release(); c->result.release(); c->ticket.release(); c->walk_totals.release();
+  for (auto& cl : c->cloud) cl.release();
+  c->pool_cls[0].release(); c->pool_cls[1].release(); c->rank_of_cube.release(); c->pool_tmp.release();
+  c->pool_tmp_cls.release(); c->cmp_pos.release(); c->cmp_bsum.release();
+  if (c->ev_xfer) cudaEventDestroy(c->ev_xfer); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -276,16 +282,14 @@ int loam_b200_sync(loam_b200_ctx* c) {
 void* loam_b200_stream(loam_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 // ------------------------------------------------------------------------------------------------ features
-int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const int32_t* ring_start,
-                               const int32_t* ring_end, int n_rings, const loam_b200_reg_params* prm,
-                               loam_b200_features* out) {
-  CHECK_CTX(c);
-  if (!pts || n < 0 || !ring_start || !ring_end || n_rings <= 0 || n_rings > 256 || !prm || !out)
-    return LOAM_B200_ERR_ARG;
+// Shared by the host-buffer entry point and the device-resident stage: points are in d_pts (n), ring ranges on the
+// host.  Results: dense index lists behind the per-ring slots of reg_picks, gathered feature clouds + less-flat DS in
+// the REG_* cloud slots, labels in reg_label, totals in c->reg_totals (host, after one sync).
+static int run_features(loam_b200_ctx* c, const float4* d_pts, int n, const int32_t* ring_start, const int32_t* ring_end,
+                        int n_rings, const loam_b200_reg_params* prm) {
   if (prm->curvatureRegion < 1 || prm->curvatureRegion > 15 || prm->nFeatureRegions < 1 || prm->maxCornerSharp < 0 ||
       prm->maxCornerLessSharp < prm->maxCornerSharp || prm->maxSurfaceFlat < 0 || !(prm->lessFlatFilterSize > 0.f))
     return LOAM_B200_ERR_ARG;
-  out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
   int max_ring = 0;
   for (int r = 0; r < n_rings; r++) {
     const long long s = ring_start[r], e = ring_end[r];
@@ -294,6 +298,11 @@ int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const 
     }
     if (e >= s) max_ring = std::max(max_ring, (int)(e - s + 1));
   }
+  for (int k = 0; k < 4; k++) c->reg_totals[k] = 0;
+  c->reg_n = n;
+  c->reg_n_rings = n_rings;
+  c->cloud_n[LOAM_B200_C_REG_SHARP] = c->cloud_n[LOAM_B200_C_REG_LESS_SHARP] = 0;
+  c->cloud_n[LOAM_B200_C_REG_FLAT] = c->cloud_n[LOAM_B200_C_REG_LESS_FLAT] = 0;
   if (n == 0) return LOAM_B200_OK;
   FeatParams fp;
   fp.nFeatureRegions = prm->nFeatureRegions;
@@ -306,6 +315,9 @@ int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const 
   fp.cap_sharp = prm->nFeatureRegions * prm->maxCornerSharp;
   fp.cap_less = prm->nFeatureRegions * prm->maxCornerLessSharp;
   fp.cap_flat = prm->nFeatureRegions * prm->maxSurfaceFlat;
+  c->reg_slots.cap_sharp = fp.cap_sharp;
+  c->reg_slots.cap_less = fp.cap_less;
+  c->reg_slots.cap_flat = fp.cap_flat;
   const int slots = fp.cap_sharp + fp.cap_less + fp.cap_flat;
 
   int ncap = (max_ring + 31) & ~31;
@@ -315,37 +327,65 @@ int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const 
   const size_t smem = (size_t)ncap * (16 + 4 + 4 + 2) + (size_t)n2cap * 8;
   if (smem > 200 * 1024) return LOAM_B200_ERR_CAPACITY;  // ring longer than ~5.7 k points
 
-  LB_CUDA(c, c->reg_pts.reserve(n));
   LB_CUDA(c, c->reg_ring_start.reserve(n_rings));
   LB_CUDA(c, c->reg_ring_end.reserve(n_rings));
   LB_CUDA(c, c->reg_picks.reserve((size_t)n_rings * slots * 2 + 16));
   LB_CUDA(c, c->reg_counts.reserve((size_t)n_rings * 4 + 8));
   LB_CUDA(c, c->reg_label.reserve(n));
   LB_CUDA(c, c->reg_lessflat.reserve(n));
-  LB_CUDA(c, c->tmp_pts.reserve(n));
-  LB_CUDA(c, cudaMemcpyAsync(c->reg_pts.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  LB_CUDA(c, c->cloud[LOAM_B200_C_REG_SHARP].reserve((size_t)n_rings * fp.cap_sharp + 1));
+  LB_CUDA(c, c->cloud[LOAM_B200_C_REG_LESS_SHARP].reserve((size_t)n_rings * fp.cap_less + 1));
+  LB_CUDA(c, c->cloud[LOAM_B200_C_REG_FLAT].reserve((size_t)n_rings * fp.cap_flat + 1));
+  LB_CUDA(c, c->cloud[LOAM_B200_C_REG_LESS_FLAT].reserve(n));
   LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_start.p, ring_start, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
   LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_end.p, ring_end, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
 
   prof_begin(c, LOAM_B200_K_FEATURES);
-  feature_ring_kernel<<<n_rings, FEAT_THREADS, smem, c->stream>>>(c->reg_pts.p, c->reg_ring_start.p,
-                                                                  c->reg_ring_end.p, fp, ncap, n2cap, c->reg_picks.p,
-                                                                  c->reg_counts.p, c->reg_label.p, c->reg_lessflat.p);
+  feature_ring_kernel<<<n_rings, FEAT_THREADS, smem, c->stream>>>(d_pts, c->reg_ring_start.p, c->reg_ring_end.p, fp,
+                                                                  ncap, n2cap, c->reg_picks.p, c->reg_counts.p,
+                                                                  c->reg_label.p, c->reg_lessflat.p);
   LB_LAUNCH_CHECK(c);
-  // dense outputs: three pick lists live behind the per-ring slots, totals behind the counts
   int* dense = c->reg_picks.p + (size_t)n_rings * slots;
   int* totals = c->reg_counts.p + (size_t)n_rings * 4;
-  feature_pack_kernel<<<1, 256, 0, c->stream>>>(c->reg_counts.p, c->reg_picks.p, c->reg_ring_start.p,
-                                                c->reg_lessflat.p, n_rings, fp, dense,
-                                                dense + (size_t)n_rings * fp.cap_sharp,
-                                                dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less), c->tmp_pts.p,
-                                                totals);
+  feature_pack_kernel<<<n_rings, 256, 0, c->stream>>>(
+      c->reg_counts.p, c->reg_picks.p, c->reg_ring_start.p, d_pts, c->reg_lessflat.p, n_rings, fp, dense,
+      dense + (size_t)n_rings * fp.cap_sharp, dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less),
+      c->cloud[LOAM_B200_C_REG_SHARP].p, c->cloud[LOAM_B200_C_REG_LESS_SHARP].p, c->cloud[LOAM_B200_C_REG_FLAT].p,
+      c->cloud[LOAM_B200_C_REG_LESS_FLAT].p, totals);
   LB_LAUNCH_CHECK(c);
   prof_end(c);
-
-  int h_tot[4];
-  LB_CUDA(c, cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaMemcpyAsync(c->reg_totals, totals, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->cloud_n[LOAM_B200_C_REG_SHARP] = c->reg_totals[0];
+  c->cloud_n[LOAM_B200_C_REG_LESS_SHARP] = c->reg_totals[1];
+  c->cloud_n[LOAM_B200_C_REG_FLAT] = c->reg_totals[2];
+  c->cloud_n[LOAM_B200_C_REG_LESS_FLAT] = c->reg_totals[3];
+  return LOAM_B200_OK;
+}
+
+static const int* reg_dense_list(loam_b200_ctx* c, int which) {
+  const int slots = c->reg_slots.cap_sharp + c->reg_slots.cap_less + c->reg_slots.cap_flat;
+  const int* dense = c->reg_picks.p + (size_t)c->reg_n_rings * slots;
+  if (which == 1) return dense;
+  if (which == 2) return dense + (size_t)c->reg_n_rings * c->reg_slots.cap_sharp;
+  return dense + (size_t)c->reg_n_rings * (c->reg_slots.cap_sharp + c->reg_slots.cap_less);
+}
+
+int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const int32_t* ring_start,
+                               const int32_t* ring_end, int n_rings, const loam_b200_reg_params* prm,
+                               loam_b200_features* out) {
+  CHECK_CTX(c);
+  if (!pts || n < 0 || !ring_start || !ring_end || n_rings <= 0 || n_rings > 256 || !prm || !out)
+    return LOAM_B200_ERR_ARG;
+  out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
+  if (n > 0) {
+    LB_CUDA(c, c->reg_pts.reserve(n));
+    LB_CUDA(c, cudaMemcpyAsync(c->reg_pts.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  }
+  int rc = run_features(c, c->reg_pts.p, n, ring_start, ring_end, n_rings, prm);
+  if (rc) return rc;
+  if (n == 0) return LOAM_B200_OK;
+  const int* h_tot = c->reg_totals;
   out->n_sharp = h_tot[0];
   out->n_less_sharp = h_tot[1];
   out->n_flat = h_tot[2];
@@ -354,16 +394,15 @@ int loam_b200_extract_features(loam_b200_ctx* c, const float* pts, int n, const 
       (out->flat_idx && h_tot[2] > out->flat_cap) || (out->less_flat_ds && h_tot[3] > out->less_flat_cap))
     return LOAM_B200_ERR_CAPACITY;
   if (out->sharp_idx && h_tot[0])
-    LB_CUDA(c, cudaMemcpyAsync(out->sharp_idx, dense, h_tot[0] * 4, cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaMemcpyAsync(out->sharp_idx, reg_dense_list(c, 1), h_tot[0] * 4, cudaMemcpyDeviceToHost, c->stream));
   if (out->less_sharp_idx && h_tot[1])
-    LB_CUDA(c, cudaMemcpyAsync(out->less_sharp_idx, dense + (size_t)n_rings * fp.cap_sharp, h_tot[1] * 4,
-                               cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaMemcpyAsync(out->less_sharp_idx, reg_dense_list(c, 2), h_tot[1] * 4, cudaMemcpyDeviceToHost, c->stream));
   if (out->flat_idx && h_tot[2])
-    LB_CUDA(c, cudaMemcpyAsync(out->flat_idx, dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less), h_tot[2] * 4,
-                               cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaMemcpyAsync(out->flat_idx, reg_dense_list(c, 3), h_tot[2] * 4, cudaMemcpyDeviceToHost, c->stream));
   if (out->label) LB_CUDA(c, cudaMemcpyAsync(out->label, c->reg_label.p, n, cudaMemcpyDeviceToHost, c->stream));
   if (out->less_flat_ds && h_tot[3])
-    LB_CUDA(c, cudaMemcpyAsync(out->less_flat_ds, c->tmp_pts.p, (size_t)h_tot[3] * 16, cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaMemcpyAsync(out->less_flat_ds, c->cloud[LOAM_B200_C_REG_LESS_FLAT].p, (size_t)h_tot[3] * 16,
+                               cudaMemcpyDeviceToHost, c->stream));
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
   return LOAM_B200_OK;
 }
@@ -373,6 +412,7 @@ int loam_b200_tree_build(loam_b200_ctx* c, int slot, const float* pts, int m) {
   CHECK_CTX(c);
   if (slot < 0 || slot >= LOAM_B200_NUM_TREES || m < 0 || (m > 0 && !pts)) return LOAM_B200_ERR_ARG;
   Tree& t = c->tree[slot];
+  t.ext_pts = nullptr;
   int rc = upload_points(c, t.pts, pts, m);
   if (rc) return rc;
   prof_begin(c, LOAM_B200_K_TREE_BUILD);
@@ -546,7 +586,7 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
     LB_CUDA(c, c->dbg_sel.reserve(nsh + nfl));
   }
   prof_begin(c, LOAM_B200_K_ODOM_ITER);
-  odom_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.pts.p, ts.pts.p, c->od_q.p, nsh,
+  odom_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh,
                                                         nfl, cb, a, c->od_ind.p, c->partials.p, c->result.p,
                                                         c->ticket.p, dbg ? c->dbg_coeff.p : nullptr,
                                                         dbg ? c->dbg_sel.p : nullptr);
@@ -654,3 +694,5 @@ int loam_b200_profile_get(loam_b200_ctx* c, int family, double* gpu_ms, long lon
 long long loam_b200_launch_count(loam_b200_ctx* c) { return c ? c->launches : 0; }
 
 }  // extern "C"
+
+#include "stages.inc"

@@ -244,6 +244,59 @@ def test_pipeline_trajectory_vlp16(checker, scene, sweeps_vlp16, map_200k):
     assert abs(pg.mapping.cloud("surf_cubes").shape[0] - pc.mapping.cloud("surf_cubes").shape[0]) <= 5
 
 
+def test_hostcloud_chain_equals_fused_chain(scene, sweeps_vlp16, map_200k):
+    """The reference-style use of the three classes (host pcl clouds between them, processScanlines(vector<Cloud>))
+    and the fused device-resident chain are the same computation: identical poses, bit for bit."""
+    from loam_velodyne_b200 import api
+    corner, surf = map_200k
+    pa, pb = api.Pipeline(), api.Pipeline()
+    pa.seed_map(corner, surf)
+    pb.seed_map(corner, surf)
+    for i, (pts, rs) in enumerate(sweeps_vlp16[:5]):
+        _, od_a, aft_a, _ = pa.sweep(pts, rs, mode="fused")
+        _, od_b, aft_b, _ = pb.sweep(pts, rs, mode="hostclouds")
+        np.testing.assert_array_equal(od_a, od_b)
+        np.testing.assert_array_equal(aft_a, aft_b)
+        np.testing.assert_array_equal(pa.odom.cloud("last_surf"), pb.odom.cloud("last_surf"))
+    np.testing.assert_array_equal(pa.mapping.cloud("surf_cubes"), pb.mapping.cloud("surf_cubes"))
+
+
+def test_device_resident_sweep_input(scene, sweeps_vlp16, map_200k):
+    """Sweeps handed over as device pointers give the same result as host buffers."""
+    import torch
+    from loam_velodyne_b200 import api
+    corner, surf = map_200k
+    pa, pb = api.Pipeline(), api.Pipeline()
+    pa.seed_map(corner, surf)
+    pb.seed_map(corner, surf)
+    for pts, rs in sweeps_vlp16[:3]:
+        t = torch.from_numpy(pts).cuda()
+        torch.cuda.synchronize()
+        _, od_a, aft_a, _ = pa.sweep(pts, rs)
+        _, od_b, aft_b, _ = pb.sweep_device(t.data_ptr(), rs)
+        np.testing.assert_array_equal(od_a, od_b)
+        np.testing.assert_array_equal(aft_a, aft_b)
+
+
+def test_map_grid_roll_and_drop(checker):
+    """Drive the sensor 130 m along x so the cube grid rolls and far cubes leave the 5x5x5 window; poses must keep
+    matching the oracle while the map is being shifted / dropped."""
+    from loam_velodyne_b200 import api, synth
+    sc = synth.make_scene(seed=3, extent=160.0)
+    lidar = synth.Lidar(16, 600, -15.0, 15.0)
+    corner, surf = synth.make_map(sc, 150_000, window=150.0)
+    pg, pc = api.Pipeline(), checker.pipeline()
+    pg.seed_map(corner, surf)
+    pc.seed_map(corner, surf)
+    # 30 m/s for 45 sweeps = 135 m: crosses two cube boundaries (the grid keeps the sensor >= 3 cubes from its faces)
+    for i in range(45):
+        pts, rs = synth.make_sweep(sc, lidar, i, v=(30.0, 0.0, 0.0), yaw_rate=0.0)
+        _, od_g, aft_g, _ = pg.sweep(pts, rs)
+        _, od_c, aft_c, _ = pc.sweep(pts, rs)
+        assert np.abs(aft_g - aft_c).max() <= 2e-3, (i, aft_g, aft_c)  # fast motion, coarse map: looser than POSE_TOL
+    assert abs(pg.mapping.cloud("corner_from_map").shape[0] - pc.mapping.cloud("corner_from_map").shape[0]) <= 3
+
+
 def test_golden_pipeline_on_gpu():
     """The committed golden vectors (recorded from the compiled reference) against the CUDA path."""
     from loam_velodyne_b200 import api
