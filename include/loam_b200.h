@@ -243,6 +243,8 @@ int loam_b200_profile_reset(loam_b200_ctx* ctx);
 int loam_b200_profile_get(loam_b200_ctx* ctx, int family, double* gpu_ms, long long* launches);
 /* total kernel launches issued by this context since creation */
 long long loam_b200_launch_count(loam_b200_ctx* ctx);
+/* ... by every context of this process */
+long long loam_b200_total_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -128,6 +128,7 @@ def lib():
         "loam_b200_profile_reset": (C.c_int, [vp]),
         "loam_b200_profile_get": (C.c_int, [vp, C.c_int, _D, C.POINTER(C.c_longlong)]),
         "loam_b200_launch_count": (C.c_longlong, [vp]),
+        "loam_b200_total_launch_count": (C.c_longlong, []),
         # host handles
         "loam_b200_host_last_error": (C.c_char_p, []),
         "loam_b200_host_set_device": (None, [C.c_int]),

@@ -206,9 +206,12 @@ inline int fail_cuda(loam_b200_ctx* c, cudaError_t e, const char* what, int line
     if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, #expr, __LINE__); \
   } while (0)
 
+extern long long g_total_launches;
+
 #define LB_LAUNCH_CHECK(ctx)                                                            \
   do {                                                                                  \
     (ctx)->launches++;                                                                  \
+    loamb::g_total_launches++;                                                          \
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, "kernel launch", __LINE__); \
   } while (0)

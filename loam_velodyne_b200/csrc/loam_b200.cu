@@ -12,6 +12,10 @@
 
 using namespace loamb;
 
+namespace loamb {
+long long g_total_launches = 0;
+}
+
 #define CHECK_CTX(c) \
   if (!(c)) return LOAM_B200_ERR_ARG
 
@@ -692,6 +696,7 @@ int loam_b200_profile_get(loam_b200_ctx* c, int family, double* gpu_ms, long lon
   return LOAM_B200_OK;
 }
 long long loam_b200_launch_count(loam_b200_ctx* c) { return c ? c->launches : 0; }
+long long loam_b200_total_launch_count(void) { return loamb::g_total_launches; }
 
 }  // extern "C"
 
