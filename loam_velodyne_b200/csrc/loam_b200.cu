@@ -590,6 +590,12 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
     LB_CUDA(c, c->dbg_sel.reserve(nsh + nfl));
   }
   prof_begin(c, LOAM_B200_K_ODOM_ITER);
+  if (pose->iter % 5 == 0) {
+    const int warps = nsh + nfl;
+    odom_search_kernel<<<blocks_for((long long)warps * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
+        view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, a, c->od_ind.p);
+    LB_LAUNCH_CHECK(c);
+  }
   odom_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh,
                                                         nfl, cb, a, c->od_ind.p, c->partials.p, c->result.p,
                                                         c->ticket.p, dbg ? c->dbg_coeff.p : nullptr,

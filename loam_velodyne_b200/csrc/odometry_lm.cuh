@@ -75,6 +75,122 @@ __device__ __forceinline__ float sqdiff3(const float4& a, float bx, float by, fl
   return dx * dx + dy * dy + dz * dz;
 }
 
+// ---- correspondence search, every 5th iteration (BasicLaserOdometry.cpp:250-302, :368-435): one WARP per feature
+// point.  Lane 0 walks the BVH for the closest point (d^2 < 25 gate); then the whole warp scans the ring-ordered last
+// cloud forwards and backwards 32 candidates at a time.  The reference's sequential loops are reproduced exactly:
+// a chunk stops at the first candidate that trips the ring `break` (ballot + ffs), candidates are compared by
+// (distance, scan order) so the strict `<` updates of the serial loop pick the same index, and the forward loops
+// keep the reference's bound by the CURRENT feature count (:262, :378).
+struct ScanBest {
+  float d;
+  int ord;  // position in the reference's visiting order (forward first, then backward)
+  int idx;
+};
+// candidate of the serial loop `if (d < best) { best = d; idx = j; }` with best starting at 25: only d < 25 can ever
+// win, and among equal distances the one visited first
+__device__ __forceinline__ void scan_best_min(ScanBest& a, float d, int ord, int idx) {
+  if (d < 25.f && (d < a.d || (d == a.d && ord < a.ord))) { a.d = d; a.ord = ord; a.idx = idx; }
+}
+__device__ __forceinline__ void scan_best_warp(ScanBest& a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float d = __shfl_xor_sync(0xffffffffu, a.d, o);
+    const int ord = __shfl_xor_sync(0xffffffffu, a.ord, o);
+    const int idx = __shfl_xor_sync(0xffffffffu, a.idx, o);
+    scan_best_min(a, d, ord, idx);
+  }
+}
+
+__global__ void __launch_bounds__(LM_THREADS)
+odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
+                   const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
+                   OdomIterArgs a, int* __restrict__ ind) {
+  const int lane = threadIdx.x & 31;
+  const int qi = (blockIdx.x * LM_THREADS + threadIdx.x) >> 5;  // one warp per query
+  if (qi >= n_sharp + n_flat) return;
+  const bool is_corner = qi < n_sharp;
+  const float4* last = is_corner ? last_corner : last_surf;
+  const int n_last = is_corner ? a.n_last_corner : a.n_last_surf;
+  const float4 po = queries[qi];
+  float sx, sy, sz;
+  transform_to_start(a, po, sx, sy, sz);  // every lane evaluates the same values
+  int i1 = -1;
+  if (lane == 0) {
+    KnnResult<1> nn;
+    knn_walk<1>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 25.0f, nn);
+    i1 = nn.idx[0];
+  }
+  i1 = __shfl_sync(0xffffffffu, i1, 0);
+  int i2 = -1, i3 = -1;
+  if (i1 >= 0) {
+    const int scan = (int)last[i1].w;
+    ScanBest b2{25.f, 0x7fffffff, -1}, b3{25.f, 0x7fffffff, -1};
+    int ord = 0;
+    // forward: j = i1 + 1 .. fend - 1 while ring <= scan + 2.5
+    const int fend = min(is_corner ? n_sharp : n_flat, n_last);
+    for (int j0 = i1 + 1; j0 < fend; j0 += 32) {
+      const int j = j0 + lane;
+      bool brk = false;
+      float d = 0.f;
+      int r = 0;
+      if (j < fend) {
+        const float4 p = last[j];
+        r = (int)p.w;
+        brk = (double)r > (double)scan + 2.5;
+        d = sqdiff3(p, sx, sy, sz);
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, brk);
+      const int stop = bm ? __ffs(bm) - 1 : 32;
+      if (j < fend && lane < stop) {
+        if (is_corner) {
+          if (r > scan) scan_best_min(b2, d, ord + lane, j);
+        } else {
+          if (r <= scan) scan_best_min(b2, d, ord + lane, j);
+          else scan_best_min(b3, d, ord + lane, j);
+        }
+      }
+      ord += 32;
+      if (bm) break;
+    }
+    // backward: j = i1 - 1 .. 0 while ring >= scan - 2.5
+    for (int j0 = i1 - 1; j0 >= 0; j0 -= 32) {
+      const int j = j0 - lane;
+      bool brk = false;
+      float d = 0.f;
+      int r = 0;
+      if (j >= 0) {
+        const float4 p = last[j];
+        r = (int)p.w;
+        brk = (double)r < (double)scan - 2.5;
+        d = sqdiff3(p, sx, sy, sz);
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, brk);
+      const int stop = bm ? __ffs(bm) - 1 : 32;
+      if (j >= 0 && lane < stop) {
+        if (is_corner) {
+          if (r < scan) scan_best_min(b2, d, ord + lane, j);
+        } else {
+          if (r >= scan) scan_best_min(b2, d, ord + lane, j);
+          else scan_best_min(b3, d, ord + lane, j);
+        }
+      }
+      ord += 32;
+      if (bm) break;
+    }
+    scan_best_warp(b2);
+    i2 = b2.idx;
+    if (!is_corner) {
+      scan_best_warp(b3);
+      i3 = b3.idx;
+    }
+  }
+  if (lane == 0) {
+    ind[qi * 3 + 0] = i1;
+    ind[qi * 3 + 1] = i2;
+    ind[qi * 3 + 2] = i3;
+  }
+}
+
 __global__ void __launch_bounds__(LM_THREADS)
 odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
                     const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
@@ -94,70 +210,8 @@ odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __re
     const float4 po = queries[qi];
     float sx, sy, sz;
     transform_to_start(a, po, sx, sy, sz);
-    int i1, i2, i3 = -1;
-    if (a.iter % 5 == 0) {
-      KnnResult<1> nn;
-      knn_walk<1>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 25.0f, nn);
-      i1 = nn.idx[0];
-      i2 = -1;
-      if (is_corner) {
-        if (i1 >= 0) {
-          const int scan = (int)last_corner[i1].w;
-          float min2 = 25.f;
-          // forward scan bounded by the CURRENT sharp count (BasicLaserOdometry.cpp:262), clamped to the cloud
-          const int fend = min(n_sharp, a.n_last_corner);
-          for (int j = i1 + 1; j < fend; j++) {
-            const float4 p = last_corner[j];
-            const int r = (int)p.w;
-            if ((double)r > (double)scan + 2.5) break;
-            const float d = sqdiff3(p, sx, sy, sz);
-            if (r > scan && d < min2) { min2 = d; i2 = j; }
-          }
-          for (int j = i1 - 1; j >= 0; j--) {
-            const float4 p = last_corner[j];
-            const int r = (int)p.w;
-            if ((double)r < (double)scan - 2.5) break;
-            const float d = sqdiff3(p, sx, sy, sz);
-            if (r < scan && d < min2) { min2 = d; i2 = j; }
-          }
-        }
-      } else {
-        if (i1 >= 0) {
-          const int scan = (int)last_surf[i1].w;
-          float min2 = 25.f, min3 = 25.f;
-          const int fend = min(n_flat, a.n_last_surf);  // :378
-          for (int j = i1 + 1; j < fend; j++) {
-            const float4 p = last_surf[j];
-            const int r = (int)p.w;
-            if ((double)r > (double)scan + 2.5) break;
-            const float d = sqdiff3(p, sx, sy, sz);
-            if (r <= scan) {
-              if (d < min2) { min2 = d; i2 = j; }
-            } else {
-              if (d < min3) { min3 = d; i3 = j; }
-            }
-          }
-          for (int j = i1 - 1; j >= 0; j--) {
-            const float4 p = last_surf[j];
-            const int r = (int)p.w;
-            if ((double)r < (double)scan - 2.5) break;
-            const float d = sqdiff3(p, sx, sy, sz);
-            if (r >= scan) {
-              if (d < min2) { min2 = d; i2 = j; }
-            } else {
-              if (d < min3) { min3 = d; i3 = j; }
-            }
-          }
-        }
-      }
-      ind[qi * 3 + 0] = i1;
-      ind[qi * 3 + 1] = i2;
-      ind[qi * 3 + 2] = i3;
-    } else {
-      i1 = ind[qi * 3 + 0];
-      i2 = ind[qi * 3 + 1];
-      i3 = ind[qi * 3 + 2];
-    }
+    // correspondences of the last search iteration (odom_search_kernel)
+    const int i1 = ind[qi * 3 + 0], i2 = ind[qi * 3 + 1], i3 = ind[qi * 3 + 2];
 
     float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
     bool sel = false;
