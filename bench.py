@@ -212,7 +212,7 @@ def kernel_roofline(args, api, corner, surf, sweep, pipe):
     ctx.tree_build(api.TREE_MAP_CORNER, cm)
     ctx.tree_build(api.TREE_MAP_SURF, sm)
     ctx.map_set_queries(cq, sq)
-    _, nodes, leaves = ctx.map_iterate_stats(twist)
+    _, probes, cands = ctx.map_iterate_stats(twist)
     nq = cq.shape[0] + sq.shape[0]
     for _ in range(5):
         ctx.map_iterate(twist)
@@ -222,8 +222,9 @@ def kernel_roofline(args, api, corner, surf, sweep, pipe):
         ctx.map_iterate(twist)
     ms, n = ctx.profile_get()["map_iter"]
     ctx.profile(False)
-    # algorithmic bytes per launch: Q * 16 + nodes * 64 + leaves * LEAF(8) * 16 + 36 * 4
-    alg_bytes = nq * 16 + nodes * 64 + leaves * 8 * 16 + 36 * 4
+    # algorithmic bytes per launch (DESIGN.md "Roofline"): every query reads itself (16 B), its 27 cell-table entries
+    # (16 B each, counted as probed) and every candidate point of the occupied cells (16 B each); the 36-float result
+    alg_bytes = nq * 16 + probes * 16 + cands * 16 + 36 * 4
     dur_s = ms / n * 1e-3
     peak, how = measure_peaks()
     achieved = alg_bytes / dur_s / 1e9
@@ -231,11 +232,11 @@ def kernel_roofline(args, api, corner, surf, sweep, pipe):
     # here (three private contexts); the kernel ABI context exposes its own launch counter instead
     launches_per_sweep = estimate_launches(api, pipe)
     ctx.close()
-    return ({"bound": "hbm", "kernel": "map_iterate_kernel (fused 5-NN walk + line/plane fit + Jacobian + 6x6 reduction)",
+    return ({"bound": "hbm", "kernel": "map_iterate_kernel (fused fixed-radius 5-NN + line/plane fit + Jacobian + 6x6 reduction)",
              "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
              "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes),
-             "avg_launch_us": round(dur_s * 1e6, 2), "queries": int(nq), "nodes_per_query": round(nodes / max(nq, 1), 2),
-             "leaves_per_query": round(leaves / max(nq, 1), 2),
+             "avg_launch_us": round(dur_s * 1e6, 2), "queries": int(nq), "table_probes_per_query": round(probes / max(nq, 1), 2),
+             "candidate_points_per_query": round(cands / max(nq, 1), 2),
              "note": "1M-pt map + nodes fit in the 126 MB L2, so DRAM traffic is structurally far below the algorithmic bytes"},
             launches_per_sweep)
 

@@ -127,10 +127,11 @@ int loam_b200_map_iterate(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b
 int loam_b200_map_iterate_debug(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b200_normal_eq* out,
                                 float* coeff, int8_t* selected);
 
-/* instrumented variant: same result plus the number of BVH nodes / leaves the 5-NN walks visited in this launch
- * (feeds the algorithmic-bytes figure of the roofline); slower, never used on the timed path */
+/* instrumented variant: same result plus the number of grid-table probes (16 B each) and candidate map points (16 B
+ * each) the 5-NN searches of this launch read (feeds the algorithmic-bytes figure of the roofline); slower, never
+ * used on the timed path */
 int loam_b200_map_iterate_stats(loam_b200_ctx* ctx, const loam_b200_pose* pose, loam_b200_normal_eq* out,
-                                unsigned long long* nodes_visited, unsigned long long* leaves_visited);
+                                unsigned long long* table_probes, unsigned long long* candidate_points);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Scan-to-scan Gauss-Newton iteration: replaces the body of the iteration loop of BasicLaserOdometry::process up to

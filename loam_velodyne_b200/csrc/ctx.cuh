@@ -107,6 +107,15 @@ struct Tree {
 struct FeatSlots { int cap_sharp = 0, cap_less = 0, cap_flat = 0; };
 struct CubeGridHost { int cen_w = 10, cen_h = 5, cen_d = 10; };
 
+struct GridMetaHost { int v[6]; };
+struct Grid {            // uniform 1 m grid over a map cloud (gridnn.cuh)
+  int m = 0;
+  unsigned mask = 0;
+  DevBuf<uint4> table;
+  DevBuf<float4> sorted;
+  DevBuf<GridMetaHost> meta;
+};
+
 struct SortScratch {
   DevBuf<uint32_t> keys_a, keys_b;
   DevBuf<int> vals_a, vals_b;
@@ -142,6 +151,7 @@ struct loam_b200_ctx {
 
   // trees
   loamb::Tree tree[LOAM_B200_NUM_TREES];
+  loamb::Grid grid[2];  // corner / surface surrounding map
   loamb::SortScratch sort;
   loamb::DevBuf<float> bbox;  // 6 floats (encoded) for the tree build
   loamb::DevBuf<float4> knn_q;

@@ -1,0 +1,172 @@
+// Fixed-radius exact 5-NN for the scan-to-map loop.
+//
+// The reference only uses a map correspondence when the 5th neighbour is closer than 1 m
+// (pointSearchSqDis[4] < 1.0, BasicLaserMapping.cpp:671,760), so the search is a fixed-radius query: every accepted
+// neighbour lies in the 3 x 3 x 3 block of 1 m cells around the query.  The ncu profile of the BVH walk on this
+// workload (profiles/r1_v2_map_iterate_bvh.md) shows ~48 dependent node visits per query at 5.6 / 32 active lanes;
+// a Morton-free uniform grid removes both the dependency chain and the divergence:
+//   build : cell key (z, y, x) per point -> LSD radix sort -> points gathered in cell order (xyz + original index) ->
+//           open-addressing table cell -> (start, count)
+//   query : 27 independent table probes (issued nine at a time), then the candidates of each occupied cell, four
+//           loads in flight; a candidate enters the running top-5 only when strictly closer than the current 5th
+//           (nanoflann's KNNResultSet::addPoint, nanoflann.hpp:115-139), distances accumulate x -> y -> z in fp32
+//           exactly like L2_Simple_Adaptor::evalMetric (nanoflann.hpp:372-379).
+// Cell coordinates are floorf(x) - origin with an INTEGER origin, so |p - q| < 1 implies the two cell indices differ
+// by at most one per axis exactly (no subtraction rounding) and the 27-cell candidate set is a true superset.
+// The general-radius searches (odometry 1-NN within 5 m, loam_b200_tree_knn) keep the BVH of lbvh.cuh.
+#pragma once
+
+#include "lbvh.cuh"
+
+namespace loamb {
+
+struct GridMeta {       // written by grid_meta_kernel, read by every later kernel (no host round trip)
+  int ox, oy, oz;       // integer origin = floor(bbox min) - 1
+  int nx, ny, nz;       // cells per axis (clamped so the key fits 31 bits)
+};
+
+struct GridView {
+  const uint4* table;   // {key + 1 (0 = empty), start, count, -}
+  unsigned mask;        // table size - 1 (power of two)
+  const float4* sorted; // points in cell order, w = original index bits
+  const GridMeta* meta;
+  int m;
+};
+
+__device__ __forceinline__ unsigned grid_hash(unsigned k) {
+  k ^= k >> 16;
+  k *= 0x7feb352dU;
+  k ^= k >> 15;
+  k *= 0x846ca68bU;
+  k ^= k >> 16;
+  return k;
+}
+
+__global__ void grid_meta_kernel(const unsigned* __restrict__ bb, GridMeta* __restrict__ meta) {
+  if (threadIdx.x != 0) return;
+  const float lx = dec_f(bb[0]), ly = dec_f(bb[1]), lz = dec_f(bb[2]);
+  const float hx = dec_f(bb[3]), hy = dec_f(bb[4]), hz = dec_f(bb[5]);
+  GridMeta g;
+  g.ox = (int)floorf(lx) - 1;
+  g.oy = (int)floorf(ly) - 1;
+  g.oz = (int)floorf(lz) - 1;
+  g.nx = min(max((int)floorf(hx) - g.ox + 2, 1), 1290);
+  g.ny = min(max((int)floorf(hy) - g.oy + 2, 1), 1290);
+  g.nz = min(max((int)floorf(hz) - g.oz + 2, 1), 1290);
+  *meta = g;
+}
+
+__device__ __forceinline__ unsigned grid_key(const GridMeta& g, int cx, int cy, int cz) {
+  return (unsigned)((cz * g.ny + cy) * g.nx + cx);
+}
+
+__global__ void grid_key_kernel(const float4* __restrict__ p, int m, const GridMeta* __restrict__ meta,
+                                unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const GridMeta g = *meta;
+  const float4 q = p[i];
+  const int cx = min(max((int)floorf(q.x) - g.ox, 0), g.nx - 1);
+  const int cy = min(max((int)floorf(q.y) - g.oy, 0), g.ny - 1);
+  const int cz = min(max((int)floorf(q.z) - g.oz, 0), g.nz - 1);
+  keys[i] = grid_key(g, cx, cy, cz);
+  vals[i] = i;
+}
+
+// one thread per sorted point; run heads insert (key, start, count) with linear probing
+__global__ void grid_insert_kernel(const unsigned* __restrict__ keys, int m, uint4* __restrict__ table, unsigned mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned k = keys[i];
+  if (i > 0 && keys[i - 1] == k) return;
+  int cnt = 1;
+  while (i + cnt < m && keys[i + cnt] == k) cnt++;
+  unsigned h = grid_hash(k) & mask;
+  while (true) {
+    const unsigned prev = atomicCAS(&table[h].x, 0u, k + 1u);
+    if (prev == 0u) {
+      table[h].y = (unsigned)i;
+      table[h].z = (unsigned)cnt;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+struct Top5 {
+  float d[5], x[5], y[5], z[5];
+  int idx[5];
+};
+
+__device__ __forceinline__ void top5_offer(Top5& r, const float4& p, float qx, float qy, float qz) {
+  const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+  const float d = dx * dx + dy * dy + dz * dz;
+  if (d < r.d[4]) {
+    float cd = d, cx = p.x, cy = p.y, cz = p.z;
+    int ci = __float_as_int(p.w);
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+      if (cd < r.d[s]) {
+        const float td = r.d[s], tx = r.x[s], ty = r.y[s], tz = r.z[s];
+        const int ti = r.idx[s];
+        r.d[s] = cd; r.x[s] = cx; r.y[s] = cy; r.z[s] = cz; r.idx[s] = ci;
+        cd = td; cx = tx; cy = ty; cz = tz; ci = ti;
+      }
+    }
+  }
+}
+
+// Exact 5 nearest map points with d2 < 1.0 (idx[j] = -1 for missing ones).  stats[0] += table probes,
+// stats[1] += candidate points read (when STATS).
+template <bool STATS>
+__device__ __forceinline__ void grid_knn5(const GridView& g, float qx, float qy, float qz, Top5& r, unsigned* stats) {
+#pragma unroll
+  for (int i = 0; i < 5; i++) { r.d[i] = 1.0f; r.idx[i] = -1; r.x[i] = 0.f; r.y[i] = 0.f; r.z[i] = 0.f; }
+  if (g.m <= 0) return;
+  const GridMeta gm = *g.meta;
+  const int cx = (int)floorf(qx) - gm.ox, cy = (int)floorf(qy) - gm.oy, cz = (int)floorf(qz) - gm.oz;
+  // outside the occupied volume by more than one cell: nothing within 1 m
+  if (cx < -1 || cy < -1 || cz < -1 || cx > gm.nx || cy > gm.ny || cz > gm.nz) return;
+#pragma unroll 1
+  for (int dz = -1; dz <= 1; dz++) {
+    const int z = cz + dz;
+    if (z < 0 || z >= gm.nz) continue;
+    // nine probes of this z-slice in flight together
+    unsigned start[9], count[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int y = cy + (t / 3) - 1, x = cx + (t % 3) - 1;
+      count[t] = 0;
+      start[t] = 0;
+      if (y < 0 || y >= gm.ny || x < 0 || x >= gm.nx) continue;
+      const unsigned key = grid_key(gm, x, y, z);
+      unsigned h = grid_hash(key) & g.mask;
+      uint4 e = __ldg(&g.table[h]);
+      if (STATS) stats[0]++;
+      while (e.x != 0u && e.x != key + 1u) {  // collisions are rare at the table's load factor
+        h = (h + 1) & g.mask;
+        e = __ldg(&g.table[h]);
+        if (STATS) stats[0]++;
+      }
+      if (e.x == key + 1u) { start[t] = e.y; count[t] = e.z; }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const unsigned n = count[t];
+      const float4* src = g.sorted + start[t];
+      for (unsigned i = 0; i < n; i += 4) {
+        const float4 p0 = __ldg(src + i);
+        const float4 p1 = (i + 1 < n) ? __ldg(src + i + 1) : p0;
+        const float4 p2 = (i + 2 < n) ? __ldg(src + i + 2) : p0;
+        const float4 p3 = (i + 3 < n) ? __ldg(src + i + 3) : p0;
+        top5_offer(r, p0, qx, qy, qz);
+        if (i + 1 < n) top5_offer(r, p1, qx, qy, qz);
+        if (i + 2 < n) top5_offer(r, p2, qx, qy, qz);
+        if (i + 3 < n) top5_offer(r, p3, qx, qy, qz);
+      }
+      if (STATS) stats[1] += n;
+    }
+  }
+}
+
+}  // namespace loamb

@@ -33,15 +33,16 @@ TreeView view_of(const Tree& t) {
   return v;
 }
 
-// radix sort (keys, vals) of length m in ctx->sort; result ends in keys_a / vals_a (4 passes = even)
-int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits) {
+// radix sort (keys, vals) of length m in ctx->sort (input in keys_a / vals_a); 8 bits per pass.  The sorted arrays are
+// returned through keys_out / vals_out (buffer a after an even number of passes, b after an odd one).
+int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr) {
   SortScratch& s = c->sort;
   const int n_tiles = blocks_for(m, RS_TILE);
   LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles));
   unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
   int *va = s.vals_a.p, *vb = s.vals_b.p;
   int passes = (key_bits + 7) / 8;
-  if (passes & 1) passes++;  // keep the result in buffer a
+  if (!keys_out && (passes & 1)) passes++;  // callers that read buffer a directly need an even count
   for (int p = 0; p < passes; p++) {
     const int shift = p * 8;
     radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, shift, s.hist.p, n_tiles);
@@ -53,6 +54,57 @@ int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits) {
     unsigned* tk = ka; ka = kb; kb = tk;
     int* tv = va; va = vb; vb = tv;
   }
+  if (keys_out) *keys_out = ka;
+  if (vals_out) *vals_out = va;
+  return LOAM_B200_OK;
+}
+
+GridView grid_view_of(const Grid& g) {
+  GridView v;
+  v.table = g.table.p;
+  v.mask = g.mask;
+  v.sorted = g.sorted.p;
+  v.meta = reinterpret_cast<const GridMeta*>(g.meta.p);
+  v.m = g.m;
+  return v;
+}
+
+// 1 m uniform grid over d_pts (m points): the search structure of the scan-to-map loop (gridnn.cuh)
+int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m) {
+  g.m = m;
+  if (m <= 0) return LOAM_B200_OK;
+  SortScratch& s = c->sort;
+  LB_CUDA(c, s.keys_a.reserve(m));
+  LB_CUDA(c, s.keys_b.reserve(m));
+  LB_CUDA(c, s.vals_a.reserve(m));
+  LB_CUDA(c, s.vals_b.reserve(m));
+  LB_CUDA(c, c->bbox.reserve(8));
+  LB_CUDA(c, g.sorted.reserve(m));
+  LB_CUDA(c, g.meta.reserve(1));
+  size_t tsize = 1024;
+  while (tsize < (size_t)m) tsize <<= 1;  // load factor = occupied cells / table <= 1, typically ~0.15
+  LB_CUDA(c, g.table.reserve(tsize));
+  g.mask = (unsigned)(tsize - 1);
+  LB_CUDA(c, cudaMemsetAsync(g.table.p, 0, tsize * sizeof(uint4), c->stream));
+  unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
+  GridMeta* meta = reinterpret_cast<GridMeta*>(g.meta.p);
+  bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
+  LB_LAUNCH_CHECK(c);
+  const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 8);
+  bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(d_pts, m, bb);
+  LB_LAUNCH_CHECK(c);
+  grid_meta_kernel<<<1, 32, 0, c->stream>>>(bb, meta);
+  LB_LAUNCH_CHECK(c);
+  grid_key_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, m, meta, s.keys_a.p, s.vals_a.p);
+  LB_LAUNCH_CHECK(c);
+  unsigned* keys = nullptr;
+  int* vals = nullptr;
+  int rc = radix_sort_pairs(c, m, 32, &keys, &vals);  // keys < 1290^3 < 2^31
+  if (rc) return rc;
+  gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, vals, m, g.sorted.p);
+  LB_LAUNCH_CHECK(c);
+  grid_insert_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(keys, m, g.table.p, g.mask);
+  LB_LAUNCH_CHECK(c);
   return LOAM_B200_OK;
 }
 
@@ -265,6 +317,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   c->bbox.release(); c->knn_q.release(); c->knn_idx.release(); c->knn_d2.release();
   c->map_q.release(); c->partials.release(); c->result.release(); c->ticket.release(); c->walk_totals.release();
   for (auto& cl : c->cloud) cl.release();
+  for (auto& g : c->grid) { g.table.release(); g.sorted.release(); g.meta.release(); }
   c->pool_cls[0].release(); c->pool_cls[1].release(); c->rank_of_cube.release(); c->pool_tmp.release();
   c->pool_tmp_cls.release(); c->cmp_pos.release(); c->cmp_bsum.release();
   if (c->ev_xfer) cudaEventDestroy(c->ev_xfer); c->dbg_coeff.release();
@@ -421,6 +474,9 @@ int loam_b200_tree_build(loam_b200_ctx* c, int slot, const float* pts, int m) {
   if (rc) return rc;
   prof_begin(c, LOAM_B200_K_TREE_BUILD);
   rc = tree_build_device(c, t, m);
+  // the scan-to-map kernels search the two map slots through the 1 m grid
+  if (rc == LOAM_B200_OK && slot >= LOAM_B200_TREE_MAP_CORNER)
+    rc = grid_build_device(c, c->grid[slot - LOAM_B200_TREE_MAP_CORNER], t.points(), m);
   prof_end(c);
   if (rc) return rc;
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -498,7 +554,7 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     LB_CUDA(c, c->walk_totals.reserve(2));
     LB_CUDA(c, cudaMemsetAsync(c->walk_totals.p, 0, 2 * sizeof(unsigned long long), c->stream));
     map_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(
-        view_of(c->tree[LOAM_B200_TREE_MAP_CORNER]), view_of(c->tree[LOAM_B200_TREE_MAP_SURF]), c->map_q.p, nc, ns, cb,
+        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, ns, cb,
         a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
     LB_LAUNCH_CHECK(c);
     LB_CUDA(c, cudaMemcpyAsync(walk_totals_host, c->walk_totals.p, 2 * sizeof(unsigned long long),
@@ -506,7 +562,7 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   } else {
     prof_begin(c, LOAM_B200_K_MAP_ITER);
     map_iterate_kernel<false><<<nb, LM_THREADS, 0, c->stream>>>(
-        view_of(c->tree[LOAM_B200_TREE_MAP_CORNER]), view_of(c->tree[LOAM_B200_TREE_MAP_SURF]), c->map_q.p, nc, ns, cb,
+        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, ns, cb,
         a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
         nullptr);
     LB_LAUNCH_CHECK(c);

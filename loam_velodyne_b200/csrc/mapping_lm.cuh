@@ -1,11 +1,13 @@
 // Fused scan-to-map Gauss-Newton iteration.
-// One thread per stack point: pointAssociateToMap (BasicLaserMapping.cpp:207-219) -> 5-NN against the corner /
-// surface map BVH with the d5^2 < 1.0 gate folded into the walk (:669-671, :758-760) -> PCA line fit (:673-710) or
+// One thread per stack point: pointAssociateToMap (BasicLaserMapping.cpp:207-219) -> exact 5-NN against the corner /
+// surface map through the 1 m uniform grid of gridnn.cuh, the d5^2 < 1.0 gate (:669-671, :758-760) being what makes
+// the fixed-radius search exact -> PCA line fit (:673-710) or
 // 5x3 least-squares plane fit (:762-791) -> residual weight (:712-749, :795-814) -> Jacobian row (:842-861) ->
 // warp-shuffle tree reduction of the 21 + 6 normal-equation accumulators (+ counts), one partial per CTA,
 // combined in fixed order by the last CTA to finish (deterministic run to run).
 #pragma once
 
+#include "gridnn.cuh"
 #include "lbvh.cuh"
 #include "linalg.cuh"
 
@@ -48,7 +50,8 @@ __device__ __forceinline__ void line_residual(float x0, float y0, float z0, floa
 }
 
 // corner correspondence (:671-751). Returns true when the point is selected; coeff = (s*la, s*lb, s*lc, s*ld2)
-__device__ __forceinline__ bool corner_fit(const KnnResult<5>& nn, float sx, float sy, float sz, float4& coeff) {
+template <typename NN>
+__device__ __forceinline__ bool corner_fit(const NN& nn, float sx, float sy, float sz, float4& coeff) {
   if (nn.idx[4] < 0) return false;  // fewer than five map points with d2 < 1.0  <=>  pointSearchSqDis[4] >= 1.0
   float vx = 0.f, vy = 0.f, vz = 0.f;
 #pragma unroll
@@ -86,7 +89,8 @@ __device__ __forceinline__ bool corner_fit(const KnnResult<5>& nn, float sx, flo
 }
 
 // surface correspondence (:760-816)
-__device__ __forceinline__ bool surf_fit(const KnnResult<5>& nn, float sx, float sy, float sz, float4& coeff) {
+template <typename NN>
+__device__ __forceinline__ bool surf_fit(const NN& nn, float sx, float sy, float sz, float4& coeff) {
   if (nn.idx[4] < 0) return false;
   float A[15], b[5], x[3];
 #pragma unroll
@@ -160,7 +164,7 @@ __device__ __forceinline__ void reduce_normal_equations(float* acc, float* __res
 
 template <bool STATS>
 __global__ void __launch_bounds__(LM_THREADS)
-map_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ queries, int n_corner,
+map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __restrict__ queries, int n_corner,
                    int n_surf, int corner_blocks, MapIterArgs a, float* __restrict__ partials,
                    float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
                    int8_t* __restrict__ dbg_sel, unsigned long long* __restrict__ walk_totals) {
@@ -177,9 +181,9 @@ map_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
     const float4 po = queries[qi];
     float sx, sy, sz;
     associate_to_map(a, po, sx, sy, sz);
-    KnnResult<5> nn;
+    Top5 nn;
     unsigned ws[2] = {0u, 0u};
-    knn_walk<5, STATS>(is_corner ? corner_tree : surf_tree, sx, sy, sz, 1.0f, nn, ws);
+    grid_knn5<STATS>(is_corner ? corner_grid : surf_grid, sx, sy, sz, nn, ws);
     if (STATS) {
       atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
       atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
