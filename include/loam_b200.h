@@ -234,6 +234,18 @@ int loam_b200_map_end_sweep(loam_b200_ctx* ctx, const loam_b200_pose* optimised)
 int loam_b200_map_surround(loam_b200_ctx* ctx, const int cen[3], const int32_t* surround_cubes, int n, float leaf);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  With a shard set, loam_b200_map_iterate evaluates this rank's contiguous slice
+ * of the corner and surface queries; with a communicator the 32-float partial normal equations are all-reduced
+ * (NCCL, sum, fp32) on the context's stream directly behind the kernel, so every rank returns the same totals and
+ * runs the same 6x6 solve.  rank 0 creates the id, the caller distributes it (torch.distributed, MPI, a file, ...).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int loam_b200_comm_unique_id(unsigned char out[128]);
+int loam_b200_comm_init(loam_b200_ctx* ctx, int rank, int world, const unsigned char id[128]);
+int loam_b200_comm_destroy(loam_b200_ctx* ctx);
+/* slice only, no collective: loam_b200_map_iterate returns PARTIAL sums for the caller to reduce */
+int loam_b200_map_set_shard(loam_b200_ctx* ctx, int rank, int world);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Kernel timing (CUDA events on the context's stream) for bench.py's roofline: accumulated GPU milliseconds and
  * launch counts per kernel family since the last reset.
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -124,6 +124,10 @@ def lib():
         "loam_b200_map_begin_sweep": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(MapWindow), _I]),
         "loam_b200_map_end_sweep": (C.c_int, [vp, C.POINTER(Pose)]),
         "loam_b200_map_surround": (C.c_int, [vp, _I, _I, C.c_int, C.c_float]),
+        "loam_b200_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+        "loam_b200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
+        "loam_b200_comm_destroy": (C.c_int, [vp]),
+        "loam_b200_map_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
         "loam_b200_profile_enable": (C.c_int, [vp, C.c_int]),
         "loam_b200_profile_reset": (C.c_int, [vp]),
         "loam_b200_profile_get": (C.c_int, [vp, C.c_int, _D, C.POINTER(C.c_longlong)]),
@@ -159,6 +163,8 @@ def lib():
         "loam_b200_map_cloud_size": (C.c_int, [vp, C.c_int]),
         "loam_b200_map_cloud_copy": (C.c_int, [vp, C.c_int, _F]),
         "loam_b200_map_last_iterations": (C.c_int, [vp]),
+        "loam_b200_host_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+        "loam_b200_map_enable_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
         "loam_b200_pipeline_create": (vp, [C.c_float, C.c_int, C.c_int]),
         "loam_b200_pipeline_destroy": (None, [vp]),
         "loam_b200_pipeline_seed_map": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
@@ -280,6 +286,9 @@ class Ctx:
         self._ck(self.L.loam_b200_tree_knn(self.h, slot, _fp(q), q.shape[0], k, np.float32(max_d2), _ip(idx), _fp(d2)),
                  "tree_knn")
         return idx, d2
+
+    def map_set_shard(self, rank, world):
+        self._ck(self.L.loam_b200_map_set_shard(self.h, rank, world), "map_set_shard")
 
     def map_set_queries(self, corner, surf):
         c, s = _pts(corner), _pts(surf)
@@ -504,6 +513,15 @@ class LaserMapping(_Handle):
     def last_iterations(self):
         return self.L.loam_b200_map_last_iterations(self.h)
 
+    def enable_sharding(self, rank, world, nccl_id: bytes | None):
+        """Evaluate the rank-th of `world` query slices; with nccl_id (128 bytes, same on every rank) the normal
+        equations are all-reduced over NCCL each iteration."""
+        if nccl_id is None:
+            self._ck(self.L.loam_b200_map_enable_sharding(self.h, rank, world, None), "enableSharding")
+        else:
+            buf = (C.c_ubyte * 128).from_buffer_copy(nccl_id)
+            self._ck(self.L.loam_b200_map_enable_sharding(self.h, rank, world, buf), "enableSharding")
+
 
 class Pipeline(_Handle):
     """registration -> odometry -> mapping chained in-process on one sweep (SURVEY.md §8b "who calls it")."""
@@ -547,6 +565,19 @@ class Pipeline(_Handle):
                                                              _fp(odom), _fp(aft), st.ctypes.data_as(_D)),
                       "pipeline_sweep_device")
         return bool(ok), odom, aft, st
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id (call on rank 0, broadcast to the others)."""
+    buf = (C.c_ubyte * 128)()
+    if lib().loam_b200_host_nccl_unique_id(buf) != 0:
+        raise LoamB200Error(lib().loam_b200_host_last_error().decode())
+    return bytes(buf)
+
+
+def shard_slice(n: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of n queries evaluated by `rank` (mirror of map_iterate_impl in csrc/loam_b200.cu)."""
+    return n * rank // world, n * (rank + 1) // world
 
 
 def set_device(device: int):

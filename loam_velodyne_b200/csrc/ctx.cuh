@@ -139,6 +139,10 @@ struct loam_b200_ctx {
   int prof_family = -1;
   long long prof_launches_at_begin = 0;
 
+  // multi-GPU: query slice of this rank and the NCCL communicator (comm.inc)
+  void* comm = nullptr;
+  int shard_rank = 0, shard_world = 1;
+
   // scan registration
   loamb::DevBuf<float4> reg_pts;
   loamb::DevBuf<int> reg_ring_start, reg_ring_end;

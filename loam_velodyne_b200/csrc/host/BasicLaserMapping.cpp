@@ -50,6 +50,13 @@ pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::surfStackDS() const { 
 pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::cornerFromMap() const { return _c[M_CORNER_FROM_MAP].host(); }
 pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::surfFromMap() const { return _c[M_SURF_FROM_MAP].host(); }
 
+void BasicLaserMapping::enableSharding(int rank, int world, const unsigned char* ncclId) {
+  if (ncclId)
+    _gpu->check(loam_b200_comm_init(_gpu->get(), rank, world, ncclId), "loam_b200_comm_init");
+  else
+    _gpu->check(loam_b200_map_set_shard(_gpu->get(), rank, world), "loam_b200_map_set_shard");
+}
+
 void BasicLaserMapping::adopt(BasicLaserOdometry& odom) {
   static const int to[3] = {M_CORNER_LAST, M_SURF_LAST, M_FULL};
   for (int i = 0; i < 3; i++) {

@@ -208,6 +208,14 @@ void loam_b200_pipeline_destroy(void* h) { delete (PipeH*)h; }
 int loam_b200_pipeline_seed_map(void* h, const float* corner, int n_corner, const float* surf, int n_surf) {
   return loam_b200_map_seed(&((PipeH*)h)->map, corner, n_corner, surf, n_surf);
 }
+int loam_b200_host_nccl_unique_id(unsigned char* out128) {
+  const int rc = loam_b200_comm_unique_id(out128);
+  if (rc) g_err = std::string("loam_b200_comm_unique_id: ") + loam_b200_strerror(rc);
+  return rc;
+}
+int loam_b200_map_enable_sharding(void* h, int rank, int world, const unsigned char* nccl_id128) {
+  return guarded([&] { ((MapH*)h)->m.enableSharding(rank, world, nccl_id128); return 0; });
+}
 void* loam_b200_pipeline_scanreg(void* h) { return &((PipeH*)h)->reg; }
 void* loam_b200_pipeline_odom(void* h) { return &((PipeH*)h)->odom; }
 void* loam_b200_pipeline_map(void* h) { return &((PipeH*)h)->map; }

@@ -85,6 +85,10 @@ class BasicLaserMapping {
   // host round trip (LaserOdometry::publishResult -> LaserMapping::*Handler upstream)
   void adopt(BasicLaserOdometry& odom);
   b200::Context* deviceContext() { return _gpu; }
+  // multi-GPU (one process per GPU): this object evaluates the rank-th of `world` slices of the correspondences and
+  // all-reduces the 6x6 normal equations over NCCL every iteration (ncclId: 128 bytes from
+  // loam_b200_comm_unique_id on rank 0; nullptr = slice only, the caller reduces)
+  void enableSharding(int rank, int world, const unsigned char* ncclId);
 
  private:
   typedef pcl::PointCloud<pcl::PointXYZI> Cloud;

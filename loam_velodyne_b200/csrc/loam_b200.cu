@@ -243,6 +243,8 @@ int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
 
 }  // namespace
 
+#include "comm.inc"
+
 extern "C" {
 
 const char* loam_b200_strerror(int status) {
@@ -320,7 +322,8 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   for (auto& g : c->grid) { g.table.release(); g.sorted.release(); g.meta.release(); }
   c->pool_cls[0].release(); c->pool_cls[1].release(); c->rank_of_cube.release(); c->pool_tmp.release();
   c->pool_tmp_cls.release(); c->cmp_pos.release(); c->cmp_bsum.release();
-  if (c->ev_xfer) cudaEventDestroy(c->ev_xfer); c->dbg_coeff.release();
+  if (c->ev_xfer) cudaEventDestroy(c->ev_xfer);
+  if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -542,19 +545,28 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   if (nc + ns == 0) return LOAM_B200_OK;
   MapIterArgs a;
   fill_map_args(pose, a);
-  const int cb = blocks_for(nc, LM_THREADS), sb = blocks_for(ns, LM_THREADS);
-  const int nb = cb + sb;
+  // this rank's contiguous slice of each query kind (everything when not sharded)
+  const int W = c->shard_world, R = c->shard_rank;
+  const int c0 = (int)((long long)nc * R / W), c1 = (int)((long long)nc * (R + 1) / W);
+  const int s0 = (int)((long long)ns * R / W), s1 = (int)((long long)ns * (R + 1) / W);
+  const int lc = c1 - c0, ls = s1 - s0;
+  const int cb = blocks_for(lc, LM_THREADS), sb = blocks_for(ls, LM_THREADS);
+  const int nb = std::max(cb + sb, 1);
   LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
   const bool dbg = coeff != nullptr;
   if (dbg) {
     LB_CUDA(c, c->dbg_coeff.reserve(nc + ns));
     LB_CUDA(c, c->dbg_sel.reserve(nc + ns));
+    if (W > 1) {
+      LB_CUDA(c, cudaMemsetAsync(c->dbg_coeff.p, 0, (size_t)(nc + ns) * 16, c->stream));
+      LB_CUDA(c, cudaMemsetAsync(c->dbg_sel.p, 0, (size_t)(nc + ns), c->stream));
+    }
   }
   if (walk_totals_host) {
     LB_CUDA(c, c->walk_totals.reserve(2));
     LB_CUDA(c, cudaMemsetAsync(c->walk_totals.p, 0, 2 * sizeof(unsigned long long), c->stream));
     map_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(
-        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, ns, cb,
+        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, c0, lc, s0, ls, cb,
         a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
     LB_LAUNCH_CHECK(c);
     LB_CUDA(c, cudaMemcpyAsync(walk_totals_host, c->walk_totals.p, 2 * sizeof(unsigned long long),
@@ -562,11 +574,15 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   } else {
     prof_begin(c, LOAM_B200_K_MAP_ITER);
     map_iterate_kernel<false><<<nb, LM_THREADS, 0, c->stream>>>(
-        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, ns, cb,
+        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, c0, lc, s0, ls, cb,
         a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
         nullptr);
     LB_LAUNCH_CHECK(c);
     prof_end(c);
+  }
+  {
+    const int rcc = allreduce_result(c);  // no-op without a communicator
+    if (rcc) return rcc;
   }
   int rc = fetch_normal_eq(c, out);
   if (rc) return rc;

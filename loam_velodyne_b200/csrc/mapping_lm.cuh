@@ -164,8 +164,9 @@ __device__ __forceinline__ void reduce_normal_equations(float* acc, float* __res
 
 template <bool STATS>
 __global__ void __launch_bounds__(LM_THREADS)
-map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __restrict__ queries, int n_corner,
-                   int n_surf, int corner_blocks, MapIterArgs a, float* __restrict__ partials,
+map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __restrict__ queries, int n_corner_total,
+                   int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a,
+                   float* __restrict__ partials,
                    float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
                    int8_t* __restrict__ dbg_sel, unsigned long long* __restrict__ walk_totals) {
   float acc[29];
@@ -175,7 +176,8 @@ map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __res
   const bool is_corner = (int)blockIdx.x < corner_blocks;
   const int local = is_corner ? blockIdx.x * LM_THREADS + threadIdx.x
                               : (blockIdx.x - corner_blocks) * LM_THREADS + threadIdx.x;
-  const int qi = is_corner ? local : n_corner + local;
+  // this rank's slice: corners [c0, c0 + n_corner), surfaces [s0, s0 + n_surf) (the whole range on one GPU)
+  const int qi = is_corner ? c0 + local : n_corner_total + s0 + local;
   const bool active = is_corner ? (local < n_corner) : (local < n_surf);
   if (active) {
     const float4 po = queries[qi];

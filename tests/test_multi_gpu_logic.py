@@ -1,0 +1,90 @@
+"""Host-side logic of the multi-GPU path on CPU: two gloo ranks each evaluate their query slice of one scan-to-map
+iteration (through the oracle -- there is no GPU here), all-reduce the 32-float normal-equation message and must
+reproduce the unsharded normal equations.  Exercises the slice arithmetic the CUDA path uses (api.shard_slice mirrors
+map_iterate_impl) and the collective's message layout."""
+import math
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import math, os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch
+import torch.distributed as dist
+from loam_velodyne_b200 import api, synth
+from oracle import pydriver
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+orc = pydriver.load("restatement")
+scene = synth.make_scene()
+corner, surf = synth.make_map(scene, 60_000)
+pts, rs = synth.make_sweep(scene, synth.Lidar(16, 900, -15.0, 15.0), 4, yaw_rate=math.radians(5.0))
+s = orc.scanreg(); s.process(pts, rs)
+cq = orc.voxel_grid(s.cloud("less_sharp"), 0.2)
+sq = orc.voxel_grid(s.cloud("less_flat"), 0.4)
+pos, yaw = synth.pose_at(0.5, np.array([0.0, 0.0, 1.0]), math.radians(5.0))
+twist = np.array([0.0, yaw, 0.0, *pos], np.float32)
+full = pydriver.map_iteration(orc, corner, surf, cq, sq, twist)
+c0, c1 = api.shard_slice(cq.shape[0], rank, world)
+s0, s1 = api.shard_slice(sq.shape[0], rank, world)
+part = pydriver.map_iteration(orc, corner, surf, cq[c0:c1], sq[s0:s1], twist)
+# 36-float message: 21 upper-triangle AtA + 6 AtB + n_selected, padded (SURVEY.md 8e)
+msg = torch.zeros(36, dtype=torch.float32)
+iu = np.triu_indices(6)
+msg[:21] = torch.from_numpy(part["AtA"][iu])
+msg[21:27] = torch.from_numpy(part["AtB"])
+msg[27] = float(part["n_selected"])
+dist.all_reduce(msg, op=dist.ReduceOp.SUM)
+AtA = np.zeros((6, 6), np.float32); AtA[iu] = msg[:21].numpy(); AtA = AtA + AtA.T - np.diag(np.diag(AtA))
+rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+assert int(msg[27].item()) == full["n_selected"], (msg[27].item(), full["n_selected"])
+assert rel(AtA, full["AtA"]) < 1e-5, rel(AtA, full["AtA"])
+assert rel(msg[21:27].numpy(), full["AtB"]) < 1e-5
+# every rank holds the same reduced message -> identical solves
+gathered = [torch.zeros_like(msg) for _ in range(world)]
+dist.all_gather(gathered, msg)
+assert all(torch.equal(g, gathered[0]) for g in gathered)
+# the slices tile the query range exactly
+lo = [api.shard_slice(1001, r, world) for r in range(world)]
+assert lo[0][0] == 0 and lo[-1][1] == 1001 and all(lo[i][1] == lo[i + 1][0] for i in range(world - 1))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_sharded_normal_equations_gloo_world2(build_libs, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    port = _free_port()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
+
+
+def test_shard_slice_properties():
+    from loam_velodyne_b200 import api
+    for n in (0, 1, 7, 1138, 16535):
+        for world in (1, 2, 4, 8):
+            sl = [api.shard_slice(n, r, world) for r in range(world)]
+            assert sl[0][0] == 0 and sl[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+            sizes = [b - a for a, b in sl]
+            assert max(sizes) - min(sizes) <= 1
