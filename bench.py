@@ -113,7 +113,16 @@ def run_cuda(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     api.set_device(local_rank)
     n_total = args.warmup + args.steps
-    lidar, corner, surf, sweeps = make_workload(args.workload, n_total, rank)
+    sharded = world > 1 and args.mode == "sharded"
+    lidar, corner, surf, sweeps = make_workload(args.workload, n_total, 0 if sharded else rank)
+    nccl_id = None
+    if sharded:
+        nid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            nid = torch.tensor(list(api.nccl_unique_id()), dtype=torch.uint8, device=f"cuda:{local_rank}")
+        dist.broadcast(nid, 0)
+        nccl_id = bytes(nid.cpu().tolist())
+    streams = 1 if sharded else world  # independent sweep streams processed by the job
 
     def barrier():
         torch.cuda.synchronize()
@@ -147,22 +156,26 @@ def run_cuda(args, rank, world, local_rank):
     torch.cuda.synchronize()
     pipe_dev = api.Pipeline()
     pipe_dev.seed_map(corner, surf)
+    if sharded:
+        pipe_dev.mapping.enable_sharding(rank, world, nccl_id)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     el_dev, stage_dev, _, _, aft_dev = timed(lambda p, i: p.sweep_device(d_sweeps[i].data_ptr(), sweeps[i][1]), pipe_dev)
-    value = world * args.steps / el_dev
+    value = streams * args.steps / el_dev
     del pipe_dev
 
     # ---- arm 2 ("e2e"): host buffers through the reference-facing call, H2D of the sweep and D2H of the poses inside
     pipe = api.Pipeline()
     pipe.seed_map(corner, surf)
+    if sharded:
+        pipe.mapping.enable_sharding(rank, world, nccl_id)
     L = api.lib()
     launches_before = L.loam_b200_total_launch_count()
     elapsed, stage, iters_o, iters_m, aft_host = timed(lambda p, i: p.sweep(*sweeps[i]), pipe)
     launches_timed = L.loam_b200_total_launch_count() - launches_before
     clocks = sampler.stop() if rank == 0 else None
-    e2e_value = world * args.steps / elapsed
+    e2e_value = streams * args.steps / elapsed
     if rank == 0 and not np.array_equal(aft_dev, aft_host):
         raise SystemExit(f"device-input and host-input arms disagree: {aft_dev} vs {aft_host}")
 
@@ -182,9 +195,13 @@ def run_cuda(args, rank, world, local_rank):
         out = {
             "metric": "sweeps/sec scan-to-map", "value": round(value, 3), "unit": "sweeps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * el_dev / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": n_pts,
-                       "map_points": int(corner.shape[0] + surf.shape[0]), "mode": "replicas" if world > 1 else "single",
+                       "map_points": int(corner.shape[0] + surf.shape[0]),
+                       "mode": ("sharded: one stream, query slices + NCCL all-reduce of AtA/AtB per LM iteration" if sharded
+                                else "replicas: one independent sweep stream and map per GPU, no data-path collective"
+                                if world > 1 else "single"),
                        "l2_note": "inputs change every step (new sweep, rebuilt map BVH); 1M-pt map (16 MB) is L2-resident by construction",
                        "odom_iters_per_sweep": round(iters_o / args.steps, 2), "map_iters_per_sweep": round(iters_m / args.steps, 2),
                        "stage_ms_device_input": {k: round(1e3 * v / args.steps, 3) for k, v in zip(["registration", "odometry", "full_to_end", "mapping", "total"], stage_dev)},
@@ -309,6 +326,10 @@ def main():
     ap.add_argument("--workload", default="hdl64_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sweeps", type=int, default=12, help="sweeps timed for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: 'replicas' = one independent sweep stream per GPU (weak scaling, default); 'sharded' = one "
+                         "stream, every rank evaluates a slice of the scan-to-map correspondences, NCCL all-reduce of the "
+                         "normal equations per LM iteration (strong scaling)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
