@@ -63,6 +63,8 @@ int loam_b200_map_get_twist(void* h, int which, float* out6);
 int loam_b200_map_cloud_size(void* h, int which);
 int loam_b200_map_cloud_copy(void* h, int which, float* out);
 int loam_b200_map_last_iterations(void* h);
+/* host wall seconds of the last process(): begin_sweep, LM loop, end_sweep, surround map */
+int loam_b200_map_last_phase_seconds(void* h, double* out4);
 /* multi-GPU, one process per GPU: rank 0 calls loam_b200_host_nccl_unique_id and distributes the 128 bytes; every rank
  * then enables sharding on its mapping object (nccl_id128 = NULL: slice the queries only, no collective) */
 int loam_b200_host_nccl_unique_id(unsigned char* out128);

@@ -163,6 +163,7 @@ def lib():
         "loam_b200_map_cloud_size": (C.c_int, [vp, C.c_int]),
         "loam_b200_map_cloud_copy": (C.c_int, [vp, C.c_int, _F]),
         "loam_b200_map_last_iterations": (C.c_int, [vp]),
+        "loam_b200_map_last_phase_seconds": (C.c_int, [vp, _D]),
         "loam_b200_host_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
         "loam_b200_pipeline_create": (vp, [C.c_float, C.c_int, C.c_int]),
@@ -512,6 +513,11 @@ class LaserMapping(_Handle):
 
     def last_iterations(self):
         return self.L.loam_b200_map_last_iterations(self.h)
+
+    def last_phase_ms(self):
+        out = np.zeros(4, np.float64)
+        self.L.loam_b200_map_last_phase_seconds(self.h, out.ctypes.data_as(_D))
+        return dict(zip(["begin_sweep", "lm_loop", "end_sweep", "surround"], np.round(out * 1e3, 3)))
 
     def enable_sharding(self, rank, world, nccl_id: bytes | None):
         """Evaluate the rank-th of `world` query slices; with nccl_id (128 bytes, same on every rank) the normal

@@ -191,6 +191,9 @@ struct loam_b200_ctx {
   loamb::DevBuf<float4> pool_tmp;
   loamb::DevBuf<unsigned char> pool_tmp_cls;
   loamb::DevBuf<unsigned> cmp_pos, cmp_bsum;
+  loamb::DevBuf<int> dcount;          // device-side element counts (stage API keeps sizes on the GPU between kernels)
+  loamb::PinBuf<int> hcount;          // their pinned host mirror (one readback per stage)
+  loamb::PinBuf<unsigned char> cube_table_host;
   loamb::CubeGridHost map_grid;
   int map_n_valid = 0;
   float map_leaf[2] = {0.2f, 0.4f};

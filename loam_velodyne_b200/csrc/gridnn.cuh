@@ -30,7 +30,7 @@ struct GridView {
   unsigned mask;        // table size - 1 (power of two)
   const float4* sorted; // points in cell order, w = original index bits
   const GridMeta* meta;
-  int m;
+  int m;                // upper bound of the point count (0 = empty grid)
 };
 
 __device__ __forceinline__ unsigned grid_hash(unsigned k) {
@@ -61,9 +61,15 @@ __device__ __forceinline__ unsigned grid_key(const GridMeta& g, int cx, int cy, 
 }
 
 __global__ void grid_key_kernel(const float4* __restrict__ p, int m, const GridMeta* __restrict__ meta,
-                                unsigned* __restrict__ keys, int* __restrict__ vals) {
+                                unsigned* __restrict__ keys, int* __restrict__ vals,
+                                const int* __restrict__ n_dev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
+  if (n_dev && i >= *n_dev) {  // padding up to the launch bound sorts behind every real key
+    keys[i] = 0xffffffffu;
+    vals[i] = i;
+    return;
+  }
   const GridMeta g = *meta;
   const float4 q = p[i];
   const int cx = min(max((int)floorf(q.x) - g.ox, 0), g.nx - 1);
@@ -74,8 +80,10 @@ __global__ void grid_key_kernel(const float4* __restrict__ p, int m, const GridM
 }
 
 // one thread per sorted point; run heads insert (key, start, count) with linear probing
-__global__ void grid_insert_kernel(const unsigned* __restrict__ keys, int m, uint4* __restrict__ table, unsigned mask) {
+__global__ void grid_insert_kernel(const unsigned* __restrict__ keys, int m, uint4* __restrict__ table, unsigned mask,
+                                   const int* __restrict__ n_dev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) m = min(m, *n_dev);
   if (i >= m) return;
   const unsigned k = keys[i];
   if (i > 0 && keys[i - 1] == k) return;

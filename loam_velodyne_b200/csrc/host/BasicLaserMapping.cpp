@@ -5,6 +5,7 @@
 // calls through include/loam_b200.h.
 #include "loam_velodyne/BasicLaserMapping.h"
 
+#include <chrono>
 #include <cmath>
 
 #include "b200_runtime.h"
@@ -258,6 +259,8 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   win.n_valid = (int)valid.size();
   win.corner_leaf = b200::leafOf(_downSizeFilterCorner);
   win.surf_leaf = b200::leafOf(_downSizeFilterSurf);
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tp0 = now();
   loam_b200_pose predicted;
   b200::fillPose(_transformTobeMapped, predicted);
   _gpu->check(loam_b200_map_begin_sweep(_gpu->get(), &predicted, &win, _mapSizes), "loam_b200_map_begin_sweep");
@@ -266,7 +269,9 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   _c[M_CORNER_STACK_DS].deviceWritten(_mapSizes[2]);
   _c[M_SURF_STACK_DS].deviceWritten(_mapSizes[3]);
 
+  const double tp1 = now();
   optimizeTransformTobeMapped();
+  const double tp2 = now();
 
   // GPU: insert the down-sized stack points with the optimised pose, voxel-filter every valid cube, move the
   // full-resolution cloud into the map frame (upstream :536-595)
@@ -274,8 +279,11 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   b200::fillPose(_transformTobeMapped, optimised);
   _gpu->check(loam_b200_map_end_sweep(_gpu->get(), &optimised), "loam_b200_map_end_sweep");
   _c[M_FULL].deviceWritten((int)_c[M_FULL].size());
+  const double tp3 = now();
 
   _downsizedMapCreated = createDownsizedMap();
+  const double tp4 = now();
+  _phase[0] = tp1 - tp0; _phase[1] = tp2 - tp1; _phase[2] = tp3 - tp2; _phase[3] = tp4 - tp3;
   return true;
 }
 

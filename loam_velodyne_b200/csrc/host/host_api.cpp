@@ -200,6 +200,11 @@ int loam_b200_map_get_twist(void* h, int which, float* out6) {
 int loam_b200_map_cloud_size(void* h, int which) { return (int)((MapH*)h)->cloud(which).size(); }
 int loam_b200_map_cloud_copy(void* h, int which, float* out) { dump(((MapH*)h)->cloud(which), out); return 0; }
 int loam_b200_map_last_iterations(void* h) { return (int)((MapH*)h)->m.lastIterationCount(); }
+int loam_b200_map_last_phase_seconds(void* h, double* out4) {
+  const double* p = ((MapH*)h)->m.lastPhaseSeconds();
+  for (int i = 0; i < 4; i++) out4[i] = p[i];
+  return 0;
+}
 
 void* loam_b200_pipeline_create(float scanPeriod, int odomMaxIter, int mapMaxIter) {
   return new PipeH(scanPeriod, odomMaxIter, mapMaxIter);

@@ -75,6 +75,8 @@ class BasicLaserMapping {
   // cube-index arithmetic as the insertion step (upstream BasicLaserMapping.cpp:540-553); introspection for tests.
   void seedMap(pcl::PointCloud<pcl::PointXYZI> const& cornerPoints, pcl::PointCloud<pcl::PointXYZI> const& surfPoints);
   size_t lastIterationCount() const { return _lastIterations; }
+  // host wall seconds of the last process(): begin_sweep, LM loop, end_sweep, surround map
+  const double* lastPhaseSeconds() const { return _phase; }
   auto const& transformTobeMapped() const { return _transformTobeMapped; }
   pcl::PointCloud<pcl::PointXYZI> const& cornerStackDS() const;
   pcl::PointCloud<pcl::PointXYZI> const& surfStackDS() const;
@@ -126,6 +128,7 @@ class BasicLaserMapping {
   b200::GaussNewtonSolver* _solver;
   std::vector<float> _bufA, _bufB;
   size_t _lastIterations = 0;
+  double _phase[4] = {0, 0, 0, 0};
 };
 
 }  // namespace loam

@@ -38,7 +38,10 @@ __global__ void bbox_init_kernel(unsigned* bb) {
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
 }
 
-__global__ void bbox_kernel(const float4* __restrict__ p, int m, unsigned* bb) {
+// n_dev (optional): the live point count sits in device memory (produced by a compaction earlier on the stream);
+// m is then only the launch bound
+__global__ void bbox_kernel(const float4* __restrict__ p, int m, unsigned* bb, const int* __restrict__ n_dev = nullptr) {
+  if (n_dev) m = min(m, *n_dev);
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const float4 q = p[i];
@@ -137,18 +140,62 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__
   }
 }
 
+// exclusive scan inside each digit row of the digit-major table (one CTA per digit) + the row totals; the scatter
+// kernel turns the 256 totals into digit bases itself, so a pass needs no serial scan over 256 * n_tiles counters
+__global__ void __launch_bounds__(256)
+radix_scan_digits_kernel(unsigned* __restrict__ hist, int n_tiles, unsigned* __restrict__ digit_totals) {
+  __shared__ unsigned ws[8];
+  __shared__ unsigned carry;
+  unsigned* row = hist + (size_t)blockIdx.x * n_tiles;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 256) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < n_tiles ? row[i] : 0u;
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += ws[w];
+    const unsigned incl = x + woff + carry;
+    if (i < n_tiles) row[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) digit_totals[blockIdx.x] = carry;
+}
+
 // stable scatter: each warp owns RS_ITEMS*32 consecutive keys of the tile and processes them 32 at a time;
 // rank within the CTA = (keys of the same digit in earlier warps) + (earlier keys of the same digit in this warp)
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int m, int shift,
-                     const unsigned* __restrict__ hist, int n_tiles, unsigned* __restrict__ keys_out,
-                     int* __restrict__ vals_out) {
+                     const unsigned* __restrict__ hist, int n_tiles, const unsigned* __restrict__ digit_totals,
+                     unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
   constexpr int NW = RS_THREADS / 32;
   __shared__ unsigned wcount[NW][256];   // per-warp digit counts, then exclusive prefix over warps
   __shared__ unsigned gbase[256];
+  __shared__ unsigned dsum[NW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = lane; d < 256; d += 32) wcount[warp][d] = 0;
-  gbase[threadIdx.x] = hist[threadIdx.x * n_tiles + blockIdx.x];
+  {
+    // digit base = exclusive scan of the 256 digit totals (thread d <-> digit d), + this tile's offset inside the digit
+    const unsigned v = digit_totals[threadIdx.x];
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) dsum[warp] = x;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < warp; w++) woff += dsum[w];
+    gbase[threadIdx.x] = (x - v) + woff + hist[(size_t)threadIdx.x * n_tiles + blockIdx.x];
+  }
   __syncwarp();
   const int wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
   unsigned mykeys[RS_ITEMS];
@@ -201,8 +248,9 @@ radix_scatter_kernel(const unsigned* __restrict__ keys_in, const int* __restrict
 
 // ---------------------------------------------------------------- gather + leaves
 __global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ order, int m,
-                                     float4* __restrict__ sorted) {
+                                     float4* __restrict__ sorted, const int* __restrict__ n_dev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) m = min(m, *n_dev);
   if (i >= m) return;
   const int o = order[i];
   float4 p = pts[o];

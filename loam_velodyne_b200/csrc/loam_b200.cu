@@ -38,7 +38,8 @@ TreeView view_of(const Tree& t) {
 int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr) {
   SortScratch& s = c->sort;
   const int n_tiles = blocks_for(m, RS_TILE);
-  LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles));
+  LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles + 256));
+  unsigned* digit_totals = s.hist.p + (size_t)256 * n_tiles;
   unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
   int *va = s.vals_a.p, *vb = s.vals_b.p;
   int passes = (key_bits + 7) / 8;
@@ -47,9 +48,9 @@ int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out 
     const int shift = p * 8;
     radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, shift, s.hist.p, n_tiles);
     LB_LAUNCH_CHECK(c);
-    radix_scan_kernel<<<1, 1024, 0, c->stream>>>(s.hist.p, 256 * n_tiles);
+    radix_scan_digits_kernel<<<256, 256, 0, c->stream>>>(s.hist.p, n_tiles, digit_totals);
     LB_LAUNCH_CHECK(c);
-    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, m, shift, s.hist.p, n_tiles, kb, vb);
+    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, m, shift, s.hist.p, n_tiles, digit_totals, kb, vb);
     LB_LAUNCH_CHECK(c);
     unsigned* tk = ka; ka = kb; kb = tk;
     int* tv = va; va = vb; vb = tv;
@@ -69,8 +70,9 @@ GridView grid_view_of(const Grid& g) {
   return v;
 }
 
-// 1 m uniform grid over d_pts (m points): the search structure of the scan-to-map loop (gridnn.cuh)
-int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m) {
+// 1 m uniform grid over d_pts: the search structure of the scan-to-map loop (gridnn.cuh).  m is the launch bound; when
+// n_dev is given the live count is read on the device (no host round trip after the compaction that produced it).
+int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m, const int* n_dev = nullptr) {
   g.m = m;
   if (m <= 0) return LOAM_B200_OK;
   SortScratch& s = c->sort;
@@ -91,19 +93,19 @@ int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m) {
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
   const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 8);
-  bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(d_pts, m, bb);
+  bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(d_pts, m, bb, n_dev);
   LB_LAUNCH_CHECK(c);
   grid_meta_kernel<<<1, 32, 0, c->stream>>>(bb, meta);
   LB_LAUNCH_CHECK(c);
-  grid_key_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, m, meta, s.keys_a.p, s.vals_a.p);
+  grid_key_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, m, meta, s.keys_a.p, s.vals_a.p, n_dev);
   LB_LAUNCH_CHECK(c);
   unsigned* keys = nullptr;
   int* vals = nullptr;
-  int rc = radix_sort_pairs(c, m, 32, &keys, &vals);  // keys < 1290^3 < 2^31
+  int rc = radix_sort_pairs(c, m, 32, &keys, &vals);  // keys < 1290^3 < 2^31; padding keys are 0xffffffff
   if (rc) return rc;
-  gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, vals, m, g.sorted.p);
+  gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, vals, m, g.sorted.p, n_dev);
   LB_LAUNCH_CHECK(c);
-  grid_insert_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(keys, m, g.table.p, g.mask);
+  grid_insert_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(keys, m, g.table.p, g.mask, n_dev);
   LB_LAUNCH_CHECK(c);
   return LOAM_B200_OK;
 }
@@ -321,7 +323,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   for (auto& cl : c->cloud) cl.release();
   for (auto& g : c->grid) { g.table.release(); g.sorted.release(); g.meta.release(); }
   c->pool_cls[0].release(); c->pool_cls[1].release(); c->rank_of_cube.release(); c->pool_tmp.release();
-  c->pool_tmp_cls.release(); c->cmp_pos.release(); c->cmp_bsum.release();
+  c->pool_tmp_cls.release(); c->cmp_pos.release(); c->cmp_bsum.release(); c->dcount.release(); c->hcount.release(); c->cube_table_host.release();
   if (c->ev_xfer) cudaEventDestroy(c->ev_xfer);
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();

@@ -88,11 +88,13 @@ compact_count_kernel(const unsigned char* __restrict__ cls, int n, int limit, un
 // scatter selected points (and optionally their source index / class) to dst + dst_offset
 __global__ void compact_scatter_kernel(const float4* __restrict__ src, const unsigned char* __restrict__ cls, int n,
                                        const unsigned* __restrict__ local_pos, const unsigned* __restrict__ block_off,
-                                       float4* __restrict__ dst, unsigned char* __restrict__ dst_cls, int dst_offset) {
+                                       float4* __restrict__ dst, unsigned char* __restrict__ dst_cls, int dst_offset,
+                                       const int* __restrict__ dst_offset_dev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned pv = local_pos[i];
   if (!(pv >> 31)) return;
+  if (dst_offset_dev) dst_offset += *dst_offset_dev;
   const unsigned d = (pv & 0x7fffffffu) + block_off[i / SCAN_BS] + (unsigned)dst_offset;
   dst[d] = src[i];
   if (dst_cls) dst_cls[d] = cls[i];
@@ -140,20 +142,15 @@ __global__ void stack_roundtrip_kernel(const float4* __restrict__ in, int n, Map
   out[i] = make_float4(x3, y3, z2, q.w);
 }
 
-// new map points: pointAssociateToMap(stackDS) with the optimised pose, classified on the fly (:536-577)
-__global__ void insert_points_kernel(const float4* __restrict__ stack_ds, int n, MapIterArgs a, CubeGrid g,
-                                     const unsigned char* __restrict__ rank_of_cube, float4* __restrict__ dst,
-                                     unsigned char* __restrict__ dst_cls) {
+// new map points: pointAssociateToMap(stackDS) with the optimised pose (:536-577)
+__global__ void insert_points_kernel(const float4* __restrict__ stack_ds, int n, MapIterArgs a,
+                                     float4* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 q = stack_ds[i];
   float x, y, z;
   associate_to_map(a, q, x, y, z);
-  const float4 o = make_float4(x, y, z, q.w);
-  int ci, cj, ck;
-  const int c = cube_index(o, g, ci, cj, ck);
-  dst[i] = o;
-  dst_cls[i] = c < 0 ? CLS_DROP : rank_of_cube[c];
+  dst[i] = make_float4(x, y, z, q.w);
 }
 
 }  // namespace loamb

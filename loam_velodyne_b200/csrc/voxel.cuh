@@ -69,80 +69,116 @@ __global__ void voxel_centroid_kernel(const float4* __restrict__ p, const unsign
   out[dst] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
 }
 
-// d_in: n points on the device; d_out: capacity n.  *count receives the number of voxels (host sync inside).
-inline int voxel_grid_device(loam_b200_ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* count) {
-  *count = 0;
-  if (n <= 0) return LOAM_B200_OK;
+struct VoxMeta {
+  int minb0, minb1, minb2, div0, div1, overflow;
+};
+
+// bbox -> voxel grid origin / extents on the device (pcl::VoxelGrid::applyFilter's min_b_ / div_b_ and its int32
+// overflow guard "Leaf size is too small for the input dataset")
+__global__ void voxel_meta_kernel(const unsigned* __restrict__ bb, float inv, VoxMeta* __restrict__ meta) {
+  if (threadIdx.x != 0) return;
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; a++) { mn[a] = dec_f(bb[a]); mx[a] = dec_f(bb[3 + a]); }
+  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
+                  dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  VoxMeta m;
+  m.overflow = (dx * dy * dz > 2147483647ll) ? 1 : 0;
+  m.minb0 = (int)floorf(mn[0] * inv);
+  m.minb1 = (int)floorf(mn[1] * inv);
+  m.minb2 = (int)floorf(mn[2] * inv);
+  m.div0 = (int)floorf(mx[0] * inv) - m.minb0 + 1;
+  m.div1 = (int)floorf(mx[1] * inv) - m.minb1 + 1;
+  *meta = m;
+}
+
+// keys from the device-side meta; on overflow every point keeps its own key (= its index), which makes the filter an
+// identity exactly like pcl's early return
+__global__ void voxel_key_meta_kernel(const float4* __restrict__ p, int n, float inv, const VoxMeta* __restrict__ meta,
+                                      unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const VoxMeta m = *meta;
+  vals[i] = i;
+  if (m.overflow) {
+    keys[i] = (unsigned)i;
+    return;
+  }
+  const float4 q = p[i];
+  const int i0 = (int)(floorf(q.x * inv) - (float)m.minb0);
+  const int i1 = (int)(floorf(q.y * inv) - (float)m.minb1);
+  const int i2 = (int)(floorf(q.z * inv) - (float)m.minb2);
+  keys[i] = (unsigned)(i0 + i1 * m.div0 + i2 * m.div0 * m.div1);
+}
+
+__global__ void copy_u32_kernel(const unsigned* __restrict__ src, int* __restrict__ dst) {
+  if (threadIdx.x == 0) *dst = (int)*src;
+}
+
+// Stream-ordered voxel filter without host round trips: d_in (n points, n known on the host) -> d_out (capacity n);
+// the number of occupied voxels is written to *d_count (device memory).
+inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* d_count) {
+  if (n <= 0) {
+    LB_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
+    return LOAM_B200_OK;
+  }
   SortScratch& s = c->sort;
+  const int n_tiles = (n + RS_TILE - 1) / RS_TILE;
   LB_CUDA(c, s.keys_a.reserve(n));
   LB_CUDA(c, s.keys_b.reserve(n));
   LB_CUDA(c, s.vals_a.reserve(n));
   LB_CUDA(c, s.vals_b.reserve(n));
-  LB_CUDA(c, c->bbox.reserve(8));
+  LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles + 256));
+  LB_CUDA(c, c->bbox.reserve(16));
   unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
+  VoxMeta* meta = reinterpret_cast<VoxMeta*>(c->bbox.p + 8);
+  const float inv = 1.0f / leaf;
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
   const int bbox_blocks = std::min((n + 255) / 256, c->sm_count * 8);
   bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(d_in, n, bb);
   LB_LAUNCH_CHECK(c);
-  unsigned hb[6];
-  LB_CUDA(c, cudaMemcpyAsync(hb, bb, sizeof hb, cudaMemcpyDeviceToHost, c->stream));
-  LB_CUDA(c, cudaStreamSynchronize(c->stream));
-  float mn[3], mx[3];
-  for (int a = 0; a < 3; a++) { mn[a] = dec_f(hb[a]); mx[a] = dec_f(hb[3 + a]); }
-  const float inv = 1.0f / leaf;
-  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
-                  dz = (long long)((mx[2] - mn[2]) * inv) + 1;
-  if (dx * dy * dz > 2147483647ll) {
-    // pcl: "Leaf size is too small for the input dataset" -> output = input
-    LB_CUDA(c, cudaMemcpyAsync(d_out, d_in, (size_t)n * 16, cudaMemcpyDeviceToDevice, c->stream));
-    *count = n;
-    return LOAM_B200_OK;
-  }
-  const int minb0 = (int)floorf(mn[0] * inv), minb1 = (int)floorf(mn[1] * inv), minb2 = (int)floorf(mn[2] * inv);
-  const int div0 = (int)floorf(mx[0] * inv) - minb0 + 1, div1 = (int)floorf(mx[1] * inv) - minb1 + 1;
-  const int div2 = (int)floorf(mx[2] * inv) - minb2 + 1;
-  voxel_key_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, inv, minb0, minb1, minb2, div0, div1, s.keys_a.p,
-                                                           s.vals_a.p);
+  voxel_meta_kernel<<<1, 32, 0, c->stream>>>(bb, inv, meta);
   LB_LAUNCH_CHECK(c);
-  // only as many radix passes as the voxel index needs
-  long long span = (long long)div0 * div1 * div2;
-  int bits = 1;
-  while ((1ll << bits) < span && bits < 32) bits++;
-  int rc = LOAM_B200_OK;
-  {
-    const int n_tiles = (n + RS_TILE - 1) / RS_TILE;
-    LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles));
-    unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
-    int *va = s.vals_a.p, *vb = s.vals_b.p;
-    int passes = (bits + 7) / 8;
-    if (passes & 1) passes++;
-    for (int p = 0; p < passes; p++) {
-      radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, n, p * 8, s.hist.p, n_tiles);
-      LB_LAUNCH_CHECK(c);
-      radix_scan_kernel<<<1, 1024, 0, c->stream>>>(s.hist.p, 256 * n_tiles);
-      LB_LAUNCH_CHECK(c);
-      radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, n, p * 8, s.hist.p, n_tiles, kb, vb);
-      LB_LAUNCH_CHECK(c);
-      unsigned* tk = ka; ka = kb; kb = tk;
-      int* tv = va; va = vb; vb = tv;
-    }
+  voxel_key_meta_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, inv, meta, s.keys_a.p, s.vals_a.p);
+  LB_LAUNCH_CHECK(c);
+  // voxel indices are < 2^31 by pcl's own guard: four 8-bit passes
+  unsigned* digit_totals = s.hist.p + (size_t)256 * n_tiles;
+  unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
+  int *va = s.vals_a.p, *vb = s.vals_b.p;
+  for (int p = 0; p < 4; p++) {
+    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, n, p * 8, s.hist.p, n_tiles);
+    LB_LAUNCH_CHECK(c);
+    radix_scan_digits_kernel<<<256, 256, 0, c->stream>>>(s.hist.p, n_tiles, digit_totals);
+    LB_LAUNCH_CHECK(c);
+    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, n, p * 8, s.hist.p, n_tiles, digit_totals, kb, vb);
+    LB_LAUNCH_CHECK(c);
+    unsigned* tk = ka; ka = kb; kb = tk;
+    int* tv = va; va = vb; vb = tv;
   }
-  if (rc) return rc;
   const int nb = (n + SCAN_BS - 1) / SCAN_BS;
   LB_CUDA(c, c->vox_key.reserve((size_t)n + nb + 8));
   unsigned* pos = c->vox_key.p;
   unsigned* bsum = c->vox_key.p + n;
-  voxel_head_kernel<<<nb, SCAN_BS, 0, c->stream>>>(s.keys_a.p, n, pos, bsum);
+  voxel_head_kernel<<<nb, SCAN_BS, 0, c->stream>>>(ka, n, pos, bsum);
   LB_LAUNCH_CHECK(c);
   radix_scan_kernel<<<1, 1024, 0, c->stream>>>(bsum, nb + 1);  // exclusive; entry nb receives the grand total
   LB_LAUNCH_CHECK(c);
-  voxel_centroid_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, s.keys_a.p, s.vals_a.p, pos, bsum, n, d_out);
+  voxel_centroid_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, ka, va, pos, bsum, n, d_out);
   LB_LAUNCH_CHECK(c);
-  unsigned total = 0;
-  LB_CUDA(c, cudaMemcpyAsync(&total, bsum + nb, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+  copy_u32_kernel<<<1, 32, 0, c->stream>>>(bsum + nb, d_count);
+  LB_LAUNCH_CHECK(c);
+  return LOAM_B200_OK;
+}
+
+// synchronous convenience: *count on the host
+inline int voxel_grid_device(loam_b200_ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* count) {
+  *count = 0;
+  if (n <= 0) return LOAM_B200_OK;
+  LB_CUDA(c, c->dcount.reserve(64));
+  int rc = voxel_grid_async(c, d_in, n, leaf, d_out, c->dcount.p + 63);
+  if (rc) return rc;
+  LB_CUDA(c, cudaMemcpyAsync(count, c->dcount.p + 63, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
-  *count = (int)total;
   return LOAM_B200_OK;
 }
 

@@ -15,7 +15,7 @@ def main():
     for i in range(n):
         pts, rs = synth.make_sweep(scene, lidar, i, yaw_rate=math.radians(5.0))
         ok, od, aft, st = p.sweep(pts, rs)
-        print(i, np.round(st * 1e3, 3), "iters", p.odom.last_iterations(), p.mapping.last_iterations(), flush=True)
+        print(i, np.round(st * 1e3, 3), "iters", p.odom.last_iterations(), p.mapping.last_iterations(), p.mapping.last_phase_ms(), flush=True)
 
 if __name__ == "__main__":
     main()
