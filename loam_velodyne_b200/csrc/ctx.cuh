@@ -199,6 +199,21 @@ struct loam_b200_ctx {
   float map_leaf[2] = {0.2f, 0.4f};
   cudaEvent_t ev_xfer = nullptr;
 
+  // extra lanes: independent pieces of a stage (corner / surface kind, stack filter / map grid) run concurrently on
+  // their own stream with their own scratch; LaneScope swaps a lane's stream + scratch into the fields above
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    loamb::SortScratch sort;
+    loamb::DevBuf<float> bbox;
+    loamb::DevBuf<uint32_t> vox_key;
+    loamb::DevBuf<unsigned> cmp_pos, cmp_bsum;
+    loamb::DevBuf<float4> tmp_pts, tmp_pts2, pool_tmp;
+  };
+  static constexpr int NUM_LANES = 3;   // lanes 1..3 (lane 0 = the context's own stream and scratch)
+  Lane lanes[NUM_LANES];
+  cudaEvent_t ev_fork = nullptr;
+
   // generic scratch
   loamb::DevBuf<float4> tmp_pts;
   loamb::DevBuf<float4> tmp_pts2;
@@ -232,6 +247,42 @@ extern long long g_total_launches;
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, "kernel launch", __LINE__); \
   } while (0)
+
+// Run the enclosed calls on lane `i` (1..NUM_LANES; 0 = the context's own stream): swaps stream + scratch buffers in,
+// and back out on destruction.  Callers fork / join the lanes with lanes_fork / lanes_join.
+struct LaneScope {
+  loam_b200_ctx* c;
+  loam_b200_ctx::Lane* l;
+  LaneScope(loam_b200_ctx* ctx, int i) : c(ctx), l(i > 0 ? &ctx->lanes[i - 1] : nullptr) { swap(); }
+  ~LaneScope() { swap(); }
+  void swap() {
+    if (!l) return;
+    std::swap(c->stream, l->stream);
+    std::swap(c->sort, l->sort);
+    std::swap(c->bbox, l->bbox);
+    std::swap(c->vox_key, l->vox_key);
+    std::swap(c->cmp_pos, l->cmp_pos);
+    std::swap(c->cmp_bsum, l->cmp_bsum);
+    std::swap(c->tmp_pts, l->tmp_pts);
+    std::swap(c->tmp_pts2, l->tmp_pts2);
+    std::swap(c->pool_tmp, l->pool_tmp);
+  }
+};
+// every lane starts after everything enqueued so far on the main stream ...
+inline cudaError_t lanes_fork(loam_b200_ctx* c, int n_lanes) {
+  cudaError_t e = cudaEventRecord(c->ev_fork, c->stream);
+  for (int i = 0; i < n_lanes && e == cudaSuccess; i++) e = cudaStreamWaitEvent(c->lanes[i].stream, c->ev_fork, 0);
+  return e;
+}
+// ... and the main stream continues after all of them
+inline cudaError_t lanes_join(loam_b200_ctx* c, int n_lanes) {
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < n_lanes && e == cudaSuccess; i++) {
+    e = cudaEventRecord(c->lanes[i].done, c->lanes[i].stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->lanes[i].done, 0);
+  }
+  return e;
+}
 
 // RAII-less profiling bracket: begin/end around a family's kernels on the ctx stream
 inline void prof_begin(loam_b200_ctx* c, int family) {

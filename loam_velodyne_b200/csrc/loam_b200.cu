@@ -293,6 +293,15 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
     delete c;
     return LOAM_B200_ERR_CUDA;
   }
+  bool lanes_ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (auto& l : c->lanes)
+    lanes_ok = lanes_ok && cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming) == cudaSuccess;
+  if (!lanes_ok) {
+    cudaGetLastError();
+    delete c;
+    return LOAM_B200_ERR_CUDA;
+  }
   cudaFuncSetAttribute(feature_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||
       c->ticket.reserve(4) != cudaSuccess || c->result_host.reserve(NEQ) != cudaSuccess) {
@@ -324,6 +333,15 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   for (auto& g : c->grid) { g.table.release(); g.sorted.release(); g.meta.release(); }
   c->pool_cls[0].release(); c->pool_cls[1].release(); c->rank_of_cube.release(); c->pool_tmp.release();
   c->pool_tmp_cls.release(); c->cmp_pos.release(); c->cmp_bsum.release(); c->dcount.release(); c->hcount.release(); c->cube_table_host.release();
+  for (auto& l : c->lanes) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    l.sort.keys_a.release(); l.sort.keys_b.release(); l.sort.vals_a.release(); l.sort.vals_b.release(); l.sort.hist.release();
+    l.bbox.release(); l.vox_key.release(); l.cmp_pos.release(); l.cmp_bsum.release();
+    l.tmp_pts.release(); l.tmp_pts2.release(); l.pool_tmp.release();
+    if (l.done) cudaEventDestroy(l.done);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_xfer) cudaEventDestroy(c->ev_xfer);
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
