@@ -10,6 +10,8 @@
 //   bottom-up box refit.  Nodes are 64 B (both child boxes + links): one aligned 64 B read per visit.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "ctx.cuh"
 
 namespace loamb {
@@ -92,22 +94,151 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;                        // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // keys per CTA
 
-__global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const unsigned* __restrict__ keys, int m, int shift, unsigned* __restrict__ hist, int n_tiles) {
-  __shared__ unsigned h[256];
+// ---- per-tile / per-digit building blocks, shared by the three-kernel path and the single cooperative kernel
+__device__ __forceinline__ void radix_hist_tile(const unsigned* __restrict__ keys, int m, int shift,
+                                                unsigned* __restrict__ hist, int n_tiles, int tile, unsigned* h) {
   h[threadIdx.x] = 0;
   __syncthreads();
-  const int base = blockIdx.x * RS_TILE;
+  const int base = tile * RS_TILE;
   for (int it = 0; it < RS_ITEMS; it++) {
     const int i = base + it * RS_THREADS + threadIdx.x;
     if (i < m) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
   }
   __syncthreads();
-  hist[threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];  // digit-major so one scan gives global offsets
+  hist[(size_t)threadIdx.x * n_tiles + tile] = h[threadIdx.x];  // digit-major so one scan per digit gives offsets
+  __syncthreads();
 }
 
-// exclusive scan of 256 * n_tiles counters by a single CTA (n_tiles is small: m / 4096)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ hist, int total) {
+// exclusive scan inside digit row d of the digit-major table by one CTA, + the row total
+__device__ __forceinline__ void radix_scan_row(unsigned* __restrict__ hist, int n_tiles,
+                                               unsigned* __restrict__ digit_totals, int d, unsigned* ws, unsigned* carry) {
+  unsigned* row = hist + (size_t)d * n_tiles;
+  if (threadIdx.x == 0) *carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += RS_THREADS) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < n_tiles ? row[i] : 0u;
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += ws[w];
+    const unsigned incl = x + woff + *carry;
+    if (i < n_tiles) row[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == RS_THREADS - 1) *carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) digit_totals[d] = *carry;
+  __syncthreads();
+}
+
+// same for short rows (n_tiles <= 32): one WARP per digit row
+__device__ __forceinline__ void radix_scan_row_warp(unsigned* __restrict__ hist, int n_tiles,
+                                                    unsigned* __restrict__ digit_totals, int d) {
+  const int lane = threadIdx.x & 31;
+  unsigned* row = hist + (size_t)d * n_tiles;
+  const unsigned v = lane < n_tiles ? row[lane] : 0u;
+  unsigned x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane < n_tiles) row[lane] = x - v;
+  const unsigned tot = __shfl_sync(0xffffffffu, x, 31);
+  if (lane == 0) digit_totals[d] = tot;
+}
+
+// stable scatter of one tile: each warp owns RS_ITEMS*32 consecutive keys and processes them 32 at a time;
+// rank within the CTA = (keys of the same digit in earlier warps) + (earlier keys of the same digit in this warp)
+struct RadixScatterSmem {
+  unsigned wcount[RS_THREADS / 32][256];
+  unsigned gbase[256];
+  unsigned dsum[RS_THREADS / 32];
+};
+__device__ __forceinline__ void radix_scatter_tile(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in,
+                                                   int m, int shift, const unsigned* __restrict__ hist, int n_tiles,
+                                                   const unsigned* __restrict__ digit_totals,
+                                                   unsigned* __restrict__ keys_out, int* __restrict__ vals_out, int tile,
+                                                   RadixScatterSmem& sm) {
+  constexpr int NW = RS_THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) sm.wcount[warp][d] = 0;
+  {
+    // digit base = exclusive scan of the 256 digit totals (thread d <-> digit d), + this tile's offset inside the digit
+    const unsigned v = digit_totals[threadIdx.x];
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) sm.dsum[warp] = x;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < warp; w++) woff += sm.dsum[w];
+    sm.gbase[threadIdx.x] = (x - v) + woff + hist[(size_t)threadIdx.x * n_tiles + tile];
+  }
+  __syncwarp();
+  const int wbase = tile * RS_TILE + warp * (RS_ITEMS * 32);
+  unsigned mykeys[RS_ITEMS];
+  unsigned short myrank[RS_ITEMS];
+  for (int it = 0; it < RS_ITEMS; it++) {
+    const int i = wbase + it * 32 + lane;
+    const bool valid = i < m;
+    const unsigned k = valid ? keys_in[i] : 0xffffffffu;
+    mykeys[it] = k;
+    const unsigned d = (k >> shift) & 255u;
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    for (int b = 0; b < 8; b++) {
+      const unsigned bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
+    const unsigned before = __popc(peers & ((1u << lane) - 1u));
+    unsigned prior = 0;
+    if (valid) prior = sm.wcount[warp][d];
+    myrank[it] = (unsigned short)(prior + before);
+    __syncwarp();
+    if (valid && before == 0) sm.wcount[warp][d] = prior + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;
+    unsigned acc = 0;
+    for (int wv = 0; wv < NW; wv++) {
+      const unsigned c = sm.wcount[wv][d];
+      sm.wcount[wv][d] = acc;
+      acc += c;
+    }
+  }
+  __syncthreads();
+  for (int it = 0; it < RS_ITEMS; it++) {
+    const int i = wbase + it * 32 + lane;
+    if (i < m) {
+      const unsigned k = mykeys[it];
+      const unsigned d = (k >> shift) & 255u;
+      const unsigned dst = sm.gbase[d] + sm.wcount[warp][d] + myrank[it];
+      keys_out[dst] = k;
+      vals_out[dst] = vals_in[i];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const unsigned* __restrict__ keys, int m, int shift, unsigned* __restrict__ hist, int n_tiles) {
+  __shared__ unsigned h[256];
+  radix_hist_tile(keys, m, shift, hist, n_tiles, blockIdx.x, h);
+}
+
+// exclusive scan of `total` counters by a single CTA (block sums of compactions / voxel heads)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ hist, int total,
+                                                           int* __restrict__ last_out = nullptr) {
   __shared__ unsigned warp_sums[32];
   __shared__ unsigned carry;
   if (threadIdx.x == 0) carry = 0;
@@ -134,115 +265,57 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__
     const unsigned woff = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u;
     const unsigned incl = x + woff + carry;
     if (i < total) hist[i] = incl - v;
+    // callers scan n + 1 entries so that the last one receives the grand total; optionally mirror it
+    if (last_out && i == total - 1) *last_out = (int)(incl - v);
     __syncthreads();
     if (threadIdx.x == 1023) carry = incl;
     __syncthreads();
   }
 }
 
-// exclusive scan inside each digit row of the digit-major table (one CTA per digit) + the row totals; the scatter
-// kernel turns the 256 totals into digit bases itself, so a pass needs no serial scan over 256 * n_tiles counters
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RS_THREADS)
 radix_scan_digits_kernel(unsigned* __restrict__ hist, int n_tiles, unsigned* __restrict__ digit_totals) {
-  __shared__ unsigned ws[8];
+  __shared__ unsigned ws[RS_THREADS / 32];
   __shared__ unsigned carry;
-  unsigned* row = hist + (size_t)blockIdx.x * n_tiles;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n_tiles; base += 256) {
-    const int i = base + threadIdx.x;
-    const unsigned v = i < n_tiles ? row[i] : 0u;
-    unsigned x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-    __syncthreads();
-    unsigned woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += ws[w];
-    const unsigned incl = x + woff + carry;
-    if (i < n_tiles) row[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == 255) carry = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) digit_totals[blockIdx.x] = carry;
+  radix_scan_row(hist, n_tiles, digit_totals, blockIdx.x, ws, &carry);
 }
 
-// stable scatter: each warp owns RS_ITEMS*32 consecutive keys of the tile and processes them 32 at a time;
-// rank within the CTA = (keys of the same digit in earlier warps) + (earlier keys of the same digit in this warp)
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int m, int shift,
                      const unsigned* __restrict__ hist, int n_tiles, const unsigned* __restrict__ digit_totals,
                      unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
-  constexpr int NW = RS_THREADS / 32;
-  __shared__ unsigned wcount[NW][256];   // per-warp digit counts, then exclusive prefix over warps
-  __shared__ unsigned gbase[256];
-  __shared__ unsigned dsum[NW];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int d = lane; d < 256; d += 32) wcount[warp][d] = 0;
-  {
-    // digit base = exclusive scan of the 256 digit totals (thread d <-> digit d), + this tile's offset inside the digit
-    const unsigned v = digit_totals[threadIdx.x];
-    unsigned x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+  __shared__ RadixScatterSmem sm;
+  radix_scatter_tile(keys_in, vals_in, m, shift, hist, n_tiles, digit_totals, keys_out, vals_out, blockIdx.x, sm);
+}
+
+// ---- the whole LSD sort in ONE cooperative launch: persistent CTAs loop over tiles, grid-wide barriers separate the
+// histogram / digit-scan / scatter phases of each pass.  Twelve dependent launches per sort become one, which is what
+// the launch-bound mapping stage needs (the host thread, not the GPU, was the bottleneck: profiles/r1_v3_*.md).
+__global__ void __launch_bounds__(RS_THREADS)
+radix_sort_coop_kernel(unsigned* ka, int* va, unsigned* kb, int* vb, int m, int passes, unsigned* __restrict__ hist,
+                       int n_tiles, unsigned* __restrict__ digit_totals) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ RadixScatterSmem sm;
+  __shared__ unsigned h[256];
+  __shared__ unsigned carry;
+  for (int p = 0; p < passes; p++) {
+    const int shift = p * 8;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) radix_hist_tile(ka, m, shift, hist, n_tiles, tile, h);
+    grid.sync();
+    if (n_tiles <= 32) {
+      const int warps_per_grid = gridDim.x * (RS_THREADS / 32);
+      for (int d = blockIdx.x * (RS_THREADS / 32) + (threadIdx.x >> 5); d < 256; d += warps_per_grid)
+        radix_scan_row_warp(hist, n_tiles, digit_totals, d);
+    } else {
+      for (int d = blockIdx.x; d < 256; d += gridDim.x) radix_scan_row(hist, n_tiles, digit_totals, d, sm.dsum, &carry);
     }
-    if (lane == 31) dsum[warp] = x;
-    __syncthreads();
-    unsigned woff = 0;
-    for (int w = 0; w < warp; w++) woff += dsum[w];
-    gbase[threadIdx.x] = (x - v) + woff + hist[(size_t)threadIdx.x * n_tiles + blockIdx.x];
-  }
-  __syncwarp();
-  const int wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
-  unsigned mykeys[RS_ITEMS];
-  unsigned short myrank[RS_ITEMS];
-  // pass A: per-warp counts and the in-warp rank of every key
-  for (int it = 0; it < RS_ITEMS; it++) {
-    const int i = wbase + it * 32 + lane;
-    const bool valid = i < m;
-    const unsigned k = valid ? keys_in[i] : 0xffffffffu;
-    mykeys[it] = k;
-    const unsigned d = (k >> shift) & 255u;
-    // peers with the same digit among valid lanes
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-    for (int b = 0; b < 8; b++) {
-      const unsigned bit = (d >> b) & 1u;
-      const unsigned bal = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? bal : ~bal;
-    }
-    const unsigned before = __popc(peers & ((1u << lane) - 1u));
-    unsigned prior = 0;
-    if (valid) prior = wcount[warp][d];
-    myrank[it] = (unsigned short)(prior + before);
-    __syncwarp();
-    if (valid && before == 0) wcount[warp][d] = prior + __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  // exclusive prefix over warps for each digit
-  {
-    const int d = threadIdx.x;
-    unsigned acc = 0;
-    for (int wv = 0; wv < NW; wv++) {
-      const unsigned c = wcount[wv][d];
-      wcount[wv][d] = acc;
-      acc += c;
-    }
-  }
-  __syncthreads();
-  for (int it = 0; it < RS_ITEMS; it++) {
-    const int i = wbase + it * 32 + lane;
-    if (i < m) {
-      const unsigned k = mykeys[it];
-      const unsigned d = (k >> shift) & 255u;
-      const unsigned dst = gbase[d] + wcount[warp][d] + myrank[it];
-      keys_out[dst] = k;
-      vals_out[dst] = vals_in[i];
-    }
+    grid.sync();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      radix_scatter_tile(ka, va, m, shift, hist, n_tiles, digit_totals, kb, vb, tile, sm);
+    grid.sync();
+    unsigned* tk = ka; ka = kb; kb = tk;
+    int* tv = va; va = vb; vb = tv;
   }
 }
 

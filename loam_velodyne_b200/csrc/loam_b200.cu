@@ -33,9 +33,12 @@ TreeView view_of(const Tree& t) {
   return v;
 }
 
+}  // namespace
+
+namespace loamb {
 // radix sort (keys, vals) of length m in ctx->sort (input in keys_a / vals_a); 8 bits per pass.  The sorted arrays are
 // returned through keys_out / vals_out (buffer a after an even number of passes, b after an odd one).
-int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr) {
+int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out, int** vals_out) {
   SortScratch& s = c->sort;
   const int n_tiles = blocks_for(m, RS_TILE);
   LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles + 256));
@@ -44,21 +47,40 @@ int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out 
   int *va = s.vals_a.p, *vb = s.vals_b.p;
   int passes = (key_bits + 7) / 8;
   if (!keys_out && (passes & 1)) passes++;  // callers that read buffer a directly need an even count
-  for (int p = 0; p < passes; p++) {
-    const int shift = p * 8;
-    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, shift, s.hist.p, n_tiles);
+  if (c->coop_blocks > 0) {
+    // one cooperative launch for all passes
+    int grid = std::min(std::max(n_tiles, 1), c->coop_blocks);
+    int m_arg = m, passes_arg = passes, n_tiles_arg = n_tiles;
+    unsigned* hist_p = s.hist.p;
+    void* args[] = {&ka, &va, &kb, &vb, &m_arg, &passes_arg, &hist_p, &n_tiles_arg, &digit_totals};
+    LB_CUDA(c, cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(grid), dim3(RS_THREADS), args, 0,
+                                           c->stream));
     LB_LAUNCH_CHECK(c);
-    radix_scan_digits_kernel<<<256, 256, 0, c->stream>>>(s.hist.p, n_tiles, digit_totals);
-    LB_LAUNCH_CHECK(c);
-    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, m, shift, s.hist.p, n_tiles, digit_totals, kb, vb);
-    LB_LAUNCH_CHECK(c);
-    unsigned* tk = ka; ka = kb; kb = tk;
-    int* tv = va; va = vb; vb = tv;
+    if (passes & 1) {
+      unsigned* tk = ka; ka = kb; kb = tk;
+      int* tv = va; va = vb; vb = tv;
+    }
+  } else {
+    for (int p = 0; p < passes; p++) {
+      const int shift = p * 8;
+      radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, shift, s.hist.p, n_tiles);
+      LB_LAUNCH_CHECK(c);
+      radix_scan_digits_kernel<<<256, RS_THREADS, 0, c->stream>>>(s.hist.p, n_tiles, digit_totals);
+      LB_LAUNCH_CHECK(c);
+      radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, m, shift, s.hist.p, n_tiles, digit_totals, kb, vb);
+      LB_LAUNCH_CHECK(c);
+      unsigned* tk = ka; ka = kb; kb = tk;
+      int* tv = va; va = vb; vb = tv;
+    }
   }
   if (keys_out) *keys_out = ka;
   if (vals_out) *vals_out = va;
   return LOAM_B200_OK;
 }
+
+}  // namespace loamb
+
+namespace {
 
 GridView grid_view_of(const Grid& g) {
   GridView v;
@@ -301,6 +323,15 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
     cudaGetLastError();
     delete c;
     return LOAM_B200_ERR_CUDA;
+  }
+  {
+    // co-resident CTAs for the cooperative radix sort (0 disables it: LOAM_B200_NO_COOP=1 or no device support)
+    int per_sm = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (coop && !getenv("LOAM_B200_NO_COOP") &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_coop_kernel, RS_THREADS, 0) == cudaSuccess)
+      c->coop_blocks = per_sm * prop.multiProcessorCount;
+    cudaGetLastError();
   }
   cudaFuncSetAttribute(feature_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||

@@ -8,6 +8,9 @@
 
 namespace loamb {
 
+// defined in loam_b200.cu: LSD radix sort of (keys_a, vals_a) in c->sort; sorted arrays returned through the out params
+int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr);
+
 __global__ void voxel_key_kernel(const float4* __restrict__ p, int n, float inv, int minb0, int minb1, int minb2,
                                  int div0, int div1, unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,18 +145,11 @@ inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float l
   voxel_key_meta_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, inv, meta, s.keys_a.p, s.vals_a.p);
   LB_LAUNCH_CHECK(c);
   // voxel indices are < 2^31 by pcl's own guard: four 8-bit passes
-  unsigned* digit_totals = s.hist.p + (size_t)256 * n_tiles;
-  unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
-  int *va = s.vals_a.p, *vb = s.vals_b.p;
-  for (int p = 0; p < 4; p++) {
-    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, n, p * 8, s.hist.p, n_tiles);
-    LB_LAUNCH_CHECK(c);
-    radix_scan_digits_kernel<<<256, 256, 0, c->stream>>>(s.hist.p, n_tiles, digit_totals);
-    LB_LAUNCH_CHECK(c);
-    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, n, p * 8, s.hist.p, n_tiles, digit_totals, kb, vb);
-    LB_LAUNCH_CHECK(c);
-    unsigned* tk = ka; ka = kb; kb = tk;
-    int* tv = va; va = vb; vb = tv;
+  unsigned* ka = nullptr;
+  int* va = nullptr;
+  {
+    const int rc = radix_sort_pairs(c, n, 32, &ka, &va);
+    if (rc) return rc;
   }
   const int nb = (n + SCAN_BS - 1) / SCAN_BS;
   LB_CUDA(c, c->vox_key.reserve((size_t)n + nb + 8));
@@ -161,11 +157,9 @@ inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float l
   unsigned* bsum = c->vox_key.p + n;
   voxel_head_kernel<<<nb, SCAN_BS, 0, c->stream>>>(ka, n, pos, bsum);
   LB_LAUNCH_CHECK(c);
-  radix_scan_kernel<<<1, 1024, 0, c->stream>>>(bsum, nb + 1);  // exclusive; entry nb receives the grand total
+  radix_scan_kernel<<<1, 1024, 0, c->stream>>>(bsum, nb + 1, d_count);  // entry nb = number of voxels, mirrored to d_count
   LB_LAUNCH_CHECK(c);
   voxel_centroid_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, ka, va, pos, bsum, n, d_out);
-  LB_LAUNCH_CHECK(c);
-  copy_u32_kernel<<<1, 32, 0, c->stream>>>(bsum + nb, d_count);
   LB_LAUNCH_CHECK(c);
   return LOAM_B200_OK;
 }
