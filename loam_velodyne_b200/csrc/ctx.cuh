@@ -179,6 +179,7 @@ struct loam_b200_ctx {
   int od_nsharp = 0, od_nflat = 0;
   loamb::DevBuf<int> od_ind;   // (n_sharp + n_flat) x 3 persisted correspondence indices
   bool od_last_set = false;
+  bool od_rebuild_pending = false;
 
   // device-resident clouds of the stage API
   loamb::DevBuf<float4> cloud[LOAM_B200_NUM_CLOUDS];

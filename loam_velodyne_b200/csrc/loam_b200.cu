@@ -1,5 +1,6 @@
 // libloam_b200.so -- extern "C" entry points (include/loam_b200.h) over the sm_100a kernels.
 // There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point fails loudly.
+#include <chrono>
 #include <cmath>
 
 #include "ctx.cuh"
@@ -114,7 +115,7 @@ int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m, con
   GridMeta* meta = reinterpret_cast<GridMeta*>(g.meta.p);
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
-  const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 8);
+  const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 2);
   bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(d_pts, m, bb, n_dev);
   LB_LAUNCH_CHECK(c);
   grid_meta_kernel<<<1, 32, 0, c->stream>>>(bb, meta);
@@ -156,7 +157,7 @@ int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
   unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
-  const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 8);
+  const int bbox_blocks = std::min(blocks_for(m, 256), c->sm_count * 2);
   bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(t.points(), m, bb);
   LB_LAUNCH_CHECK(c);
   morton_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(t.points(), m, bb, s.keys_a.p, s.vals_a.p);
@@ -245,6 +246,13 @@ void fill_odom_args(const loam_b200_odom_pose* p, OdomIterArgs& a) {
   a.k12 = ty * crx * srz;  a.k13 = tx * crx * crz;
   a.atx_y = crx * srz;  a.aty_y = crx * crz;
   a.atz_x = crx * sry;  a.atz_y = srx;  a.atz_z = crx * cry;
+}
+
+// BVHs of the last clouds are rebuilt asynchronously on lanes 1 / 2 (loam_b200_odom_rebuild_last)
+cudaError_t odom_join_rebuild(loam_b200_ctx* c) {
+  if (!c->od_rebuild_pending) return cudaSuccess;
+  c->od_rebuild_pending = false;
+  return lanes_join(c, 2);
 }
 
 int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
@@ -695,6 +703,7 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
   CHECK_CTX(c);
   if (!pose || !out) return LOAM_B200_ERR_ARG;
   if (!c->od_last_set) return LOAM_B200_ERR_STATE;
+  LB_CUDA(c, odom_join_rebuild(c));
   const int nsh = c->od_nsharp, nfl = c->od_nflat;
   memset(out, 0, sizeof *out);
   if (nsh + nfl == 0) return LOAM_B200_OK;

@@ -137,7 +137,7 @@ inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float l
   const float inv = 1.0f / leaf;
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
-  const int bbox_blocks = std::min((n + 255) / 256, c->sm_count * 8);
+  const int bbox_blocks = std::min((n + 255) / 256, c->sm_count * 2);
   bbox_kernel<<<bbox_blocks, 256, 0, c->stream>>>(d_in, n, bb);
   LB_LAUNCH_CHECK(c);
   voxel_meta_kernel<<<1, 32, 0, c->stream>>>(bb, inv, meta);
