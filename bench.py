@@ -165,7 +165,10 @@ def run_cuda(args, rank, world, local_rank):
     value = streams * args.steps / el_dev
     del pipe_dev
 
-    # ---- arm 2 ("e2e"): host buffers through the reference-facing call, H2D of the sweep and D2H of the poses inside
+    # ---- arm 2 ("e2e"): host buffers through the reference-facing call, H2D of the sweep and D2H of the poses inside.
+    # The sweeps sit in pinned host memory (contract: "from pinned host memory"); the library just sees host pointers.
+    pinned = [torch.from_numpy(p).pin_memory() for p, _ in sweeps]
+    sweeps = [(pinned[i].numpy(), sweeps[i][1]) for i in range(len(sweeps))]
     pipe = api.Pipeline()
     pipe.seed_map(corner, surf)
     if sharded:
