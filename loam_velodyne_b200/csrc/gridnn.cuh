@@ -106,73 +106,108 @@ struct Top5 {
   int idx[5];
 };
 
-__device__ __forceinline__ void top5_offer(Top5& r, const float4& p, float qx, float qy, float qz) {
-  const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-  const float d = dx * dx + dy * dy + dz * dz;
+// ---- eight lanes per query ------------------------------------------------------------------------------------
+// The scan-to-map stage has only ~18 k queries per launch; one thread per query leaves a B200 at ~4 warps per SM and
+// the kernel was a serial latency chain (profiles/r1_v3_map_iterate_grid_tpq.md: 13.5 k instructions per warp, 6 % of
+// the warp slots, 11 % issue utilisation).  Eight lanes share a query instead: lane s probes cells s, s+8, s+16, s+24
+// of the 3 x 3 x 3 block and keeps a private top-5 (distance, position in the sorted cloud) over the points of its own
+// cells; five rounds of an 8-lane shuffle arg-min ("take the smallest head, advance that lane") merge the private
+// lists into the exact global top-5.  Ties are broken by position in the sorted cloud (deterministic).
+struct Cand5 {
+  float d[5];
+  int id[5];
+};
+
+__device__ __forceinline__ void cand5_offer(Cand5& r, float d, int id) {
   if (d < r.d[4]) {
-    float cd = d, cx = p.x, cy = p.y, cz = p.z;
-    int ci = __float_as_int(p.w);
+    float cd = d;
+    int ci = id;
 #pragma unroll
     for (int s = 0; s < 5; s++) {
       if (cd < r.d[s]) {
-        const float td = r.d[s], tx = r.x[s], ty = r.y[s], tz = r.z[s];
-        const int ti = r.idx[s];
-        r.d[s] = cd; r.x[s] = cx; r.y[s] = cy; r.z[s] = cz; r.idx[s] = ci;
-        cd = td; cx = tx; cy = ty; cz = tz; ci = ti;
+        const float td = r.d[s];
+        const int ti = r.id[s];
+        r.d[s] = cd; r.id[s] = ci;
+        cd = td; ci = ti;
       }
     }
   }
 }
 
-// Exact 5 nearest map points with d2 < 1.0 (idx[j] = -1 for missing ones).  stats[0] += table probes,
-// stats[1] += candidate points read (when STATS).
+// All 8 lanes of the group call this with the same query; on return every lane holds the group's exact 5 nearest
+// (d2 < 1.0) in `out` (ascending; id = -1 for missing ones).  gmask = the group's 8 lanes within the warp.
 template <bool STATS>
-__device__ __forceinline__ void grid_knn5(const GridView& g, float qx, float qy, float qz, Top5& r, unsigned* stats) {
+__device__ __forceinline__ void grid_knn5_group8(const GridView& g, float qx, float qy, float qz, int sub,
+                                                 unsigned gmask, Cand5& out, unsigned* stats) {
+  Cand5 mine;
 #pragma unroll
-  for (int i = 0; i < 5; i++) { r.d[i] = 1.0f; r.idx[i] = -1; r.x[i] = 0.f; r.y[i] = 0.f; r.z[i] = 0.f; }
-  if (g.m <= 0) return;
+  for (int i = 0; i < 5; i++) { mine.d[i] = 1.0f; mine.id[i] = -1; }
   const GridMeta gm = *g.meta;
   const int cx = (int)floorf(qx) - gm.ox, cy = (int)floorf(qy) - gm.oy, cz = (int)floorf(qz) - gm.oz;
-  // outside the occupied volume by more than one cell: nothing within 1 m
-  if (cx < -1 || cy < -1 || cz < -1 || cx > gm.nx || cy > gm.ny || cz > gm.nz) return;
-#pragma unroll 1
-  for (int dz = -1; dz <= 1; dz++) {
-    const int z = cz + dz;
-    if (z < 0 || z >= gm.nz) continue;
-    // nine probes of this z-slice in flight together
-    unsigned start[9], count[9];
+  const bool inside = g.m > 0 && !(cx < -1 || cy < -1 || cz < -1 || cx > gm.nx || cy > gm.ny || cz > gm.nz);
+  if (inside) {
+    // this lane's (up to four) cells: all probes issued before any candidate is touched
+    unsigned start[4], count[4];
 #pragma unroll
-    for (int t = 0; t < 9; t++) {
-      const int y = cy + (t / 3) - 1, x = cx + (t % 3) - 1;
-      count[t] = 0;
-      start[t] = 0;
-      if (y < 0 || y >= gm.ny || x < 0 || x >= gm.nx) continue;
-      const unsigned key = grid_key(gm, x, y, z);
-      unsigned h = grid_hash(key) & g.mask;
-      uint4 e = __ldg(&g.table[h]);
-      if (STATS) stats[0]++;
-      while (e.x != 0u && e.x != key + 1u) {  // collisions are rare at the table's load factor
-        h = (h + 1) & g.mask;
-        e = __ldg(&g.table[h]);
-        if (STATS) stats[0]++;
+    for (int r = 0; r < 4; r++) {
+      const int t = sub + 8 * r;
+      start[r] = 0;
+      count[r] = 0;
+      if (t < 27) {
+        const int z = cz + t / 9 - 1, y = cy + (t / 3) % 3 - 1, x = cx + t % 3 - 1;
+        if (z >= 0 && z < gm.nz && y >= 0 && y < gm.ny && x >= 0 && x < gm.nx) {
+          const unsigned key = grid_key(gm, x, y, z);
+          unsigned h = grid_hash(key) & g.mask;
+          uint4 e = __ldg(&g.table[h]);
+          if (STATS) stats[0]++;
+          while (e.x != 0u && e.x != key + 1u) {
+            h = (h + 1) & g.mask;
+            e = __ldg(&g.table[h]);
+            if (STATS) stats[0]++;
+          }
+          if (e.x == key + 1u) { start[r] = e.y; count[r] = e.z; }
+        }
       }
-      if (e.x == key + 1u) { start[t] = e.y; count[t] = e.z; }
     }
 #pragma unroll
-    for (int t = 0; t < 9; t++) {
-      const unsigned n = count[t];
-      const float4* src = g.sorted + start[t];
-      for (unsigned i = 0; i < n; i += 4) {
+    for (int r = 0; r < 4; r++) {
+      const unsigned n = count[r];
+      const float4* src = g.sorted + start[r];
+      for (unsigned i = 0; i < n; i += 2) {
         const float4 p0 = __ldg(src + i);
         const float4 p1 = (i + 1 < n) ? __ldg(src + i + 1) : p0;
-        const float4 p2 = (i + 2 < n) ? __ldg(src + i + 2) : p0;
-        const float4 p3 = (i + 3 < n) ? __ldg(src + i + 3) : p0;
-        top5_offer(r, p0, qx, qy, qz);
-        if (i + 1 < n) top5_offer(r, p1, qx, qy, qz);
-        if (i + 2 < n) top5_offer(r, p2, qx, qy, qz);
-        if (i + 3 < n) top5_offer(r, p3, qx, qy, qz);
+        {
+          const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;
+          cand5_offer(mine, dx * dx + dy * dy + dz * dz, (int)(start[r] + i));
+        }
+        if (i + 1 < n) {
+          const float dx = qx - p1.x, dy = qy - p1.y, dz = qz - p1.z;
+          cand5_offer(mine, dx * dx + dy * dy + dz * dz, (int)(start[r] + i + 1));
+        }
       }
       if (STATS) stats[1] += n;
+    }
+  }
+  // merge the eight private lists: five rounds of "smallest head wins, winner advances"
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    float bd = mine.d[0];
+    int bi = mine.id[0];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(gmask, bd, o);
+      const int oi = __shfl_xor_sync(gmask, bi, o);
+      // empty heads (id < 0) never win against a real candidate; among real ones (distance, position) ascending
+      const bool take = (oi >= 0) && (bi < 0 || od < bd || (od == bd && oi < bi));
+      if (take) { bd = od; bi = oi; }
+    }
+    out.d[k] = bd;
+    out.id[k] = bi;
+    if (bi >= 0 && bi == mine.id[0]) {  // my head won: advance
+#pragma unroll
+      for (int s = 0; s < 4; s++) { mine.d[s] = mine.d[s + 1]; mine.id[s] = mine.id[s + 1]; }
+      mine.d[4] = 1.0f;
+      mine.id[4] = -1;
     }
   }
 }

@@ -609,7 +609,7 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   const int c0 = (int)((long long)nc * R / W), c1 = (int)((long long)nc * (R + 1) / W);
   const int s0 = (int)((long long)ns * R / W), s1 = (int)((long long)ns * (R + 1) / W);
   const int lc = c1 - c0, ls = s1 - s0;
-  const int cb = blocks_for(lc, LM_THREADS), sb = blocks_for(ls, LM_THREADS);
+  const int cb = blocks_for(lc, MAP_Q_PER_BLOCK), sb = blocks_for(ls, MAP_Q_PER_BLOCK);
   const int nb = std::max(cb + sb, 1);
   LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
   const bool dbg = coeff != nullptr;

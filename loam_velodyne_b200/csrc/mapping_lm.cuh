@@ -1,5 +1,5 @@
 // Fused scan-to-map Gauss-Newton iteration.
-// One thread per stack point: pointAssociateToMap (BasicLaserMapping.cpp:207-219) -> exact 5-NN against the corner /
+// Eight lanes per stack point: pointAssociateToMap (BasicLaserMapping.cpp:207-219) -> exact 5-NN against the corner /
 // surface map through the 1 m uniform grid of gridnn.cuh, the d5^2 < 1.0 gate (:669-671, :758-760) being what makes
 // the fixed-radius search exact -> PCA line fit (:673-710) or
 // 5x3 least-squares plane fit (:762-791) -> residual weight (:712-749, :795-814) -> Jacobian row (:842-861) ->
@@ -153,62 +153,88 @@ __device__ __forceinline__ void reduce_normal_equations(float* acc, float* __res
   __syncthreads();
   if (s_last) {
     __threadfence();
+    // fixed summation order -> run-to-run deterministic: warp w folds blocks w, w+4, w+8, ... in double, then the four
+    // warp sums are added in warp order
+    __shared__ double s_fold[LM_THREADS / 32][NEQ];
+    {
+      double v = 0.0;
+      for (unsigned bk = warp; bk < gridDim.x; bk += LM_THREADS / 32) v += (double)__ldcg(&partials[(size_t)bk * NEQ + lane]);
+      s_fold[warp][lane] = v;
+    }
+    __syncthreads();
     if (threadIdx.x < NEQ) {
       double v = 0.0;
-      for (unsigned bk = 0; bk < gridDim.x; bk++) v += (double)__ldcg(&partials[(size_t)bk * NEQ + threadIdx.x]);
+      for (int wv = 0; wv < LM_THREADS / 32; wv++) v += s_fold[wv][threadIdx.x];
       result[threadIdx.x] = (float)v;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
 }
 
+constexpr int MAP_GROUP = 8;                          // lanes per query
+constexpr int MAP_Q_PER_BLOCK = LM_THREADS / MAP_GROUP;
+
 template <bool STATS>
 __global__ void __launch_bounds__(LM_THREADS)
 map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __restrict__ queries, int n_corner_total,
                    int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a,
-                   float* __restrict__ partials,
-                   float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
-                   int8_t* __restrict__ dbg_sel, unsigned long long* __restrict__ walk_totals) {
+                   float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
+                   float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
+                   unsigned long long* __restrict__ walk_totals) {
   float acc[29];
 #pragma unroll
   for (int k = 0; k < 29; k++) acc[k] = 0.f;
 
+  const int lane = threadIdx.x & 31, sub = lane & (MAP_GROUP - 1);
+  const unsigned gmask = 0xffu << (lane & ~(MAP_GROUP - 1));
   const bool is_corner = (int)blockIdx.x < corner_blocks;
-  const int local = is_corner ? blockIdx.x * LM_THREADS + threadIdx.x
-                              : (blockIdx.x - corner_blocks) * LM_THREADS + threadIdx.x;
+  const int local = (is_corner ? blockIdx.x : blockIdx.x - corner_blocks) * MAP_Q_PER_BLOCK + (threadIdx.x / MAP_GROUP);
   // this rank's slice: corners [c0, c0 + n_corner), surfaces [s0, s0 + n_surf) (the whole range on one GPU)
   const int qi = is_corner ? c0 + local : n_corner_total + s0 + local;
-  const bool active = is_corner ? (local < n_corner) : (local < n_surf);
+  const bool active = is_corner ? (local < n_corner) : (local < n_surf);  // uniform within a group of 8 lanes
   if (active) {
     const float4 po = queries[qi];
     float sx, sy, sz;
     associate_to_map(a, po, sx, sy, sz);
-    Top5 nn;
+    const GridView& grid = is_corner ? corner_grid : surf_grid;
+    Cand5 best;
     unsigned ws[2] = {0u, 0u};
-    grid_knn5<STATS>(is_corner ? corner_grid : surf_grid, sx, sy, sz, nn, ws);
+    grid_knn5_group8<STATS>(grid, sx, sy, sz, sub, gmask, best, ws);
     if (STATS) {
       atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
       atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
     }
-    float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool sel = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
-    if (dbg_coeff) {
-      dbg_coeff[qi] = coeff;
-      dbg_sel[qi] = sel ? 1 : 0;
-    }
-    if (sel) {
-      float row[6];
-      row[0] = (a.A[0] * po.x + a.A[1] * po.y + a.A[2] * po.z) * coeff.x +
-               (a.A[3] * po.x + a.A[4] * po.y + a.A[5] * po.z) * coeff.y +
-               (a.A[6] * po.x + a.A[7] * po.y + a.A[8] * po.z) * coeff.z;
-      row[1] = (a.B[0] * po.x + a.B[1] * po.y + a.B[2] * po.z) * coeff.x +
-               (a.B[6] * po.x + a.B[7] * po.y + a.B[8] * po.z) * coeff.z;
-      row[2] = (a.C[0] * po.x + a.C[1] * po.y) * coeff.x + (a.C[3] * po.x + a.C[4] * po.y) * coeff.y +
-               (a.C[6] * po.x + a.C[7] * po.y) * coeff.z;
-      row[3] = coeff.x;
-      row[4] = coeff.y;
-      row[5] = coeff.z;
-      accumulate_row(acc, row, -coeff.w, is_corner);
+    if (sub == 0) {
+      // one lane per query fits the line / plane through the five neighbours and forms the Jacobian row
+      Top5 nn;
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        nn.d[j] = best.d[j];
+        nn.idx[j] = best.id[j];
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (best.id[j] >= 0) p = __ldg(&grid.sorted[best.id[j]]);
+        nn.x[j] = p.x; nn.y[j] = p.y; nn.z[j] = p.z;
+      }
+      float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool sel = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
+      if (dbg_coeff) {
+        dbg_coeff[qi] = coeff;
+        dbg_sel[qi] = sel ? 1 : 0;
+      }
+      if (sel) {
+        float row[6];
+        row[0] = (a.A[0] * po.x + a.A[1] * po.y + a.A[2] * po.z) * coeff.x +
+                 (a.A[3] * po.x + a.A[4] * po.y + a.A[5] * po.z) * coeff.y +
+                 (a.A[6] * po.x + a.A[7] * po.y + a.A[8] * po.z) * coeff.z;
+        row[1] = (a.B[0] * po.x + a.B[1] * po.y + a.B[2] * po.z) * coeff.x +
+                 (a.B[6] * po.x + a.B[7] * po.y + a.B[8] * po.z) * coeff.z;
+        row[2] = (a.C[0] * po.x + a.C[1] * po.y) * coeff.x + (a.C[3] * po.x + a.C[4] * po.y) * coeff.y +
+                 (a.C[6] * po.x + a.C[7] * po.y) * coeff.z;
+        row[3] = coeff.x;
+        row[4] = coeff.y;
+        row[5] = coeff.z;
+        accumulate_row(acc, row, -coeff.w, is_corner);
+      }
     }
   }
   reduce_normal_equations(acc, partials, result, ticket);
