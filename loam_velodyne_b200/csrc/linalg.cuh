@@ -67,41 +67,92 @@ LB_HD void householder_apply_left(float* A, int rows, int cols, int ld, const fl
 
 // ---------------------------------------------------------------- column-pivoted Householder QR solve
 // Solves min ||A x - b|| for A (R x C, column-major, destroyed) and b (R, destroyed); x (C).
+// Every loop bound is a compile-time constant and the pivot column is applied through predicated swaps with static
+// indices, so after unrolling the whole factorisation lives in registers on the device (the per-query 5 x 3 plane fit
+// runs ~17 k times per LM iteration; with a dynamically indexed pivot the arrays went to local memory and the fit
+// dominated the kernel: profiles/r1_v3_map_iterate_grid_tpq.md).  The arithmetic (operations and their order) is
+// unchanged, so host and device still agree bit for bit with each other and with the previous formulation.
 template <int R, int C>
 LB_HD void colpiv_qr_solve(float* A, float* b, float* x) {
   constexpr int SIZE = R < C ? R : C;
   float h[SIZE];
-  int transp[SIZE];
   float nUpd[C], nDir[C];
+  int perm[C];
   float maxNorm = 0.f;
+#pragma unroll
   for (int k = 0; k < C; k++) {
     float s = 0.f;
+#pragma unroll
     for (int i = 0; i < R; i++) s += A[i + k * R] * A[i + k * R];
     nDir[k] = lb_sqrt(s);
     nUpd[k] = nDir[k];
     if (nUpd[k] > maxNorm) maxNorm = nUpd[k];
+    perm[k] = k;
   }
   const float eps = FLT_EPSILON;
   const float thr0 = maxNorm * eps;
   const float threshold_helper = thr0 * thr0 / float(R);
   const float downdate_thr = lb_sqrt(eps);
   int nonzero = SIZE;
+#pragma unroll
   for (int k = 0; k < SIZE; k++) {
     int big = k;
     float bigNorm = nUpd[k];
+#pragma unroll
     for (int j = k + 1; j < C; j++)
       if (nUpd[j] > bigNorm) { bigNorm = nUpd[j]; big = j; }
     if (nonzero == SIZE && bigNorm * bigNorm < threshold_helper * float(R - k)) nonzero = k;
-    transp[k] = big;
-    if (big != k) {
-      for (int i = 0; i < R; i++) { float t = A[i + k * R]; A[i + k * R] = A[i + big * R]; A[i + big * R] = t; }
-      float t = nUpd[k]; nUpd[k] = nUpd[big]; nUpd[big] = t;
-      t = nDir[k]; nDir[k] = nDir[big]; nDir[big] = t;
+    // bring the pivot column to position k (static indices, predicated on the pivot choice)
+#pragma unroll
+    for (int j = k + 1; j < C; j++) {
+      if (big == j) {
+#pragma unroll
+        for (int i = 0; i < R; i++) { const float t = A[i + k * R]; A[i + k * R] = A[i + j * R]; A[i + j * R] = t; }
+        float t = nUpd[k]; nUpd[k] = nUpd[j]; nUpd[j] = t;
+        t = nDir[k]; nDir[k] = nDir[j]; nDir[j] = t;
+        const int ti = perm[k]; perm[k] = perm[j]; perm[j] = ti;
+      }
     }
-    float beta;
-    householder_make<R>(A + k + k * R, R - k, h[k], beta);
+    // Householder vector of column k below the diagonal (LAPACK xLARFG convention: beta = -sign(x0) * ||x||)
+    float tau, beta;
+    {
+      float tail = 0.f;
+#pragma unroll
+      for (int i = k + 1; i < R; i++) tail += A[i + k * R] * A[i + k * R];
+      const float c0 = A[k + k * R];
+      if (R - k == 1 || tail <= FLT_MIN) {
+        tau = 0.f;
+        beta = c0;
+#pragma unroll
+        for (int i = k + 1; i < R; i++) A[i + k * R] = 0.f;
+      } else {
+        beta = lb_sqrt(c0 * c0 + tail);
+        if (c0 >= 0.f) beta = -beta;
+        const float den = c0 - beta;
+#pragma unroll
+        for (int i = k + 1; i < R; i++) A[i + k * R] = A[i + k * R] / den;
+        tau = (beta - c0) / beta;
+      }
+    }
+    h[k] = tau;
     A[k + k * R] = beta;
-    householder_apply_left(A + k + (k + 1) * R, R - k, C - k - 1, R, A + (k + 1) + k * R, h[k]);
+    // apply (I - tau v v^T) to the trailing columns
+    if (R - k == 1) {
+#pragma unroll
+      for (int j = k + 1; j < C; j++) A[k + j * R] *= (1.f - tau);
+    } else if (tau != 0.f) {
+#pragma unroll
+      for (int j = k + 1; j < C; j++) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = k + 1; i < R; i++) t += A[i + k * R] * A[i + j * R];
+        t += A[k + j * R];
+        A[k + j * R] -= tau * t;
+#pragma unroll
+        for (int i = k + 1; i < R; i++) A[i + j * R] -= tau * A[i + k * R] * t;
+      }
+    }
+#pragma unroll
     for (int j = k + 1; j < C; j++) {
       if (nUpd[j] != 0.f) {
         float t = lb_abs(A[k + j * R]) / nUpd[j];
@@ -111,6 +162,7 @@ LB_HD void colpiv_qr_solve(float* A, float* b, float* x) {
         const float t2 = t * (ratio * ratio);
         if (t2 <= downdate_thr) {
           float s = 0.f;
+#pragma unroll
           for (int i = k + 1; i < R; i++) s += A[i + j * R] * A[i + j * R];
           nDir[j] = lb_sqrt(s);
           nUpd[j] = nDir[j];
@@ -120,21 +172,47 @@ LB_HD void colpiv_qr_solve(float* A, float* b, float* x) {
       }
     }
   }
-  int perm[C];
-  for (int k = 0; k < C; k++) perm[k] = k;
-  for (int k = 0; k < SIZE; k++) { int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
   if (nonzero == 0) {
+#pragma unroll
     for (int i = 0; i < C; i++) x[i] = 0.f;
     return;
   }
-  for (int k = 0; k < nonzero; k++) householder_apply_left(b + k, R - k, 1, R, A + (k + 1) + k * R, h[k]);
-  for (int i = nonzero - 1; i >= 0; i--) {
-    float v = b[i];
-    for (int l = i + 1; l < nonzero; l++) v -= A[i + l * R] * b[l];
-    b[i] = v / A[i + i * R];
+  // c = Q^T b (reflectors 0 .. nonzero-1), back substitution on the leading nonzero x nonzero triangle
+#pragma unroll
+  for (int k = 0; k < SIZE; k++) {
+    if (k < nonzero) {
+      const float tau = h[k];
+      if (R - k == 1) {
+        b[k] *= (1.f - tau);
+      } else if (tau != 0.f) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = k + 1; i < R; i++) t += A[i + k * R] * b[i];
+        t += b[k];
+        b[k] -= tau * t;
+#pragma unroll
+        for (int i = k + 1; i < R; i++) b[i] -= tau * A[i + k * R] * t;
+      }
+    }
   }
-  for (int i = 0; i < nonzero; i++) x[perm[i]] = b[i];
-  for (int i = nonzero; i < C; i++) x[perm[i]] = 0.f;
+#pragma unroll
+  for (int i = SIZE - 1; i >= 0; i--) {
+    if (i < nonzero) {
+      float v = b[i];
+#pragma unroll
+      for (int l = i + 1; l < SIZE; l++)
+        if (l < nonzero) v -= A[i + l * R] * b[l];
+      b[i] = v / A[i + i * R];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < C; j++) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < SIZE; i++)
+      if (i < nonzero && perm[i] == j) v = b[i];
+    x[j] = v;
+  }
 }
 
 // ---------------------------------------------------------------- symmetric eigen-solver
