@@ -109,10 +109,15 @@ struct Top5 {
 // ---- eight lanes per query ------------------------------------------------------------------------------------
 // The scan-to-map stage has only ~18 k queries per launch; one thread per query leaves a B200 at ~4 warps per SM and
 // the kernel was a serial latency chain (profiles/r1_v3_map_iterate_grid_tpq.md: 13.5 k instructions per warp, 6 % of
-// the warp slots, 11 % issue utilisation).  Eight lanes share a query instead: lane s probes cells s, s+8, s+16, s+24
-// of the 3 x 3 x 3 block and keeps a private top-5 (distance, position in the sorted cloud) over the points of its own
-// cells; five rounds of an 8-lane shuffle arg-min ("take the smallest head, advance that lane") merge the private
-// lists into the exact global top-5.  Ties are broken by position in the sorted cloud (deterministic).
+// the warp slots, 11 % issue utilisation).  Eight lanes share a query instead:
+//   probe   : lane s looks up cells s, s+8, s+16, s+24 of the 3 x 3 x 3 block (all probes issued before any use);
+//   balance : the 27 (start, count) pairs go to shared memory with an exclusive prefix of the counts, so the block's
+//             candidates form ONE flattened list of T points; lane s takes candidates s, s+8, s+16, ... whatever cell
+//             they come from (the first version let every lane walk its own cells: 8-9 of 32 lanes active in the
+//             candidate loop because the centre cells hold most of the points, profiles/r1_v4_map_iterate_8lane.md);
+//   merge   : each lane keeps a private top-5 (distance, position in the sorted cloud); five rounds of an 8-lane
+//             shuffle arg-min ("take the smallest head, advance that lane") give the exact global top-5.
+// Ties are broken by position in the sorted cloud (deterministic).
 struct Cand5 {
   float d[5];
   int id[5];
@@ -134,19 +139,22 @@ __device__ __forceinline__ void cand5_offer(Cand5& r, float d, int id) {
   }
 }
 
+constexpr int GRID_SLOTS = 32;  // flattened cell slots per query: slot = lane * 4 + r (27 used)
+
 // All 8 lanes of the group call this with the same query; on return every lane holds the group's exact 5 nearest
-// (d2 < 1.0) in `out` (ascending; id = -1 for missing ones).  gmask = the group's 8 lanes within the warp.
+// (d2 < 1.0) in `out` (ascending; id = -1 for missing ones).  gmask = the group's 8 lanes within the warp;
+// pre[GRID_SLOTS + 1] / first[GRID_SLOTS] = this group's rows of shared memory.
 template <bool STATS>
 __device__ __forceinline__ void grid_knn5_group8(const GridView& g, float qx, float qy, float qz, int sub,
-                                                 unsigned gmask, Cand5& out, unsigned* stats) {
+                                                 unsigned gmask, unsigned* pre, unsigned* first, Cand5& out,
+                                                 unsigned* stats) {
   Cand5 mine;
 #pragma unroll
   for (int i = 0; i < 5; i++) { mine.d[i] = 1.0f; mine.id[i] = -1; }
   const GridMeta gm = *g.meta;
   const int cx = (int)floorf(qx) - gm.ox, cy = (int)floorf(qy) - gm.oy, cz = (int)floorf(qz) - gm.oz;
   const bool inside = g.m > 0 && !(cx < -1 || cy < -1 || cz < -1 || cx > gm.nx || cy > gm.ny || cz > gm.nz);
-  if (inside) {
-    // this lane's (up to four) cells: all probes issued before any candidate is touched
+  if (inside) {  // uniform over the group
     unsigned start[4], count[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -169,23 +177,47 @@ __device__ __forceinline__ void grid_knn5_group8(const GridView& g, float qx, fl
         }
       }
     }
+    // exclusive prefix of the counts in slot order
+    const unsigned local = count[0] + count[1] + count[2] + count[3];
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned y = __shfl_up_sync(gmask, incl, o, 8);
+      if (sub >= o) incl += y;
+    }
+    const unsigned total = __shfl_sync(gmask, incl, 7, 8);
+    unsigned run = incl - local;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const unsigned n = count[r];
-      const float4* src = g.sorted + start[r];
-      for (unsigned i = 0; i < n; i += 2) {
-        const float4 p0 = __ldg(src + i);
-        const float4 p1 = (i + 1 < n) ? __ldg(src + i + 1) : p0;
-        {
-          const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;
-          cand5_offer(mine, dx * dx + dy * dy + dz * dz, (int)(start[r] + i));
-        }
-        if (i + 1 < n) {
-          const float dx = qx - p1.x, dy = qy - p1.y, dz = qz - p1.z;
-          cand5_offer(mine, dx * dx + dy * dy + dz * dz, (int)(start[r] + i + 1));
-        }
+      pre[sub * 4 + r] = run;
+      first[sub * 4 + r] = start[r];
+      run += count[r];
+    }
+    if (sub == 7) pre[GRID_SLOTS] = total;
+    __syncwarp(gmask);
+    if (STATS && sub == 0) stats[1] += total;
+    // walk the flattened list with stride 8, two loads in flight
+    unsigned f = 0, lo = 0, hi = pre[1];
+    for (unsigned j = sub; j < total; j += 16) {
+      while (j >= hi) { f++; lo = hi; hi = pre[f + 1]; }
+      const int i0 = (int)(first[f] + (j - lo));
+      const float4 p0 = __ldg(g.sorted + i0);
+      const unsigned j1 = j + 8;
+      int i1 = -1;
+      float4 p1 = p0;
+      if (j1 < total) {
+        while (j1 >= hi) { f++; lo = hi; hi = pre[f + 1]; }
+        i1 = (int)(first[f] + (j1 - lo));
+        p1 = __ldg(g.sorted + i1);
       }
-      if (STATS) stats[1] += n;
+      {
+        const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;
+        cand5_offer(mine, dx * dx + dy * dy + dz * dz, i0);
+      }
+      if (i1 >= 0) {
+        const float dx = qx - p1.x, dy = qy - p1.y, dz = qz - p1.z;
+        cand5_offer(mine, dx * dx + dy * dy + dz * dz, i1);
+      }
     }
   }
   // merge the eight private lists: five rounds of "smallest head wins, winner advances"

@@ -624,7 +624,7 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   if (walk_totals_host) {
     LB_CUDA(c, c->walk_totals.reserve(2));
     LB_CUDA(c, cudaMemsetAsync(c->walk_totals.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    map_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(
+    map_iterate_kernel<true><<<nb, MAP_THREADS, 0, c->stream>>>(
         grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, c0, lc, s0, ls, cb,
         a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
     LB_LAUNCH_CHECK(c);
@@ -632,7 +632,7 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
                                cudaMemcpyDeviceToHost, c->stream));
   } else {
     prof_begin(c, LOAM_B200_K_MAP_ITER);
-    map_iterate_kernel<false><<<nb, LM_THREADS, 0, c->stream>>>(
+    map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
         grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, c0, lc, s0, ls, cb,
         a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
         nullptr);

