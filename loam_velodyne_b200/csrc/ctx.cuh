@@ -127,7 +127,6 @@ struct SortScratch {
 struct loam_b200_ctx {
   int device = 0;
   int sm_count = 0;
-  int coop_blocks = 0;   // co-resident CTAs of radix_sort_coop_kernel (0 = use the three-kernel path)
   cudaStream_t stream = nullptr;
   std::string last_error;
   long long launches = 0;

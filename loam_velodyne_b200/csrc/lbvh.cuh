@@ -10,7 +10,6 @@
 //   bottom-up box refit.  Nodes are 64 B (both child boxes + links): one aligned 64 B read per visit.
 #pragma once
 
-#include <cooperative_groups.h>
 
 #include "ctx.cuh"
 
@@ -88,116 +87,121 @@ __global__ void morton_kernel(const float4* __restrict__ p, int m, const unsigne
   vals[i] = i;
 }
 
-// ---------------------------------------------------------------- LSD radix sort, 8 bits per pass, 4 passes
-// Per pass: (1) per-tile digit histogram, (2) exclusive scan over (digit, tile), (3) stable scatter.
+// ---------------------------------------------------------------- LSD radix sort, 8 bits per pass ("onesweep")
+// One histogram launch for all passes, then ONE launch per 8-bit digit: a CTA takes the next tile (atomic ticket),
+// ranks its keys per digit (stable: warp w owns consecutive keys, 32 at a time, match.any gives the rank among equal
+// digits), publishes the tile's digit counts and resolves its global offsets by decoupled look-back over the earlier
+// tiles' (aggregate | inclusive prefix) words -- no grid-wide barrier and no separate scan kernel.  The first version
+// (histogram / scan / scatter per pass, later one cooperative kernel with 12 grid syncs) cost ~100 us per sort whatever
+// the size and was half of the GPU time of a sweep (profiles/r1_v3_launch_list_summary.md).
+// A pass whose digit is the same for every key (e.g. the top byte of a 22-bit cell key) degenerates to a tile copy.
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;                        // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // keys per CTA
+constexpr int RS_MAX_PASSES = 4;
+constexpr unsigned RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_COUNT_MASK = (1u << 30) - 1u;
+// scratch header (unsigned words): [RS_MAX_PASSES][256] global digit counts, then RS_MAX_PASSES tile tickets (+ pad)
+constexpr int RS_HEADER = RS_MAX_PASSES * 256 + 8;
 
-// ---- per-tile / per-digit building blocks, shared by the three-kernel path and the single cooperative kernel
-__device__ __forceinline__ void radix_hist_tile(const unsigned* __restrict__ keys, int m, int shift,
-                                                unsigned* __restrict__ hist, int n_tiles, int tile, unsigned* h) {
-  h[threadIdx.x] = 0;
+__host__ __device__ inline int rs_items_for(int m) { return m < 200000 ? 4 : 16; }
+
+// histogram of every pass's digit in one read of the keys; also clears this tile's look-back words
+template <int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS)
+onesweep_hist_kernel(const unsigned* __restrict__ keys, int m, const int* __restrict__ n_dev, int passes,
+                     unsigned* __restrict__ header, unsigned* __restrict__ status, int n_tiles) {
+  __shared__ unsigned h[RS_MAX_PASSES][256];
+  if (n_dev) m = min(m, *n_dev);
+  const int tile = blockIdx.x;
+  for (int p = 0; p < passes; p++) {
+    h[p][threadIdx.x] = 0;
+    status[((size_t)p * n_tiles + tile) * 256 + threadIdx.x] = 0u;
+  }
   __syncthreads();
-  const int base = tile * RS_TILE;
-  for (int it = 0; it < RS_ITEMS; it++) {
+  const int base = tile * (RS_THREADS * ITEMS);
+  if (base >= m) return;
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
     const int i = base + it * RS_THREADS + threadIdx.x;
-    if (i < m) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
-  }
-  __syncthreads();
-  hist[(size_t)threadIdx.x * n_tiles + tile] = h[threadIdx.x];  // digit-major so one scan per digit gives offsets
-  __syncthreads();
-}
-
-// exclusive scan inside digit row d of the digit-major table by one CTA, + the row total
-__device__ __forceinline__ void radix_scan_row(unsigned* __restrict__ hist, int n_tiles,
-                                               unsigned* __restrict__ digit_totals, int d, unsigned* ws, unsigned* carry) {
-  unsigned* row = hist + (size_t)d * n_tiles;
-  if (threadIdx.x == 0) *carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n_tiles; base += RS_THREADS) {
-    const int i = base + threadIdx.x;
-    const unsigned v = i < n_tiles ? row[i] : 0u;
-    unsigned x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
+    if (i < m) {
+      const unsigned k = keys[i];
+      for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
     }
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-    __syncthreads();
-    unsigned woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += ws[w];
-    const unsigned incl = x + woff + *carry;
-    if (i < n_tiles) row[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == RS_THREADS - 1) *carry = incl;
-    __syncthreads();
   }
-  if (threadIdx.x == 0) digit_totals[d] = *carry;
   __syncthreads();
-}
-
-// same for short rows (n_tiles <= 32): one WARP per digit row
-__device__ __forceinline__ void radix_scan_row_warp(unsigned* __restrict__ hist, int n_tiles,
-                                                    unsigned* __restrict__ digit_totals, int d) {
-  const int lane = threadIdx.x & 31;
-  unsigned* row = hist + (size_t)d * n_tiles;
-  const unsigned v = lane < n_tiles ? row[lane] : 0u;
-  unsigned x = v;
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
+  for (int p = 0; p < passes; p++) {
+    const unsigned v = h[p][threadIdx.x];
+    if (v) atomicAdd(&header[p * 256 + threadIdx.x], v);
   }
-  if (lane < n_tiles) row[lane] = x - v;
-  const unsigned tot = __shfl_sync(0xffffffffu, x, 31);
-  if (lane == 0) digit_totals[d] = tot;
 }
 
-// stable scatter of one tile: each warp owns RS_ITEMS*32 consecutive keys and processes them 32 at a time;
-// rank within the CTA = (keys of the same digit in earlier warps) + (earlier keys of the same digit in this warp)
-struct RadixScatterSmem {
+struct OnesweepSmem {
   unsigned wcount[RS_THREADS / 32][256];
   unsigned gbase[256];
   unsigned dsum[RS_THREADS / 32];
+  int tile;
+  int uniform;
 };
-__device__ __forceinline__ void radix_scatter_tile(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in,
-                                                   int m, int shift, const unsigned* __restrict__ hist, int n_tiles,
-                                                   const unsigned* __restrict__ digit_totals,
-                                                   unsigned* __restrict__ keys_out, int* __restrict__ vals_out, int tile,
-                                                   RadixScatterSmem& sm) {
+
+template <int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS)
+onesweep_pass_kernel(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int m,
+                     const int* __restrict__ n_dev, int shift, const unsigned* __restrict__ digit_counts,
+                     unsigned* status, unsigned* ticket, unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
   constexpr int NW = RS_THREADS / 32;
+  constexpr int TILE = RS_THREADS * ITEMS;
+  __shared__ OnesweepSmem sm;
+  if (n_dev) m = min(m, *n_dev);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    sm.tile = (int)atomicAdd(ticket, 1u);
+    sm.uniform = 0;
+  }
   for (int d = lane; d < 256; d += 32) sm.wcount[warp][d] = 0;
+  // global digit base = exclusive scan of the 256 digit counts (thread d <-> digit d)
+  const unsigned dc = digit_counts[threadIdx.x];
+  unsigned digit_excl;
   {
-    // digit base = exclusive scan of the 256 digit totals (thread d <-> digit d), + this tile's offset inside the digit
-    const unsigned v = digit_totals[threadIdx.x];
-    unsigned x = v;
+    unsigned x = dc;
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
     }
     if (lane == 31) sm.dsum[warp] = x;
     __syncthreads();
+    if (dc == (unsigned)m && m > 0) sm.uniform = 1;  // every key has this digit: the pass is the identity
     unsigned woff = 0;
     for (int w = 0; w < warp; w++) woff += sm.dsum[w];
-    sm.gbase[threadIdx.x] = (x - v) + woff + hist[(size_t)threadIdx.x * n_tiles + tile];
+    digit_excl = (x - dc) + woff;
   }
-  __syncwarp();
-  const int wbase = tile * RS_TILE + warp * (RS_ITEMS * 32);
-  unsigned mykeys[RS_ITEMS];
-  unsigned short myrank[RS_ITEMS];
-  for (int it = 0; it < RS_ITEMS; it++) {
+  __syncthreads();
+  const int tile = sm.tile;
+  if ((long long)tile * TILE >= m) return;
+  if (sm.uniform) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const int i = tile * TILE + it * RS_THREADS + threadIdx.x;
+      if (i < m) {
+        keys_out[i] = keys_in[i];
+        vals_out[i] = vals_in[i];
+      }
+    }
+    return;
+  }
+  const int wbase = tile * TILE + warp * (ITEMS * 32);
+  unsigned mykeys[ITEMS];
+  int myvals[ITEMS];
+  unsigned short myrank[ITEMS];
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
     const int i = wbase + it * 32 + lane;
     const bool valid = i < m;
-    const unsigned k = valid ? keys_in[i] : 0xffffffffu;
-    mykeys[it] = k;
-    const unsigned d = (k >> shift) & 255u;
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-    for (int b = 0; b < 8; b++) {
-      const unsigned bit = (d >> b) & 1u;
-      const unsigned bal = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? bal : ~bal;
-    }
+    mykeys[it] = valid ? keys_in[i] : 0xffffffffu;
+    myvals[it] = valid ? vals_in[i] : 0;
+  }
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const bool valid = wbase + it * 32 + lane < m;
+    const unsigned d = valid ? ((mykeys[it] >> shift) & 255u) : 256u;  // invalid lanes only match each other
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
     const unsigned before = __popc(peers & ((1u << lane) - 1u));
     unsigned prior = 0;
     if (valid) prior = sm.wcount[warp][d];
@@ -208,32 +212,54 @@ __device__ __forceinline__ void radix_scatter_tile(const unsigned* __restrict__ 
   }
   __syncthreads();
   {
+    // thread d: per-warp exclusive offsets of digit d inside the tile, the tile total, then the look-back
     const int d = threadIdx.x;
     unsigned acc = 0;
+#pragma unroll
     for (int wv = 0; wv < NW; wv++) {
       const unsigned c = sm.wcount[wv][d];
       sm.wcount[wv][d] = acc;
       acc += c;
     }
+    volatile unsigned* st = status;
+    unsigned excl = 0;
+    if (tile == 0) {
+      st[d] = RS_FLAG_PREFIX | acc;
+    } else {
+      st[(size_t)tile * 256 + d] = RS_FLAG_AGG | acc;
+      int t = tile - 1;
+      bool done = false;
+      while (!done) {
+        // eight earlier tiles in flight; consume in order until an inclusive prefix (or a not-yet-published word)
+        unsigned v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (t - u >= 0) ? st[(size_t)(t - u) * 256 + d] : (2u << 30);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (done) break;
+          const unsigned flag = v[u] & ~RS_COUNT_MASK;
+          if (flag == 0u) break;  // not published yet: poll again from tile t
+          excl += v[u] & RS_COUNT_MASK;
+          t--;
+          if (flag == RS_FLAG_PREFIX) done = true;
+        }
+      }
+      st[(size_t)tile * 256 + d] = RS_FLAG_PREFIX | (excl + acc);
+    }
+    sm.gbase[d] = digit_excl + excl;
   }
   __syncthreads();
-  for (int it = 0; it < RS_ITEMS; it++) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
     const int i = wbase + it * 32 + lane;
     if (i < m) {
       const unsigned k = mykeys[it];
       const unsigned d = (k >> shift) & 255u;
       const unsigned dst = sm.gbase[d] + sm.wcount[warp][d] + myrank[it];
       keys_out[dst] = k;
-      vals_out[dst] = vals_in[i];
+      vals_out[dst] = myvals[it];
     }
   }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const unsigned* __restrict__ keys, int m, int shift, unsigned* __restrict__ hist, int n_tiles) {
-  __shared__ unsigned h[256];
-  radix_hist_tile(keys, m, shift, hist, n_tiles, blockIdx.x, h);
 }
 
 // exclusive scan of `total` counters by a single CTA (block sums of compactions / voxel heads)
@@ -270,52 +296,6 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__
     __syncthreads();
     if (threadIdx.x == 1023) carry = incl;
     __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(RS_THREADS)
-radix_scan_digits_kernel(unsigned* __restrict__ hist, int n_tiles, unsigned* __restrict__ digit_totals) {
-  __shared__ unsigned ws[RS_THREADS / 32];
-  __shared__ unsigned carry;
-  radix_scan_row(hist, n_tiles, digit_totals, blockIdx.x, ws, &carry);
-}
-
-__global__ void __launch_bounds__(RS_THREADS)
-radix_scatter_kernel(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int m, int shift,
-                     const unsigned* __restrict__ hist, int n_tiles, const unsigned* __restrict__ digit_totals,
-                     unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
-  __shared__ RadixScatterSmem sm;
-  radix_scatter_tile(keys_in, vals_in, m, shift, hist, n_tiles, digit_totals, keys_out, vals_out, blockIdx.x, sm);
-}
-
-// ---- the whole LSD sort in ONE cooperative launch: persistent CTAs loop over tiles, grid-wide barriers separate the
-// histogram / digit-scan / scatter phases of each pass.  Twelve dependent launches per sort become one, which is what
-// the launch-bound mapping stage needs (the host thread, not the GPU, was the bottleneck: profiles/r1_v3_*.md).
-__global__ void __launch_bounds__(RS_THREADS)
-radix_sort_coop_kernel(unsigned* ka, int* va, unsigned* kb, int* vb, int m, int passes, unsigned* __restrict__ hist,
-                       int n_tiles, unsigned* __restrict__ digit_totals) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ RadixScatterSmem sm;
-  __shared__ unsigned h[256];
-  __shared__ unsigned carry;
-  for (int p = 0; p < passes; p++) {
-    const int shift = p * 8;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) radix_hist_tile(ka, m, shift, hist, n_tiles, tile, h);
-    grid.sync();
-    if (n_tiles <= 32) {
-      const int warps_per_grid = gridDim.x * (RS_THREADS / 32);
-      for (int d = blockIdx.x * (RS_THREADS / 32) + (threadIdx.x >> 5); d < 256; d += warps_per_grid)
-        radix_scan_row_warp(hist, n_tiles, digit_totals, d);
-    } else {
-      for (int d = blockIdx.x; d < 256; d += gridDim.x) radix_scan_row(hist, n_tiles, digit_totals, d, sm.dsum, &carry);
-    }
-    grid.sync();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      radix_scatter_tile(ka, va, m, shift, hist, n_tiles, digit_totals, kb, vb, tile, sm);
-    grid.sync();
-    unsigned* tk = ka; ka = kb; kb = tk;
-    int* tv = va; va = vb; vb = tv;
   }
 }
 

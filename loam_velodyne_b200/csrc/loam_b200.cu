@@ -39,40 +39,41 @@ TreeView view_of(const Tree& t) {
 namespace loamb {
 // radix sort (keys, vals) of length m in ctx->sort (input in keys_a / vals_a); 8 bits per pass.  The sorted arrays are
 // returned through keys_out / vals_out (buffer a after an even number of passes, b after an odd one).
-int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out, int** vals_out) {
+template <int ITEMS>
+static int radix_sort_launch(loam_b200_ctx* c, int m, int passes, const int* n_dev, unsigned*& ka, int*& va, unsigned*& kb,
+                             int*& vb) {
   SortScratch& s = c->sort;
-  const int n_tiles = blocks_for(m, RS_TILE);
-  LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles + 256));
-  unsigned* digit_totals = s.hist.p + (size_t)256 * n_tiles;
+  const int n_tiles = blocks_for(m, RS_THREADS * ITEMS);
+  LB_CUDA(c, s.hist.reserve((size_t)RS_HEADER + (size_t)passes * n_tiles * 256));
+  unsigned* header = s.hist.p;
+  unsigned* status = s.hist.p + RS_HEADER;
+  LB_CUDA(c, cudaMemsetAsync(header, 0, RS_HEADER * sizeof(unsigned), c->stream));
+  onesweep_hist_kernel<ITEMS><<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, n_dev, passes, header, status, n_tiles);
+  LB_LAUNCH_CHECK(c);
+  for (int p = 0; p < passes; p++) {
+    onesweep_pass_kernel<ITEMS><<<n_tiles, RS_THREADS, 0, c->stream>>>(
+        ka, va, m, n_dev, 8 * p, header + p * 256, status + (size_t)p * n_tiles * 256, header + RS_MAX_PASSES * 256 + p,
+        kb, vb);
+    LB_LAUNCH_CHECK(c);
+    std::swap(ka, kb);
+    std::swap(va, vb);
+  }
+  return LOAM_B200_OK;
+}
+
+// LSD radix sort of (keys_a, vals_a) in c->sort, m = launch bound, live count = min(m, *n_dev) when n_dev is given
+// (elements past it are left alone).  Sorted arrays are returned through the out params; callers that read buffer a
+// directly get an even number of passes.
+int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out, int** vals_out, const int* n_dev) {
+  SortScratch& s = c->sort;
   unsigned *ka = s.keys_a.p, *kb = s.keys_b.p;
   int *va = s.vals_a.p, *vb = s.vals_b.p;
-  int passes = (key_bits + 7) / 8;
-  if (!keys_out && (passes & 1)) passes++;  // callers that read buffer a directly need an even count
-  if (c->coop_blocks > 0) {
-    // one cooperative launch for all passes
-    int grid = std::min(std::max(n_tiles, 1), c->coop_blocks);
-    int m_arg = m, passes_arg = passes, n_tiles_arg = n_tiles;
-    unsigned* hist_p = s.hist.p;
-    void* args[] = {&ka, &va, &kb, &vb, &m_arg, &passes_arg, &hist_p, &n_tiles_arg, &digit_totals};
-    LB_CUDA(c, cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(grid), dim3(RS_THREADS), args, 0,
-                                           c->stream));
-    LB_LAUNCH_CHECK(c);
-    if (passes & 1) {
-      unsigned* tk = ka; ka = kb; kb = tk;
-      int* tv = va; va = vb; vb = tv;
-    }
-  } else {
-    for (int p = 0; p < passes; p++) {
-      const int shift = p * 8;
-      radix_hist_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, m, shift, s.hist.p, n_tiles);
-      LB_LAUNCH_CHECK(c);
-      radix_scan_digits_kernel<<<256, RS_THREADS, 0, c->stream>>>(s.hist.p, n_tiles, digit_totals);
-      LB_LAUNCH_CHECK(c);
-      radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, c->stream>>>(ka, va, m, shift, s.hist.p, n_tiles, digit_totals, kb, vb);
-      LB_LAUNCH_CHECK(c);
-      unsigned* tk = ka; ka = kb; kb = tk;
-      int* tv = va; va = vb; vb = tv;
-    }
+  int passes = std::min((key_bits + 7) / 8, RS_MAX_PASSES);
+  if (!keys_out && (passes & 1)) passes++;
+  if (m > 0) {
+    const int rc = rs_items_for(m) == 4 ? radix_sort_launch<4>(c, m, passes, n_dev, ka, va, kb, vb)
+                                        : radix_sort_launch<16>(c, m, passes, n_dev, ka, va, kb, vb);
+    if (rc) return rc;
   }
   if (keys_out) *keys_out = ka;
   if (vals_out) *vals_out = va;
@@ -124,7 +125,7 @@ int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m, con
   LB_LAUNCH_CHECK(c);
   unsigned* keys = nullptr;
   int* vals = nullptr;
-  int rc = radix_sort_pairs(c, m, 32, &keys, &vals);  // keys < 1290^3 < 2^31; padding keys are 0xffffffff
+  int rc = radix_sort_pairs(c, m, 32, &keys, &vals, n_dev);  // keys < 1290^3 < 2^31: the top pass is usually a copy
   if (rc) return rc;
   gather_sorted_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, vals, m, g.sorted.p, n_dev);
   LB_LAUNCH_CHECK(c);
@@ -331,15 +332,6 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
     cudaGetLastError();
     delete c;
     return LOAM_B200_ERR_CUDA;
-  }
-  {
-    // co-resident CTAs for the cooperative radix sort (0 disables it: LOAM_B200_NO_COOP=1 or no device support)
-    int per_sm = 0, coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-    if (coop && !getenv("LOAM_B200_NO_COOP") &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_coop_kernel, RS_THREADS, 0) == cudaSuccess)
-      c->coop_blocks = per_sm * prop.multiProcessorCount;
-    cudaGetLastError();
   }
   cudaFuncSetAttribute(feature_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||

@@ -9,7 +9,8 @@
 namespace loamb {
 
 // defined in loam_b200.cu: LSD radix sort of (keys_a, vals_a) in c->sort; sorted arrays returned through the out params
-int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr);
+int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr,
+                     const int* n_dev = nullptr);
 
 __global__ void voxel_key_kernel(const float4* __restrict__ p, int n, float inv, int minb0, int minb1, int minb2,
                                  int div0, int div1, unsigned* __restrict__ keys, int* __restrict__ vals) {
@@ -125,12 +126,10 @@ inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float l
     return LOAM_B200_OK;
   }
   SortScratch& s = c->sort;
-  const int n_tiles = (n + RS_TILE - 1) / RS_TILE;
   LB_CUDA(c, s.keys_a.reserve(n));
   LB_CUDA(c, s.keys_b.reserve(n));
   LB_CUDA(c, s.vals_a.reserve(n));
   LB_CUDA(c, s.vals_b.reserve(n));
-  LB_CUDA(c, s.hist.reserve((size_t)256 * n_tiles + 256));
   LB_CUDA(c, c->bbox.reserve(16));
   unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
   VoxMeta* meta = reinterpret_cast<VoxMeta*>(c->bbox.p + 8);
