@@ -24,7 +24,7 @@ struct DevBuf {
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     size_t want = cap ? cap : 256;
-    while (want < n) want = want + want / 2 + 256;
+    while (want < n) want = 2 * want + 256;  // a reallocation synchronises the device: keep them rare (180 GB of HBM)
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -36,7 +36,7 @@ struct DevBuf {
   cudaError_t reserve_keep(size_t n, size_t keep, cudaStream_t st) {
     if (n <= cap) return cudaSuccess;
     size_t want = cap ? cap : 256;
-    while (want < n) want = want + want / 2 + 256;
+    while (want < n) want = 2 * want + 256;
     T* q = nullptr;
     cudaError_t e = cudaMalloc((void**)&q, want * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -127,6 +127,7 @@ struct SortScratch {
 struct loam_b200_ctx {
   int device = 0;
   int sm_count = 0;
+  bool cluster_ok = false;  // single-launch cluster kernels of clustersort.cuh usable (LOAM_B200_NO_CLUSTER=1 disables)
   cudaStream_t stream = nullptr;
   std::string last_error;
   long long launches = 0;

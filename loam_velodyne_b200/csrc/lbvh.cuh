@@ -71,19 +71,21 @@ __device__ __forceinline__ unsigned expand10(unsigned v) {
   return v;
 }
 
+__device__ __forceinline__ unsigned morton_key(const float4& q, float lx, float ly, float lz, float hx, float hy, float hz) {
+  const float ex = hx - lx, ey = hy - ly, ez = hz - lz;
+  const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
+  const float sc = 1023.0f / ext;  // cubic cells
+  const unsigned ix = (unsigned)fminf(fmaxf((q.x - lx) * sc, 0.f), 1023.f);
+  const unsigned iy = (unsigned)fminf(fmaxf((q.y - ly) * sc, 0.f), 1023.f);
+  const unsigned iz = (unsigned)fminf(fmaxf((q.z - lz) * sc, 0.f), 1023.f);
+  return (expand10(ix) << 2) | (expand10(iy) << 1) | expand10(iz);
+}
+
 __global__ void morton_kernel(const float4* __restrict__ p, int m, const unsigned* __restrict__ bb,
                               unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const float lx = dec_f(bb[0]), ly = dec_f(bb[1]), lz = dec_f(bb[2]);
-  const float ex = dec_f(bb[3]) - lx, ey = dec_f(bb[4]) - ly, ez = dec_f(bb[5]) - lz;
-  const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
-  const float sc = 1023.0f / ext;  // cubic cells
-  const float4 q = p[i];
-  const unsigned ix = (unsigned)fminf(fmaxf((q.x - lx) * sc, 0.f), 1023.f);
-  const unsigned iy = (unsigned)fminf(fmaxf((q.y - ly) * sc, 0.f), 1023.f);
-  const unsigned iz = (unsigned)fminf(fmaxf((q.z - lz) * sc, 0.f), 1023.f);
-  keys[i] = (expand10(ix) << 2) | (expand10(iy) << 1) | expand10(iz);
+  keys[i] = morton_key(p[i], dec_f(bb[0]), dec_f(bb[1]), dec_f(bb[2]), dec_f(bb[3]), dec_f(bb[4]), dec_f(bb[5]));
   vals[i] = i;
 }
 
@@ -311,37 +313,44 @@ __global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* 
   sorted[i] = p;
 }
 
-__global__ void leaf_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ keys, int m, int n_leaf,
-                            unsigned* __restrict__ leaf_key, float4* __restrict__ box_lo, float4* __restrict__ box_hi,
-                            int* __restrict__ flags) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_leaf) return;
+// The three tree phases as per-element bodies: the stand-alone kernels below run one element per thread, the fused
+// cluster build (clustersort.cuh) strides over them between cluster barriers.  Data produced by another CTA earlier in
+// the same launch is read with ld.global.cg (L1 is not coherent across SMs).
+__device__ __forceinline__ void leaf_body(int l, const float4* __restrict__ sorted, int m, int n_leaf,
+                                          float4* __restrict__ box_lo, float4* __restrict__ box_hi,
+                                          int* __restrict__ flags) {
   const int b = l * LEAF_SIZE, e = min(b + LEAF_SIZE, m);
   float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
   for (int i = b; i < e; i++) {
-    const float4 p = sorted[i];
+    const float4 p = __ldcg(&sorted[i]);
     lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
     hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
   }
-  leaf_key[l] = keys[b];
   // leaves live after the n_leaf-1 internal nodes in the box arrays
   box_lo[n_leaf - 1 + l] = make_float4(lo.x, lo.y, lo.z, 0.f);
   box_hi[n_leaf - 1 + l] = make_float4(hi.x, hi.y, hi.z, 0.f);
   if (l < n_leaf - 1) flags[l] = 0;
 }
 
+__global__ void leaf_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ keys, int m, int n_leaf,
+                            unsigned* __restrict__ leaf_key, float4* __restrict__ box_lo, float4* __restrict__ box_hi,
+                            int* __restrict__ flags) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaf) return;
+  leaf_key[l] = keys[l * LEAF_SIZE];
+  leaf_body(l, sorted, m, n_leaf, box_lo, box_hi, flags);
+}
+
 // ---------------------------------------------------------------- Karras (2012) topology over leaf keys
 __device__ __forceinline__ int delta_fn(const unsigned* __restrict__ k, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
-  const unsigned a = k[i], b = k[j];
+  const unsigned a = __ldcg(&k[i]), b = __ldcg(&k[j]);
   if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);
   return __clz(a ^ b);
 }
 
-__global__ void karras_kernel(const unsigned* __restrict__ leaf_key, int n_leaf, BvhNode* __restrict__ nodes,
-                              int* __restrict__ parent) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_leaf - 1) return;
+__device__ __forceinline__ void karras_body(int i, const unsigned* __restrict__ leaf_key, int n_leaf,
+                                            BvhNode* __restrict__ nodes, int* __restrict__ parent) {
   const int d = (delta_fn(leaf_key, n_leaf, i, i + 1) - delta_fn(leaf_key, n_leaf, i, i - 1)) >= 0 ? 1 : -1;
   const int dmin = delta_fn(leaf_key, n_leaf, i, i - d);
   int lmax = 2;
@@ -368,18 +377,24 @@ __global__ void karras_kernel(const unsigned* __restrict__ leaf_key, int n_leaf,
   if (i == 0) parent[0] = -1;
 }
 
+__global__ void karras_kernel(const unsigned* __restrict__ leaf_key, int n_leaf, BvhNode* __restrict__ nodes,
+                              int* __restrict__ parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_leaf - 1) return;
+  karras_body(i, leaf_key, n_leaf, nodes, parent);
+}
+
 // bottom-up refit: one thread per leaf climbs; the second arrival at a node merges the children
-__global__ void refit_kernel(int n_leaf, BvhNode* __restrict__ nodes, const int* __restrict__ parent,
-                             float4* __restrict__ box_lo, float4* __restrict__ box_hi, int* __restrict__ flags) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_leaf) return;
+__device__ __forceinline__ void refit_body(int l, int n_leaf, BvhNode* __restrict__ nodes, const int* __restrict__ parent,
+                                           float4* __restrict__ box_lo, float4* __restrict__ box_hi,
+                                           int* __restrict__ flags) {
   int cur = n_leaf - 1 + l;
-  int p = parent[cur];
+  int p = __ldcg(&parent[cur]);
   while (p >= 0) {
     __threadfence();
     if (atomicAdd(&flags[p], 1) == 0) return;  // first arrival: sibling not ready yet
     __threadfence();
-    const int c0 = __float_as_int(nodes[p].lo0.w), c1 = __float_as_int(nodes[p].hi0.w);
+    const int c0 = __float_as_int(__ldcg(&nodes[p].lo0.w)), c1 = __float_as_int(__ldcg(&nodes[p].hi0.w));
     const int b0 = (c0 < 0) ? (n_leaf - 1 + ~c0) : c0, b1 = (c1 < 0) ? (n_leaf - 1 + ~c1) : c1;
     const float4 l0 = __ldcg(&box_lo[b0]), h0 = __ldcg(&box_hi[b0]);
     const float4 l1 = __ldcg(&box_lo[b1]), h1 = __ldcg(&box_hi[b1]);
@@ -390,8 +405,15 @@ __global__ void refit_kernel(int n_leaf, BvhNode* __restrict__ nodes, const int*
     __stcg(&box_lo[p], make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f));
     __stcg(&box_hi[p], make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f));
     cur = p;
-    p = parent[cur];
+    p = __ldcg(&parent[cur]);
   }
+}
+
+__global__ void refit_kernel(int n_leaf, BvhNode* __restrict__ nodes, const int* __restrict__ parent,
+                             float4* __restrict__ box_lo, float4* __restrict__ box_hi, int* __restrict__ flags) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaf) return;
+  refit_body(l, n_leaf, nodes, parent, box_lo, box_hi, flags);
 }
 
 // ---------------------------------------------------------------- k-NN walk (one query per thread)

@@ -10,6 +10,7 @@
 #include "odometry_lm.cuh"
 #include "voxel.cuh"
 #include "mappool.cuh"
+#include "clustersort.cuh"
 
 using namespace loamb;
 
@@ -77,6 +78,22 @@ int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out,
   }
   if (keys_out) *keys_out = ka;
   if (vals_out) *vals_out = va;
+  return LOAM_B200_OK;
+}
+
+bool cluster_path_ok(const loam_b200_ctx* c, int n) { return c->cluster_ok && n > 0 && n <= CS_MAX_N; }
+
+int voxel_filter_cluster(loam_b200_ctx* c, const float4* d_in, int n, float leaf, const void* roundtrip, float4* d_tmp,
+                         float4* d_out, int* d_count) {
+  const float inv = 1.0f / leaf;
+  if (roundtrip) {
+    voxel_filter_cluster_kernel<true><<<CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(
+        d_in, n, inv, *static_cast<const MapIterArgs*>(roundtrip), d_tmp, d_out, d_count);
+  } else {
+    voxel_filter_cluster_kernel<false><<<CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(
+        d_in, n, inv, MapIterArgs{}, nullptr, d_out, d_count);
+  }
+  LB_LAUNCH_CHECK(c);
   return LOAM_B200_OK;
 }
 
@@ -155,6 +172,13 @@ int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
   LB_CUDA(c, t.flags.reserve(n_leaf));
   LB_CUDA(c, t.box_lo.reserve(2 * (size_t)n_leaf));
   LB_CUDA(c, t.box_hi.reserve(2 * (size_t)n_leaf));
+  if (cluster_path_ok(c, m)) {
+    bvh_build_cluster_kernel<<<CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(
+        t.points(), m, n_leaf, t.sorted.p, t.leaf_key.p, t.nodes.p, t.parent.p, t.box_lo.p, t.box_hi.p, t.flags.p);
+    LB_LAUNCH_CHECK(c);
+    t.root = n_leaf == 1 ? ~0 : 0;
+    return LOAM_B200_OK;
+  }
   unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
@@ -334,6 +358,14 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
     return LOAM_B200_ERR_CUDA;
   }
   cudaFuncSetAttribute(feature_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  c->cluster_ok = !getenv("LOAM_B200_NO_CLUSTER") &&
+                  cudaFuncSetAttribute(voxel_filter_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSortSmem)) == cudaSuccess &&
+                  cudaFuncSetAttribute(voxel_filter_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSortSmem)) == cudaSuccess &&
+                  cudaFuncSetAttribute(bvh_build_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSortSmem)) == cudaSuccess;
+  cudaGetLastError();
   if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||
       c->ticket.reserve(4) != cudaSuccess || c->result_host.reserve(NEQ) != cudaSuccess) {
     cudaGetLastError();

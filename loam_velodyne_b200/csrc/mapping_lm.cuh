@@ -35,6 +35,23 @@ __device__ __forceinline__ void associate_to_map(const MapIterArgs& a, const flo
   z = z3 + a.tz;
 }
 
+// stack points: pointAssociateToMap with the predicted pose then pointAssociateTobeMapped back into the sensor frame
+// (BasicLaserMapping.cpp:282-292 and :512-516; the round trip is not an identity in fp32 and is reproduced).
+// Negated angles flip the sine only (Angle.h:47-53).
+__device__ __forceinline__ float4 stack_roundtrip(const MapIterArgs& a, const float4& q) {
+  float x, y, z;
+  associate_to_map(a, q, x, y, z);
+  // pointAssociateTobeMapped: subtract t, rotateYXZ(-ry, -rx, -rz)
+  x -= a.tx; y -= a.ty; z -= a.tz;
+  const float x1 = a.cry * x + (-a.sry) * z;
+  const float z1 = a.cry * z - (-a.sry) * x;
+  const float y2 = a.crx * y - (-a.srx) * z1;
+  const float z2 = (-a.srx) * y + a.crx * z1;
+  const float x3 = a.crz * x1 - (-a.srz) * y2;
+  const float y3 = (-a.srz) * x1 + a.crz * y2;
+  return make_float4(x3, y3, z2, q.w);
+}
+
 // closed-form point-to-line residual shared by mapping (:712-730) and odometry (BasicLaserOdometry.cpp:319-337)
 __device__ __forceinline__ void line_residual(float x0, float y0, float z0, float x1, float y1, float z1, float x2,
                                               float y2, float z2, float& la, float& lb, float& lc, float& ld2) {

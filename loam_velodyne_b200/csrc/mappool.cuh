@@ -128,18 +128,7 @@ struct ToSensorArgs {
 __global__ void stack_roundtrip_kernel(const float4* __restrict__ in, int n, MapIterArgs a, float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 q = in[i];
-  float x, y, z;
-  associate_to_map(a, q, x, y, z);
-  // pointAssociateTobeMapped: subtract t, rotateYXZ(-ry, -rx, -rz)
-  x -= a.tx; y -= a.ty; z -= a.tz;
-  const float x1 = a.cry * x + (-a.sry) * z;
-  const float z1 = a.cry * z - (-a.sry) * x;
-  const float y2 = a.crx * y - (-a.srx) * z1;
-  const float z2 = (-a.srx) * y + a.crx * z1;
-  const float x3 = a.crz * x1 - (-a.srz) * y2;
-  const float y3 = (-a.srz) * x1 + a.crz * y2;
-  out[i] = make_float4(x3, y3, z2, q.w);
+  out[i] = stack_roundtrip(a, in[i]);
 }
 
 // new map points: pointAssociateToMap(stackDS) with the optimised pose (:536-577)

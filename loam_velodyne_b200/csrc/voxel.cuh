@@ -79,10 +79,7 @@ struct VoxMeta {
 
 // bbox -> voxel grid origin / extents on the device (pcl::VoxelGrid::applyFilter's min_b_ / div_b_ and its int32
 // overflow guard "Leaf size is too small for the input dataset")
-__global__ void voxel_meta_kernel(const unsigned* __restrict__ bb, float inv, VoxMeta* __restrict__ meta) {
-  if (threadIdx.x != 0) return;
-  float mn[3], mx[3];
-  for (int a = 0; a < 3; a++) { mn[a] = dec_f(bb[a]); mx[a] = dec_f(bb[3 + a]); }
+__device__ __forceinline__ VoxMeta voxel_meta_from_bbox(const float* mn, const float* mx, float inv) {
   const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
                   dz = (long long)((mx[2] - mn[2]) * inv) + 1;
   VoxMeta m;
@@ -92,26 +89,33 @@ __global__ void voxel_meta_kernel(const unsigned* __restrict__ bb, float inv, Vo
   m.minb2 = (int)floorf(mn[2] * inv);
   m.div0 = (int)floorf(mx[0] * inv) - m.minb0 + 1;
   m.div1 = (int)floorf(mx[1] * inv) - m.minb1 + 1;
-  *meta = m;
+  return m;
 }
 
-// keys from the device-side meta; on overflow every point keeps its own key (= its index), which makes the filter an
-// identity exactly like pcl's early return
+// on overflow every point keeps its own key (= its index), which makes the filter an identity exactly like pcl's
+// early return
+__device__ __forceinline__ unsigned voxel_key_of(const float4& q, float inv, const VoxMeta& m, int i) {
+  if (m.overflow) return (unsigned)i;
+  const int i0 = (int)(floorf(q.x * inv) - (float)m.minb0);
+  const int i1 = (int)(floorf(q.y * inv) - (float)m.minb1);
+  const int i2 = (int)(floorf(q.z * inv) - (float)m.minb2);
+  return (unsigned)(i0 + i1 * m.div0 + i2 * m.div0 * m.div1);
+}
+
+__global__ void voxel_meta_kernel(const unsigned* __restrict__ bb, float inv, VoxMeta* __restrict__ meta) {
+  if (threadIdx.x != 0) return;
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; a++) { mn[a] = dec_f(bb[a]); mx[a] = dec_f(bb[3 + a]); }
+  *meta = voxel_meta_from_bbox(mn, mx, inv);
+}
+
 __global__ void voxel_key_meta_kernel(const float4* __restrict__ p, int n, float inv, const VoxMeta* __restrict__ meta,
                                       unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const VoxMeta m = *meta;
   vals[i] = i;
-  if (m.overflow) {
-    keys[i] = (unsigned)i;
-    return;
-  }
-  const float4 q = p[i];
-  const int i0 = (int)(floorf(q.x * inv) - (float)m.minb0);
-  const int i1 = (int)(floorf(q.y * inv) - (float)m.minb1);
-  const int i2 = (int)(floorf(q.z * inv) - (float)m.minb2);
-  keys[i] = (unsigned)(i0 + i1 * m.div0 + i2 * m.div0 * m.div1);
+  keys[i] = voxel_key_of(p[i], inv, m, i);
 }
 
 __global__ void copy_u32_kernel(const unsigned* __restrict__ src, int* __restrict__ dst) {
@@ -120,11 +124,18 @@ __global__ void copy_u32_kernel(const unsigned* __restrict__ src, int* __restric
 
 // Stream-ordered voxel filter without host round trips: d_in (n points, n known on the host) -> d_out (capacity n);
 // the number of occupied voxels is written to *d_count (device memory).
+// defined in loam_b200.cu: the single-launch cluster filter of clustersort.cuh (n <= CS_MAX_N); roundtrip = optional
+// MapIterArgs* of the to-map-and-back transform applied to the input first (d_tmp then receives the transformed cloud)
+int voxel_filter_cluster(loam_b200_ctx* c, const float4* d_in, int n, float leaf, const void* roundtrip, float4* d_tmp,
+                         float4* d_out, int* d_count);
+bool cluster_path_ok(const loam_b200_ctx* c, int n);
+
 inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* d_count) {
   if (n <= 0) {
     LB_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
     return LOAM_B200_OK;
   }
+  if (cluster_path_ok(c, n)) return voxel_filter_cluster(c, d_in, n, leaf, nullptr, nullptr, d_out, d_count);
   SortScratch& s = c->sort;
   LB_CUDA(c, s.keys_a.reserve(n));
   LB_CUDA(c, s.keys_b.reserve(n));
