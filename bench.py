@@ -224,6 +224,10 @@ def kernel_roofline(args, api, corner, surf, sweep, pipe):
     """North-star kernel (fused 5-NN + fit + Jacobian + reduction = map_iterate_kernel) timed with CUDA events on its
     own stream through the kernel ABI, on the same queries / map the pipeline uses."""
     ctx = api.Ctx(int(os.environ.get("LOCAL_RANK", "0")))
+    # one more sweep with the from-map clouds retained (the persistent map does not materialise them otherwise)
+    pipe.mapping.retain_from_map(True)
+    pipe.sweep(*sweep)
+    pipe.mapping.retain_from_map(False)
     cq = pipe.mapping.cloud("corner_stack_ds")
     sq = pipe.mapping.cloud("surf_stack_ds")
     cm = pipe.mapping.cloud("corner_from_map")

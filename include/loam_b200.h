@@ -232,6 +232,10 @@ int loam_b200_map_begin_sweep(loam_b200_ctx* ctx, const loam_b200_pose* predicte
 int loam_b200_map_end_sweep(loam_b200_ctx* ctx, const loam_b200_pose* optimised);
 /* createDownsizedMap (:242-264): VoxelGrid(leaf) over the corner + surface points of the surround cubes -> MAP_SURROUND_DS */
 int loam_b200_map_surround(loam_b200_ctx* ctx, const int cen[3], const int32_t* surround_cubes, int n, float leaf);
+/* Debug / test switch: loam_b200_map_begin_sweep additionally materialises the reference's laserCloud*FromMap
+ * (BasicLaserMapping.cpp:503-509: the map points of the cubes in view) in the *_FROM_MAP cloud slots.  Off by default:
+ * the persistent cell-sorted map never needs that copy, only its size (sizes_out[0..1]). */
+int loam_b200_map_debug_from_map(loam_b200_ctx* ctx, int on);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  With a shard set, loam_b200_map_iterate evaluates this rank's contiguous slice

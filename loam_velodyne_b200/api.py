@@ -124,6 +124,7 @@ def lib():
         "loam_b200_map_begin_sweep": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(MapWindow), _I]),
         "loam_b200_map_end_sweep": (C.c_int, [vp, C.POINTER(Pose)]),
         "loam_b200_map_surround": (C.c_int, [vp, _I, _I, C.c_int, C.c_float]),
+        "loam_b200_map_debug_from_map": (C.c_int, [vp, C.c_int]),
         "loam_b200_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
         "loam_b200_comm_destroy": (C.c_int, [vp]),
@@ -164,6 +165,7 @@ def lib():
         "loam_b200_map_cloud_copy": (C.c_int, [vp, C.c_int, _F]),
         "loam_b200_map_last_iterations": (C.c_int, [vp]),
         "loam_b200_map_last_phase_seconds": (C.c_int, [vp, _D]),
+        "loam_b200_map_retain_from_map": (C.c_int, [vp, C.c_int]),
         "loam_b200_host_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
         "loam_b200_pipeline_create": (vp, [C.c_float, C.c_int, C.c_int]),
@@ -486,6 +488,10 @@ class LaserMapping(_Handle):
         if getattr(self, "own", False) and self.h:
             self.L.loam_b200_map_destroy(self.h)
             self.h = None
+
+    def retain_from_map(self, on=True):
+        """Test hook: keep the reference's internal from-map clouds ("corner_from_map" / "surf_from_map") every sweep."""
+        self._ck(self.L.loam_b200_map_retain_from_map(self.h, 1 if on else 0), "retainFromMapClouds")
 
     def seed(self, corner, surf):
         c, s = _pts(corner), _pts(surf)

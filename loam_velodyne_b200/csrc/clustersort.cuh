@@ -269,6 +269,32 @@ voxel_filter_cluster_kernel(const float4* __restrict__ in, int n, float inv, Map
   cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
 }
 
+// generic (key, value) sort of a small array, in place allowed (everything is loaded before anything is stored)
+__global__ void __cluster_dims__(CS_CL, 1, 1) __launch_bounds__(CS_THREADS)
+cluster_sort_pairs_kernel(const unsigned* keys_in, const int* vals_in, int n, const int* __restrict__ n_dev, int passes,
+                          unsigned* keys_out, int* vals_out) {
+  extern __shared__ __align__(16) unsigned char cs_raw[];
+  ClusterSortSmem& sm = *reinterpret_cast<ClusterSortSmem*>(cs_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  if (n_dev) n = min(n, *n_dev);
+  if (n <= 0) return;  // uniform over the cluster
+  const unsigned my = cluster.block_rank();
+  const int per = (n + CS_CL - 1) / CS_CL;
+  const int m_local = cs_local_count(n, per, my);
+  const int g0 = (int)my * per;
+  for (int i = threadIdx.x; i < m_local; i += CS_THREADS) {
+    sm.keys[0][i] = keys_in[g0 + i];
+    sm.vals[0][i] = vals_in[g0 + i];
+  }
+  __syncthreads();
+  const int cur = cluster_sort(sm, n, per, passes);
+  for (int i = threadIdx.x; i < m_local; i += CS_THREADS) {
+    keys_out[g0 + i] = sm.keys[cur][i];
+    vals_out[g0 + i] = sm.vals[cur][i];
+  }
+  cluster.sync();
+}
+
 // LBVH build of lbvh.cuh in one launch: bbox -> Morton keys -> cluster sort -> gather -> leaves -> Karras -> refit
 __global__ void __cluster_dims__(CS_CL, 1, 1) __launch_bounds__(CS_THREADS)
 bvh_build_cluster_kernel(const float4* __restrict__ pts, int n, int n_leaf, float4* __restrict__ sorted,

@@ -190,6 +190,28 @@ struct loam_b200_ctx {
   // map pools: class per point, cube tables, scratch
   loamb::DevBuf<unsigned char> pool_cls[2];
   loamb::DevBuf<unsigned char> rank_of_cube;
+  // persistent cell-sorted map (mapstore.cuh): cloud[POOL_SLOT[k]] holds the points, these the parallel arrays;
+  // the *_alt buffers receive the merged pool of a sweep and are swapped in
+  struct MapStore {
+    loamb::DevBuf<uint32_t> keys, keys_alt;
+    loamb::DevBuf<unsigned char> state, state_alt;
+    loamb::DevBuf<float4> pts_alt;
+    loamb::DevBuf<uint4> table;
+    unsigned mask = 0;
+    loamb::DevBuf<int> cube_stats;   // [3][CUBE_NUM]: start, end, raw count per cube slot
+    loamb::DevBuf<unsigned char> valid_by_slot;
+    loamb::DevBuf<float4> s_pts, e_pts;            // this sweep's filter input / emitted points
+    loamb::DevBuf<unsigned char> e_state;
+    loamb::DevBuf<uint32_t> e_keys;                // cell keys of the emitted points (before sorting)
+    loamb::DevBuf<int> e_vals;
+    bool dirty = false;        // points were appended unsorted: rebuild before the next sweep
+    bool check_grid = false;   // the next merge must drop points whose cube is outside the grid
+    int n_raw_valid = 0;       // raw points in the cubes in view (exact, from begin_sweep's readback)
+    int n_slot = 0;            // which of the two device-side pool counters is current
+    int last_cen[3] = {1 << 30, 0, 0};
+  } store[2];
+  bool map_use_store = false;      // scan-to-map search goes through the store (stage API) / through grid[] (kernel API)
+  bool map_debug_from_map = false; // begin_sweep also materialises the from-map clouds (tests)
   loamb::DevBuf<float4> pool_tmp;
   loamb::DevBuf<unsigned char> pool_tmp_cls;
   loamb::DevBuf<unsigned> cmp_pos, cmp_bsum;
@@ -200,6 +222,8 @@ struct loam_b200_ctx {
   int map_n_valid = 0;
   float map_leaf[2] = {0.2f, 0.4f};
   cudaEvent_t ev_xfer = nullptr;
+  cudaEvent_t ev_table = nullptr;
+  bool ev_table_pending = false;
 
   // extra lanes: independent pieces of a stage (corner / surface kind, stack filter / map grid) run concurrently on
   // their own stream with their own scratch; LaneScope swaps a lane's stream + scratch into the fields above

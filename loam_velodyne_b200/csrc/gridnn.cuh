@@ -141,19 +141,50 @@ __device__ __forceinline__ void cand5_offer(Cand5& r, float d, int id) {
 
 constexpr int GRID_SLOTS = 32;  // flattened cell slots per query: slot = lane * 4 + r (27 used)
 
+// Cell lookup over the bounding-box grid of grid_build_device (kernel-level API: loam_b200_tree_build on a map slot).
+struct GridCellLookup {
+  GridView g;
+  GridMeta gm;
+  int cx, cy, cz;
+  // returns false when no neighbour of the query can hold a point
+  __device__ __forceinline__ bool prepare(float qx, float qy, float qz) {
+    gm = *g.meta;
+    cx = (int)floorf(qx) - gm.ox; cy = (int)floorf(qy) - gm.oy; cz = (int)floorf(qz) - gm.oz;
+    return g.m > 0 && !(cx < -1 || cy < -1 || cz < -1 || cx > gm.nx || cy > gm.ny || cz > gm.nz);
+  }
+  // neighbour cell t = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1) -> run of its points in `sorted`
+  template <bool STATS>
+  __device__ __forceinline__ void cell(int t, unsigned& start, unsigned& count, unsigned* stats) const {
+    const int z = cz + t / 9 - 1, y = cy + (t / 3) % 3 - 1, x = cx + t % 3 - 1;
+    if (z >= 0 && z < gm.nz && y >= 0 && y < gm.ny && x >= 0 && x < gm.nx) {
+      const unsigned key = grid_key(gm, x, y, z);
+      unsigned h = grid_hash(key) & g.mask;
+      uint4 e = __ldg(&g.table[h]);
+      if (STATS) stats[0]++;
+      while (e.x != 0u && e.x != key + 1u) {
+        h = (h + 1) & g.mask;
+        e = __ldg(&g.table[h]);
+        if (STATS) stats[0]++;
+      }
+      if (e.x == key + 1u) { start = e.y; count = e.z; }
+    }
+  }
+  __device__ __forceinline__ const float4* points() const { return g.sorted; }
+};
+
 // All 8 lanes of the group call this with the same query; on return every lane holds the group's exact 5 nearest
 // (d2 < 1.0) in `out` (ascending; id = -1 for missing ones).  gmask = the group's 8 lanes within the warp;
-// pre[GRID_SLOTS + 1] / first[GRID_SLOTS] = this group's rows of shared memory.
-template <bool STATS>
-__device__ __forceinline__ void grid_knn5_group8(const GridView& g, float qx, float qy, float qz, int sub,
+// pre[GRID_SLOTS + 1] / first[GRID_SLOTS] = this group's rows of shared memory.  LOOKUP maps a neighbour cell to its
+// run of points (GridCellLookup above, MapCellLookup in mapstore.cuh).
+template <bool STATS, typename LOOKUP>
+__device__ __forceinline__ void grid_knn5_group8(LOOKUP& lk, float qx, float qy, float qz, int sub,
                                                  unsigned gmask, unsigned* pre, unsigned* first, Cand5& out,
                                                  unsigned* stats) {
   Cand5 mine;
 #pragma unroll
   for (int i = 0; i < 5; i++) { mine.d[i] = 1.0f; mine.id[i] = -1; }
-  const GridMeta gm = *g.meta;
-  const int cx = (int)floorf(qx) - gm.ox, cy = (int)floorf(qy) - gm.oy, cz = (int)floorf(qz) - gm.oz;
-  const bool inside = g.m > 0 && !(cx < -1 || cy < -1 || cz < -1 || cx > gm.nx || cy > gm.ny || cz > gm.nz);
+  const bool inside = lk.prepare(qx, qy, qz);
+  const float4* __restrict__ sorted = lk.points();
   if (inside) {  // uniform over the group
     unsigned start[4], count[4];
 #pragma unroll
@@ -161,21 +192,7 @@ __device__ __forceinline__ void grid_knn5_group8(const GridView& g, float qx, fl
       const int t = sub + 8 * r;
       start[r] = 0;
       count[r] = 0;
-      if (t < 27) {
-        const int z = cz + t / 9 - 1, y = cy + (t / 3) % 3 - 1, x = cx + t % 3 - 1;
-        if (z >= 0 && z < gm.nz && y >= 0 && y < gm.ny && x >= 0 && x < gm.nx) {
-          const unsigned key = grid_key(gm, x, y, z);
-          unsigned h = grid_hash(key) & g.mask;
-          uint4 e = __ldg(&g.table[h]);
-          if (STATS) stats[0]++;
-          while (e.x != 0u && e.x != key + 1u) {
-            h = (h + 1) & g.mask;
-            e = __ldg(&g.table[h]);
-            if (STATS) stats[0]++;
-          }
-          if (e.x == key + 1u) { start[r] = e.y; count[r] = e.z; }
-        }
-      }
+      if (t < 27) lk.template cell<STATS>(t, start[r], count[r], stats);
     }
     // exclusive prefix of the counts in slot order
     const unsigned local = count[0] + count[1] + count[2] + count[3];
@@ -201,14 +218,14 @@ __device__ __forceinline__ void grid_knn5_group8(const GridView& g, float qx, fl
     for (unsigned j = sub; j < total; j += 16) {
       while (j >= hi) { f++; lo = hi; hi = pre[f + 1]; }
       const int i0 = (int)(first[f] + (j - lo));
-      const float4 p0 = __ldg(g.sorted + i0);
+      const float4 p0 = __ldg(sorted + i0);
       const unsigned j1 = j + 8;
       int i1 = -1;
       float4 p1 = p0;
       if (j1 < total) {
         while (j1 >= hi) { f++; lo = hi; hi = pre[f + 1]; }
         i1 = (int)(first[f] + (j1 - lo));
-        p1 = __ldg(g.sorted + i1);
+        p1 = __ldg(sorted + i1);
       }
       {
         const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;

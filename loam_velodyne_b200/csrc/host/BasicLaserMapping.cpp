@@ -58,6 +58,11 @@ void BasicLaserMapping::enableSharding(int rank, int world, const unsigned char*
     _gpu->check(loam_b200_map_set_shard(_gpu->get(), rank, world), "loam_b200_map_set_shard");
 }
 
+void BasicLaserMapping::retainFromMapClouds(bool on) {
+  _retainFromMap = on;
+  _gpu->check(loam_b200_map_debug_from_map(_gpu->get(), on ? 1 : 0), "loam_b200_map_debug_from_map");
+}
+
 void BasicLaserMapping::adopt(BasicLaserOdometry& odom) {
   static const int to[3] = {M_CORNER_LAST, M_SURF_LAST, M_FULL};
   for (int i = 0; i < 3; i++) {
@@ -264,8 +269,10 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   loam_b200_pose predicted;
   b200::fillPose(_transformTobeMapped, predicted);
   _gpu->check(loam_b200_map_begin_sweep(_gpu->get(), &predicted, &win, _mapSizes), "loam_b200_map_begin_sweep");
-  _c[M_CORNER_FROM_MAP].deviceWritten(_mapSizes[0]);
-  _c[M_SURF_FROM_MAP].deviceWritten(_mapSizes[1]);
+  // the persistent GPU map only reports how many points the cubes in view hold; the clouds themselves are
+  // materialised on request (retainFromMapClouds)
+  _c[M_CORNER_FROM_MAP].deviceWritten(_retainFromMap ? _mapSizes[0] : 0);
+  _c[M_SURF_FROM_MAP].deviceWritten(_retainFromMap ? _mapSizes[1] : 0);
   _c[M_CORNER_STACK_DS].deviceWritten(_mapSizes[2]);
   _c[M_SURF_STACK_DS].deviceWritten(_mapSizes[3]);
 

@@ -200,6 +200,9 @@ int loam_b200_map_get_twist(void* h, int which, float* out6) {
 int loam_b200_map_cloud_size(void* h, int which) { return (int)((MapH*)h)->cloud(which).size(); }
 int loam_b200_map_cloud_copy(void* h, int which, float* out) { dump(((MapH*)h)->cloud(which), out); return 0; }
 int loam_b200_map_last_iterations(void* h) { return (int)((MapH*)h)->m.lastIterationCount(); }
+int loam_b200_map_retain_from_map(void* h, int on) {
+  return guarded([&] { ((MapH*)h)->m.retainFromMapClouds(on != 0); return 0; });
+}
 int loam_b200_map_last_phase_seconds(void* h, double* out4) {
   const double* p = ((MapH*)h)->m.lastPhaseSeconds();
   for (int i = 0; i < 4; i++) out4[i] = p[i];

@@ -91,6 +91,10 @@ class BasicLaserMapping {
   // all-reduces the 6x6 normal equations over NCCL every iteration (ncclId: 128 bytes from
   // loam_b200_comm_unique_id on rank 0; nullptr = slice only, the caller reduces)
   void enableSharding(int rank, int world, const unsigned char* ncclId);
+  /** Test hook (not in the reference): keep a copy of the points of the cubes in view (upstream's internal
+   *  _laserCloudCornerFromMap / _laserCloudSurfFromMap) after every process(); off by default, the persistent GPU map
+   *  only needs their sizes. */
+  void retainFromMapClouds(bool on);
 
  private:
   typedef pcl::PointCloud<pcl::PointXYZI> Cloud;
@@ -123,6 +127,7 @@ class BasicLaserMapping {
 
   pcl::VoxelGrid<pcl::PointXYZI> _downSizeFilterCorner, _downSizeFilterSurf, _downSizeFilterMap;
   bool _downsizedMapCreated = false;
+  bool _retainFromMap = false;
 
   b200::Context* _gpu;
   b200::GaussNewtonSolver* _solver;

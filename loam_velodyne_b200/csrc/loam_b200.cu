@@ -11,6 +11,7 @@
 #include "voxel.cuh"
 #include "mappool.cuh"
 #include "clustersort.cuh"
+#include "mapstore.cuh"
 
 using namespace loamb;
 
@@ -71,7 +72,11 @@ int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out,
   int *va = s.vals_a.p, *vb = s.vals_b.p;
   int passes = std::min((key_bits + 7) / 8, RS_MAX_PASSES);
   if (!keys_out && (passes & 1)) passes++;
-  if (m > 0) {
+  if (cluster_path_ok(c, m)) {
+    // small array: the whole sort is one cluster launch (clustersort.cuh), sorted in place
+    cluster_sort_pairs_kernel<<<CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(ka, va, m, n_dev, passes, ka, va);
+    LB_LAUNCH_CHECK(c);
+  } else if (m > 0) {
     const int rc = rs_items_for(m) == 4 ? radix_sort_launch<4>(c, m, passes, n_dev, ka, va, kb, vb)
                                         : radix_sort_launch<16>(c, m, passes, n_dev, ka, va, kb, vb);
     if (rc) return rc;
@@ -109,6 +114,15 @@ GridView grid_view_of(const Grid& g) {
   v.meta = reinterpret_cast<const GridMeta*>(g.meta.p);
   v.m = g.m;
   return v;
+}
+
+MapCellLookup store_lookup_of(const loam_b200_ctx* c, int kind) {
+  const auto& st = c->store[kind];
+  MapCellLookup lk;
+  lk.g = MapGridView{st.table.p, st.mask, c->cloud[kind == 0 ? LOAM_B200_C_MAP_CORNER_POOL : LOAM_B200_C_MAP_SURF_POOL].p,
+                     c->rank_of_cube.p, c->map_grid.cen_w, c->map_grid.cen_h, c->map_grid.cen_d, c->map_n_valid};
+  lk.ax = lk.ay = lk.az = CellAxis{0, 0, 0};
+  return lk;
 }
 
 // 1 m uniform grid over d_pts: the search structure of the scan-to-map loop (gridnn.cuh).  m is the launch bound; when
@@ -343,7 +357,8 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_xfer, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_xfer, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
     delete c;
     return LOAM_B200_ERR_CUDA;
@@ -364,6 +379,8 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
                   cudaFuncSetAttribute(voxel_filter_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ClusterSortSmem)) == cudaSuccess &&
                   cudaFuncSetAttribute(bvh_build_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSortSmem)) == cudaSuccess &&
+                  cudaFuncSetAttribute(cluster_sort_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ClusterSortSmem)) == cudaSuccess;
   cudaGetLastError();
   if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||
@@ -406,6 +423,12 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_xfer) cudaEventDestroy(c->ev_xfer);
+  if (c->ev_table) cudaEventDestroy(c->ev_table);
+  for (auto& st : c->store) {
+    st.keys.release(); st.keys_alt.release(); st.state.release(); st.state_alt.release(); st.pts_alt.release();
+    st.table.release(); st.cube_stats.release(); st.valid_by_slot.release(); st.s_pts.release(); st.e_pts.release();
+    st.e_state.release(); st.e_keys.release(); st.e_vals.release();
+  }
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
@@ -561,8 +584,10 @@ int loam_b200_tree_build(loam_b200_ctx* c, int slot, const float* pts, int m) {
   prof_begin(c, LOAM_B200_K_TREE_BUILD);
   rc = tree_build_device(c, t, m);
   // the scan-to-map kernels search the two map slots through the 1 m grid
-  if (rc == LOAM_B200_OK && slot >= LOAM_B200_TREE_MAP_CORNER)
+  if (rc == LOAM_B200_OK && slot >= LOAM_B200_TREE_MAP_CORNER) {
     rc = grid_build_device(c, c->grid[slot - LOAM_B200_TREE_MAP_CORNER], t.points(), m);
+    c->map_use_store = false;  // kernel-level API: the scan-to-map search uses this grid, not the persistent store
+  }
   prof_end(c);
   if (rc) return rc;
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -648,18 +673,28 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   if (walk_totals_host) {
     LB_CUDA(c, c->walk_totals.reserve(2));
     LB_CUDA(c, cudaMemsetAsync(c->walk_totals.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    map_iterate_kernel<true><<<nb, MAP_THREADS, 0, c->stream>>>(
-        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, c0, lc, s0, ls, cb,
-        a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
+    if (c->map_use_store)
+      map_iterate_kernel<true><<<nb, MAP_THREADS, 0, c->stream>>>(
+          store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
+          c->ticket.p, nullptr, nullptr, c->walk_totals.p);
+    else
+      map_iterate_kernel<true><<<nb, MAP_THREADS, 0, c->stream>>>(
+          GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
+          cb, a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
     LB_LAUNCH_CHECK(c);
     LB_CUDA(c, cudaMemcpyAsync(walk_totals_host, c->walk_totals.p, 2 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, c->stream));
   } else {
     prof_begin(c, LOAM_B200_K_MAP_ITER);
-    map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
-        grid_view_of(c->grid[0]), grid_view_of(c->grid[1]), c->map_q.p, nc, c0, lc, s0, ls, cb,
-        a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
-        nullptr);
+    if (c->map_use_store)
+      map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
+          store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
+          c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr);
+    else
+      map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
+          GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
+          cb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
+          nullptr);
     LB_LAUNCH_CHECK(c);
     prof_end(c);
   }

@@ -200,9 +200,9 @@ static_assert(MAP_Q_PER_BLOCK == 32, "the fit phase maps one query to one lane o
 //            partial written straight from registers; the last CTA folds all partials in fixed order.
 // 64 registers / thread -> 4 CTAs per SM, so the ~550 CTAs of an HDL-64 sweep are a single wave on 148 SMs (at 72
 // registers the 8-lane kernel ran 1.06 waves: half of the kernel's time was a second wave of 63 CTAs).
-template <bool STATS>
+template <bool STATS, typename LOOKUP>
 __global__ void __launch_bounds__(MAP_THREADS, 4)
-map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __restrict__ queries, int n_corner_total,
+map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restrict__ queries, int n_corner_total,
                    int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
@@ -219,7 +219,7 @@ map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __res
   const int n_kind = is_corner ? n_corner : n_surf;
   // this rank's slice: corners [c0, c0 + n_corner), surfaces [s0, s0 + n_surf) (the whole range on one GPU)
   const int q_base = is_corner ? c0 : n_corner_total + s0;
-  const GridView& grid = is_corner ? corner_grid : surf_grid;
+  LOOKUP grid = is_corner ? corner_grid : surf_grid;  // cell -> run of map points (gridnn.cuh / mapstore.cuh)
 
   {  // ---- search: 8 lanes per query
     const int g = threadIdx.x / MAP_GROUP;
@@ -239,7 +239,7 @@ map_iterate_kernel(GridView corner_grid, GridView surf_grid, const float4* __res
         const int id = sub == 0 ? best.id[0] : sub == 1 ? best.id[1] : sub == 2 ? best.id[2] : sub == 3 ? best.id[3]
                                                                                                        : best.id[4];
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (id >= 0) p = __ldg(&grid.sorted[id]);
+        if (id >= 0) p = __ldg(&grid.points()[id]);
         p.w = __int_as_float(id);
         s_nn[g][sub] = p;
       }

@@ -42,9 +42,14 @@ __device__ __forceinline__ int cube_index(const float4& p, const CubeGrid& g, in
 
 // rank_of_cube: CUBE_NUM bytes, rank in the valid list or CLS_KEEP
 __global__ void classify_kernel(const float4* __restrict__ p, int n, CubeGrid g,
-                                const unsigned char* __restrict__ rank_of_cube, unsigned char* __restrict__ cls) {
+                                const unsigned char* __restrict__ rank_of_cube, unsigned char* __restrict__ cls,
+                                const int* __restrict__ n_dev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_dev && i >= *n_dev) {  // launch bound above the live count: never selected
+    cls[i] = CLS_DROP;
+    return;
+  }
   int ci, cj, ck;
   const int c = cube_index(p[i], g, ci, cj, ck);
   cls[i] = c < 0 ? CLS_DROP : rank_of_cube[c];

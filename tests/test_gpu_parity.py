@@ -286,6 +286,7 @@ def test_map_grid_roll_and_drop(checker):
     lidar = synth.Lidar(16, 600, -15.0, 15.0)
     corner, surf = synth.make_map(sc, 150_000, window=150.0)
     pg, pc = api.Pipeline(), checker.pipeline()
+    pg.mapping.retain_from_map(True)
     pg.seed_map(corner, surf)
     pc.seed_map(corner, surf)
     # 30 m/s for 45 sweeps = 135 m: crosses two cube boundaries (the grid keeps the sensor >= 3 cubes from its faces)
