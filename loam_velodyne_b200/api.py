@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libloam_b200.so")
+# LOAM_B200_LIB: development aid (A/B builds of the same ABI); the product library sits next to this file
+LIB_PATH = os.environ.get("LOAM_B200_LIB") or os.path.join(HERE, "libloam_b200.so")
 
 _F = C.POINTER(C.c_float)
 _I = C.POINTER(C.c_int)

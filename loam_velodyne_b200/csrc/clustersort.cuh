@@ -1,4 +1,4 @@
-// Small-cloud building blocks that live entirely inside ONE thread-block cluster (8 CTAs, distributed shared memory).
+// Small-cloud building blocks that live entirely inside ONE thread-block cluster (16 CTAs, distributed shared memory).
 //
 // The feature stacks of a sweep (5 k corner / 20 k surface points) and the odometry's last-sweep clouds are far too
 // small to fill a B200, and as chains of 12-14 tiny launches (bbox, keys, histogram, four radix passes, heads, scan,
@@ -24,8 +24,14 @@ namespace loamb {
 
 namespace cg = cooperative_groups;
 
-constexpr int CS_CL = 8;                  // CTAs per cluster (portable maximum)
-constexpr int CS_THREADS = 512;
+#ifndef LOAM_B200_CS_CL
+#define LOAM_B200_CS_CL 16                // CTAs per cluster (8 = portable maximum; 16 = non-portable opt-in, measured 25-40 % faster at 60 k points)
+#endif
+#ifndef LOAM_B200_CS_THREADS
+#define LOAM_B200_CS_THREADS 512
+#endif
+constexpr int CS_CL = LOAM_B200_CS_CL;
+constexpr int CS_THREADS = LOAM_B200_CS_THREADS;
 constexpr int CS_NW = CS_THREADS / 32;
 constexpr int CS_CAP = 8192;              // pairs per CTA
 constexpr int CS_MAX_N = CS_CL * CS_CAP;  // 65536
@@ -202,28 +208,15 @@ voxel_filter_cluster_kernel(const float4* __restrict__ in, int n, float inv, Map
   __syncthreads();
   const int cur = cluster_sort(sm, n, per, 4);
 
-  // run heads: count per CTA, exchange, then scan + centroids
+  // run heads: position of every head inside this CTA (block scan in rounds, no global traffic) -> exchange the CTA
+  // totals -> centroids.  The positions live in the sort's spare value buffer.
   auto key_at = [&](int g) -> unsigned {
     const int r = g / per;
     return cluster.map_shared_rank(&sm.keys[cur][0], r)[g - r * per];
   };
-  int n_heads = 0;
-  for (int base = 0; base < m_local; base += CS_THREADS) {
-    const int i = base + threadIdx.x;
-    const bool head = i < m_local && (g0 + i == 0 || sm.keys[cur][i] != (i > 0 ? sm.keys[cur][i - 1] : key_at(g0 - 1)));
-    n_heads += __syncthreads_count(head);
-  }
-  if (threadIdx.x == 0) sm.scal[0] = (unsigned)n_heads;
-  cluster.sync();
-  unsigned cta_base = 0, total = 0;
-  for (unsigned r = 0; r < CS_CL; r++) {
-    const unsigned h = cluster.map_shared_rank(&sm.scal[0], r)[0];
-    if (r < my) cta_base += h;
-    total += h;
-  }
-  if (my == 0 && threadIdx.x == 0) *count_out = (int)total;
+  int* head_pos = &sm.vals[cur ^ 1][0];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned carry = cta_base;
+  unsigned carry = 0;
   for (int base = 0; base < m_local; base += CS_THREADS) {
     const int i = base + threadIdx.x;
     const bool head = i < m_local && (g0 + i == 0 || sm.keys[cur][i] != (i > 0 ? sm.keys[cur][i - 1] : key_at(g0 - 1)));
@@ -236,35 +229,48 @@ voxel_filter_cluster_kernel(const float4* __restrict__ in, int n, float inv, Map
       if (w < warp) woff += c;
       round_total += c;
     }
-    if (head) {
-      const unsigned dst = carry + woff + __popc(bal & ((1u << lane) - 1u));
-      const unsigned k = sm.keys[cur][i];
-      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      int cnt = 0;
-      // walk the run (it may continue in the next CTAs' shared memory)
-      unsigned r = my;
-      int off = i;
-      const unsigned* kp = &sm.keys[cur][0];
-      const int* vp = &sm.vals[cur][0];
-      for (int g = g0 + i; g < n; g++) {
-        if (kp[off] != k) break;
-        const float4 q = __ldcg(&pts[vp[off]]);
-        sx += q.x; sy += q.y; sz += q.z; si += q.w;
-        cnt++;
-        if (++off == per) {
-          off = 0;
-          r++;
-          if (r < CS_CL) {
-            kp = cluster.map_shared_rank(&sm.keys[cur][0], r);
-            vp = cluster.map_shared_rank(&sm.vals[cur][0], r);
-          }
-        }
-      }
-      const float fn = (float)cnt;
-      out[dst] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
-    }
+    if (i < m_local) head_pos[i] = head ? (int)(carry + woff + __popc(bal & ((1u << lane) - 1u))) : -1;
     carry += round_total;
     __syncthreads();
+  }
+  if (threadIdx.x == 0) sm.scal[0] = carry;
+  cluster.sync();
+  unsigned cta_base = 0, total = 0;
+  for (unsigned r = 0; r < CS_CL; r++) {
+    const unsigned h = cluster.map_shared_rank(&sm.scal[0], r)[0];
+    if (r < my) cta_base += h;
+    total += h;
+  }
+  if (my == 0 && threadIdx.x == 0) *count_out = (int)total;
+  // centroids: every thread walks the runs that start at its elements, no barrier in between (the walk is a chain of
+  // dependent loads; with a barrier per round the slowest run of each round set the pace)
+  for (int i = threadIdx.x; i < m_local; i += CS_THREADS) {
+    const int hp = head_pos[i];
+    if (hp < 0) continue;
+    const unsigned k = sm.keys[cur][i];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    // the run may continue in the next CTAs' shared memory
+    unsigned r = my;
+    int off = i;
+    const unsigned* kp = &sm.keys[cur][0];
+    const int* vp = &sm.vals[cur][0];
+    for (int g = g0 + i; g < n; g++) {
+      if (kp[off] != k) break;
+      const float4 q = __ldcg(&pts[vp[off]]);
+      sx += q.x; sy += q.y; sz += q.z; si += q.w;
+      cnt++;
+      if (++off == per) {
+        off = 0;
+        r++;
+        if (r < CS_CL) {
+          kp = cluster.map_shared_rank(&sm.keys[cur][0], r);
+          vp = cluster.map_shared_rank(&sm.vals[cur][0], r);
+        }
+      }
+    }
+    const float fn = (float)cnt;
+    out[cta_base + (unsigned)hp] = make_float4(sx / fn, sy / fn, sz / fn, si / fn);
   }
   cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
 }

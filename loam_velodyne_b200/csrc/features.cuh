@@ -50,17 +50,17 @@ __device__ __forceinline__ void mark_as_picked_warp(const float4* P, int8_t* pic
   __syncwarp();
 }
 
-// shared-memory bitonic sort of 64-bit keys (n2 = power of two)
+// shared-memory bitonic sort of 64-bit keys (n2 = power of two); one thread per compare-exchange PAIR
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int n2) {
+  const int half = n2 >> 1;
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < n2; t += blockDim.x) {
-        const int ixj = t ^ j;
-        if (ixj > t) {
-          const unsigned long long x = a[t], y = a[ixj];
-          const bool up = ((t & k) == 0);
-          if ((x > y) == up) { a[t] = y; a[ixj] = x; }
-        }
+      for (int p = threadIdx.x; p < half; p += blockDim.x) {
+        const int t = ((p & ~(j - 1)) << 1) | (p & (j - 1));  // lower element of pair p at distance j
+        const int ixj = t | j;
+        const unsigned long long x = a[t], y = a[ixj];
+        const bool up = ((t & k) == 0);
+        if ((x > y) == up) { a[t] = y; a[ixj] = x; }
       }
       __syncthreads();
     }
@@ -151,7 +151,14 @@ feature_ring_kernel(const float4* __restrict__ pts, const int* __restrict__ ring
 
   // ---- region bounds (:180-183), all in unsigned 64-bit like the reference's size_t
   const int nreg = prm.nFeatureRegions;
-  // ---- stable ascending rank of each point inside its region (:311-317 is a stable insertion sort)
+  // ---- stable ascending order of the points of every region (:311-317 is a stable insertion sort): ONE bitonic sort
+  // of (region, curvature bits, index) keys over the whole ring -- curvatures are sums of squares (>= +0), so their bit
+  // patterns order like the floats; the index breaks ties the way a stable sort does.  (The first version ranked every
+  // point against its whole region, O(n^2): 55 % of the kernel's instructions, profiles/r1_v6_feature_ring.md.)
+  int n2r = 1;
+  while (n2r < n) n2r <<= 1;
+  for (int t = tid; t < n2r; t += blockDim.x) vkeys[t] = ~0ull;
+  __syncthreads();
   for (int j = 0; j < nreg; j++) {
     const unsigned long long a = (unsigned long long)(s + cr), b = (unsigned long long)(e - cr);
     const unsigned long long sp = (a * (unsigned long long)(nreg - j) + b * (unsigned long long)j) / (unsigned long long)nreg;
@@ -159,21 +166,18 @@ feature_ring_kernel(const float4* __restrict__ pts, const int* __restrict__ ring
     if (ep <= sp) continue;
     const int lsp = (int)(sp - (unsigned long long)s), lep = (int)(ep - (unsigned long long)s);
     for (int i = lsp + tid; i <= lep; i += blockDim.x) {
-      const float ci = curv[i];
-      int rank = 0;
-      for (int k = lsp; k <= lep; k++) {
-        const float ck = curv[k];
-        rank += (ck < ci) || (ck == ci && k < i);
-      }
-      order[lsp + rank] = i;
+      vkeys[i] = ((unsigned long long)j << 52) | ((unsigned long long)__float_as_uint(curv[i]) << 20) | (unsigned long long)i;
       label[i] = 0;  // SURFACE_LESS_FLAT (:290)
     }
   }
   __syncthreads();
+  bitonic_sort_u64(vkeys, n2r);
+  // sorted position p of the ring <-> point index vkeys[p] & 0xfffff; region j's points follow those of regions < j
 
   // ---- greedy picks, sequential over regions, executed by warp 0 (:197-235)
   if (warp == 0) {
     int n_sharp = 0, n_less = 0, n_flat = 0;
+    int roff = 0;  // sorted position of the current region's first point
     const float thr = prm.surfaceCurvatureThreshold;
     for (int j = 0; j < nreg; j++) {
       const unsigned long long a = (unsigned long long)(s + cr), b = (unsigned long long)(e - cr);
@@ -187,7 +191,7 @@ feature_ring_kernel(const float4* __restrict__ pts, const int* __restrict__ ring
       int largest = 0;
       for (int k = nr; k > 0 && largest < prm.maxCornerLessSharp; k -= 32) {
         const int pos = k - 1 - lane;
-        const int idx = pos >= 0 ? order[lsp + pos] : -1;
+        const int idx = pos >= 0 ? (int)(vkeys[roff + pos] & 0xfffffull) : -1;
         const bool above = idx >= 0 && curv[idx] > thr;
         const unsigned m_above = __ballot_sync(0xffffffffu, above);
         if (m_above == 0u) break;
@@ -220,7 +224,7 @@ feature_ring_kernel(const float4* __restrict__ pts, const int* __restrict__ ring
       int smallest = 0;
       for (int k = 0; k < nr && smallest < prm.maxSurfaceFlat; k += 32) {
         const int pos = k + lane;
-        const int idx = pos < nr ? order[lsp + pos] : -1;
+        const int idx = pos < nr ? (int)(vkeys[roff + pos] & 0xfffffull) : -1;
         const bool below = idx >= 0 && curv[idx] < thr;
         const unsigned m_below = __ballot_sync(0xffffffffu, below);
         if (m_below == 0u) break;
@@ -242,6 +246,7 @@ feature_ring_kernel(const float4* __restrict__ pts, const int* __restrict__ ring
         }
         if (m_below != 0xffffffffu) break;
       }
+      roff += nr;
     }
     if (lane == 0) {
       counts[ring * 4 + 0] = n_sharp;

@@ -373,6 +373,12 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
     return LOAM_B200_ERR_CUDA;
   }
   cudaFuncSetAttribute(feature_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (CS_CL > 8) {  // non-portable cluster size: opt in per kernel
+    cudaFuncSetAttribute(voxel_filter_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(voxel_filter_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(bvh_build_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(cluster_sort_pairs_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  }
   c->cluster_ok = !getenv("LOAM_B200_NO_CLUSTER") &&
                   cudaFuncSetAttribute(voxel_filter_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ClusterSortSmem)) == cudaSuccess &&

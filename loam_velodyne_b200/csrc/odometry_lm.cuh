@@ -126,56 +126,75 @@ odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
     const int scan = (int)last[i1].w;
     ScanBest b2{25.f, 0x7fffffff, -1}, b3{25.f, 0x7fffffff, -1};
     int ord = 0;
+    // Both scans visit 32 x SCAN_UNROLL candidates per step: the loads of a step are independent (issued together),
+    // the ring `break` is then resolved chunk by chunk in visiting order, so the result is that of the serial loop.
+    // (One chunk per step made the kernel a chain of ~60 dependent global loads per direction on the surface cloud:
+    // 70 us at 14 % of the warp slots, profiles/r1_v6_odom_search.md.)
+    constexpr int SCAN_UNROLL = 4;
     // forward: j = i1 + 1 .. fend - 1 while ring <= scan + 2.5
     const int fend = min(is_corner ? n_sharp : n_flat, n_last);
-    for (int j0 = i1 + 1; j0 < fend; j0 += 32) {
-      const int j = j0 + lane;
-      bool brk = false;
-      float d = 0.f;
-      int r = 0;
-      if (j < fend) {
-        const float4 p = last[j];
-        r = (int)p.w;
-        brk = (double)r > (double)scan + 2.5;
-        d = sqdiff3(p, sx, sy, sz);
+    for (int j0 = i1 + 1; j0 < fend; j0 += 32 * SCAN_UNROLL) {
+      float4 p[SCAN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SCAN_UNROLL; u++) {
+        const int j = j0 + u * 32 + lane;
+        p[u] = j < fend ? last[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const unsigned bm = __ballot_sync(0xffffffffu, brk);
-      const int stop = bm ? __ffs(bm) - 1 : 32;
-      if (j < fend && lane < stop) {
-        if (is_corner) {
-          if (r > scan) scan_best_min(b2, d, ord + lane, j);
-        } else {
-          if (r <= scan) scan_best_min(b2, d, ord + lane, j);
-          else scan_best_min(b3, d, ord + lane, j);
+      bool stop_all = false;
+#pragma unroll
+      for (int u = 0; u < SCAN_UNROLL; u++) {
+        if (stop_all) continue;
+        const int j = j0 + u * 32 + lane;
+        const bool in = j < fend;
+        const int r = (int)p[u].w;
+        const bool brk = in && (double)r > (double)scan + 2.5;
+        const float d = sqdiff3(p[u], sx, sy, sz);
+        const unsigned bm = __ballot_sync(0xffffffffu, brk);
+        const int stop = bm ? __ffs(bm) - 1 : 32;
+        if (in && lane < stop) {
+          if (is_corner) {
+            if (r > scan) scan_best_min(b2, d, ord + u * 32 + lane, j);
+          } else {
+            if (r <= scan) scan_best_min(b2, d, ord + u * 32 + lane, j);
+            else scan_best_min(b3, d, ord + u * 32 + lane, j);
+          }
         }
+        if (bm) stop_all = true;
       }
-      ord += 32;
-      if (bm) break;
+      ord += 32 * SCAN_UNROLL;
+      if (stop_all) break;
     }
     // backward: j = i1 - 1 .. 0 while ring >= scan - 2.5
-    for (int j0 = i1 - 1; j0 >= 0; j0 -= 32) {
-      const int j = j0 - lane;
-      bool brk = false;
-      float d = 0.f;
-      int r = 0;
-      if (j >= 0) {
-        const float4 p = last[j];
-        r = (int)p.w;
-        brk = (double)r < (double)scan - 2.5;
-        d = sqdiff3(p, sx, sy, sz);
+    for (int j0 = i1 - 1; j0 >= 0; j0 -= 32 * SCAN_UNROLL) {
+      float4 p[SCAN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SCAN_UNROLL; u++) {
+        const int j = j0 - u * 32 - lane;
+        p[u] = j >= 0 ? last[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const unsigned bm = __ballot_sync(0xffffffffu, brk);
-      const int stop = bm ? __ffs(bm) - 1 : 32;
-      if (j >= 0 && lane < stop) {
-        if (is_corner) {
-          if (r < scan) scan_best_min(b2, d, ord + lane, j);
-        } else {
-          if (r >= scan) scan_best_min(b2, d, ord + lane, j);
-          else scan_best_min(b3, d, ord + lane, j);
+      bool stop_all = false;
+#pragma unroll
+      for (int u = 0; u < SCAN_UNROLL; u++) {
+        if (stop_all) continue;
+        const int j = j0 - u * 32 - lane;
+        const bool in = j >= 0;
+        const int r = (int)p[u].w;
+        const bool brk = in && (double)r < (double)scan - 2.5;
+        const float d = sqdiff3(p[u], sx, sy, sz);
+        const unsigned bm = __ballot_sync(0xffffffffu, brk);
+        const int stop = bm ? __ffs(bm) - 1 : 32;
+        if (in && lane < stop) {
+          if (is_corner) {
+            if (r < scan) scan_best_min(b2, d, ord + u * 32 + lane, j);
+          } else {
+            if (r >= scan) scan_best_min(b2, d, ord + u * 32 + lane, j);
+            else scan_best_min(b3, d, ord + u * 32 + lane, j);
+          }
         }
+        if (bm) stop_all = true;
       }
-      ord += 32;
-      if (bm) break;
+      ord += 32 * SCAN_UNROLL;
+      if (stop_all) break;
     }
     scan_best_warp(b2);
     i2 = b2.idx;
