@@ -158,6 +158,27 @@ int loam_b200_odom_iterate(loam_b200_ctx* ctx, const loam_b200_odom_pose* pose, 
 int loam_b200_odom_iterate_debug(loam_b200_ctx* ctx, const loam_b200_odom_pose* pose, loam_b200_normal_eq* out,
                                  float* coeff, int8_t* selected, int32_t* ind);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Whole Gauss-Newton loops with the pose kept on the device: replace the iteration LOOPS of
+ * BasicLaserOdometry::process (BasicLaserOdometry.cpp:246-622: correspondences every 5th iteration, normal equations,
+ * `continue` below 10 selected points, colPivHouseholderQr solve, degeneracy projection of the first iteration, pose
+ * update, non-finite reset, deltaR / deltaT abort) and of BasicLaserMapping::optimizeTransformTobeMapped
+ * (BasicLaserMapping.cpp:646-922, `continue` below 50, eigenvalue threshold 100).  Same arithmetic as the
+ * per-iteration entry points + a host solve, except that the sin / cos of the updated angles come from the device
+ * (double sincos rounded once instead of the host's float libm).  Queries / last clouds / map as for *_iterate.
+ * loam_b200_map_solve returns LOAM_B200_ERR_STATE when a shard or communicator is set (use loam_b200_map_iterate).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  float rot[3];     /* optimised rot_x, rot_y, rot_z */
+  float pos[3];
+  int iterations;   /* iterCount + 1 of the last executed iteration (0 when nothing ran) */
+  int converged;    /* loop ended (abort thresholds met or iteration cap reached) */
+} loam_b200_lm_result;
+int loam_b200_odom_solve(loam_b200_ctx* ctx, const float rot[3], const float pos[3], float inv_scan_period,
+                         int max_iterations, float delta_t_abort, float delta_r_abort, loam_b200_lm_result* out);
+int loam_b200_map_solve(loam_b200_ctx* ctx, const float rot[3], const float pos[3], int max_iterations,
+                        float delta_t_abort, float delta_r_abort, loam_b200_lm_result* out);
+
 /* BasicLaserOdometry::transformToEnd (BasicLaserOdometry.cpp:57-87) without IMU terms, in place on n host points */
 int loam_b200_transform_to_end(loam_b200_ctx* ctx, float* pts, int n, const loam_b200_odom_pose* pose);
 /* pointAssociateToMap over n host points in place (BasicLaserMapping.cpp:207-219, 235-240) */

@@ -56,6 +56,10 @@ class OdomPose(C.Structure):
                 ("inv_scan_period", C.c_float), ("iter", C.c_int)]
 
 
+class LmResult(C.Structure):
+    _fields_ = [("rot", C.c_float * 3), ("pos", C.c_float * 3), ("iterations", C.c_int), ("converged", C.c_int)]
+
+
 class NormalEq(C.Structure):
     _fields_ = [("AtA", C.c_float * 36), ("AtB", C.c_float * 6), ("n_selected", C.c_int),
                 ("n_corner_selected", C.c_int)]
@@ -103,6 +107,8 @@ def lib():
                                           C.POINTER(C.c_ulonglong)]),
         "loam_b200_odom_set_last": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
         "loam_b200_odom_set_current": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
+        "loam_b200_odom_solve": (C.c_int, [vp, _F, _F, C.c_float, C.c_int, C.c_float, C.c_float, C.POINTER(LmResult)]),
+        "loam_b200_map_solve": (C.c_int, [vp, _F, _F, C.c_int, C.c_float, C.c_float, C.POINTER(LmResult)]),
         "loam_b200_odom_iterate": (C.c_int, [vp, C.POINTER(OdomPose), C.POINTER(NormalEq)]),
         "loam_b200_odom_iterate_debug": (C.c_int, [vp, C.POINTER(OdomPose), C.POINTER(NormalEq), _F, _B, _I]),
         "loam_b200_transform_to_end": (C.c_int, [vp, _F, C.c_int, C.POINTER(OdomPose)]),
@@ -342,6 +348,24 @@ class Ctx:
             return _ne(ne), coeff, sel, ind
         self._ck(self.L.loam_b200_odom_iterate(self.h, C.byref(p), C.byref(ne)), "odom_iterate")
         return _ne(ne)
+
+    def odom_solve(self, twist6, scan_period=0.1, max_iter=25, delta_t=0.1, delta_r=0.1):
+        """Whole scan-to-scan Gauss-Newton loop on the device -> (twist6, iterations)."""
+        t = np.ascontiguousarray(twist6, dtype=np.float32)
+        rot, pos = t[:3].copy(), t[3:].copy()
+        res = LmResult()
+        self._ck(self.L.loam_b200_odom_solve(self.h, _fp(rot), _fp(pos), np.float32(1.0) / np.float32(scan_period), max_iter,
+                                             delta_t, delta_r, C.byref(res)), "odom_solve")
+        return np.array(list(res.rot) + list(res.pos), np.float32), res.iterations
+
+    def map_solve(self, twist6, max_iter=10, delta_t=0.05, delta_r=0.05):
+        """Whole scan-to-map Gauss-Newton loop on the device -> (twist6, iterations)."""
+        t = np.ascontiguousarray(twist6, dtype=np.float32)
+        rot, pos = t[:3].copy(), t[3:].copy()
+        res = LmResult()
+        self._ck(self.L.loam_b200_map_solve(self.h, _fp(rot), _fp(pos), max_iter, delta_t, delta_r, C.byref(res)),
+                 "map_solve")
+        return np.array(list(res.rot) + list(res.pos), np.float32), res.iterations
 
     def transform_to_end(self, pts, twist6, scan_period=0.1):
         a = _pts(pts).copy()

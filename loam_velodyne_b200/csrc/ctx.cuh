@@ -173,6 +173,7 @@ struct loam_b200_ctx {
   loamb::DevBuf<float4> dbg_coeff;
   loamb::DevBuf<int8_t> dbg_sel;
   loamb::PinBuf<float> result_host;
+  loamb::DevBuf<unsigned char> lm_state;  // OdomLmState + MapLmState (lmstep.cuh): pose of the device-resident loops
 
   // odometry
   loamb::DevBuf<float4> od_q;  // sharp then flat

@@ -52,6 +52,7 @@ pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::cornerFromMap() const 
 pcl::PointCloud<pcl::PointXYZI> const& BasicLaserMapping::surfFromMap() const { return _c[M_SURF_FROM_MAP].host(); }
 
 void BasicLaserMapping::enableSharding(int rank, int world, const unsigned char* ncclId) {
+  _sharded = world > 1 && ncclId == nullptr;  // query slices without a communicator: partial sums only (tests)
   if (ncclId)
     _gpu->check(loam_b200_comm_init(_gpu->get(), rank, world, ncclId), "loam_b200_comm_init");
   else
@@ -316,6 +317,25 @@ void BasicLaserMapping::optimizeTransformTobeMapped() {
   // and the query stacks were prepared by loam_b200_map_begin_sweep
   if (_mapSizes[0] <= 10 || _mapSizes[1] <= 100) return;
 
+  if (!_sharded && b200::deviceResidentLoops()) {
+    // optional: the whole iteration loop (:646-922) on the device (loam_b200_map_solve; with a communicator the all-reduce of the
+    // partial normal equations sits between the iteration kernel and the step kernel); the per-iteration form below
+    // remains for query slices without a communicator
+    const float rot[3] = {_transformTobeMapped.rot_x.rad(), _transformTobeMapped.rot_y.rad(), _transformTobeMapped.rot_z.rad()};
+    const float pos[3] = {_transformTobeMapped.pos.x(), _transformTobeMapped.pos.y(), _transformTobeMapped.pos.z()};
+    loam_b200_lm_result res;
+    _gpu->check(loam_b200_map_solve(_gpu->get(), rot, pos, (int)_maxIterations, _deltaTAbort, _deltaRAbort, &res),
+                "loam_b200_map_solve");
+    _lastIterations = (size_t)res.iterations;
+    _transformTobeMapped.rot_x = res.rot[0];
+    _transformTobeMapped.rot_y = res.rot[1];
+    _transformTobeMapped.rot_z = res.rot[2];
+    _transformTobeMapped.pos.x() = res.pos[0];
+    _transformTobeMapped.pos.y() = res.pos[1];
+    _transformTobeMapped.pos.z() = res.pos[2];
+    transformUpdate();
+    return;
+  }
   for (size_t iterCount = 0; iterCount < _maxIterations; iterCount++) {
     _lastIterations = iterCount + 1;
     loam_b200_pose pose;

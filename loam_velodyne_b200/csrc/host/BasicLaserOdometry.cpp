@@ -149,6 +149,22 @@ void BasicLaserOdometry::process() {
     _c[C_FLAT].ensureDevice();
     _gpu->check(loam_b200_odom_prepare(_gpu->get()), "loam_b200_odom_prepare");
 
+    if (b200::deviceResidentLoops()) {
+      // optional: the whole iteration loop (:246-622) on the device (loam_b200_odom_solve, csrc/lmstep.cuh)
+      const float rot[3] = {_transform.rot_x.rad(), _transform.rot_y.rad(), _transform.rot_z.rad()};
+      const float pos[3] = {_transform.pos.x(), _transform.pos.y(), _transform.pos.z()};
+      loam_b200_lm_result res;
+      _gpu->check(loam_b200_odom_solve(_gpu->get(), rot, pos, 1.f / _scanPeriod, (int)_maxIterations, _deltaTAbort,
+                                       _deltaRAbort, &res),
+                  "loam_b200_odom_solve");
+      _lastIterations = (size_t)res.iterations;
+      _transform.rot_x = res.rot[0];
+      _transform.rot_y = res.rot[1];
+      _transform.rot_z = res.rot[2];
+      _transform.pos.x() = res.pos[0];
+      _transform.pos.y() = res.pos[1];
+      _transform.pos.z() = res.pos[2];
+    } else
     for (size_t iterCount = 0; iterCount < _maxIterations; iterCount++) {
       _lastIterations = iterCount + 1;
       loam_b200_odom_pose pose;

@@ -1,4 +1,5 @@
 #include "b200_runtime.h"
+#include "lmstep.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -67,48 +68,20 @@ void DualCloud::swap(DualCloud& o) {
 }
 
 void GaussNewtonSolver::solve(const loam_b200_normal_eq& ne, bool firstIteration, float eigenThreshold, float x[6]) {
-  // column-major copies for the dense kernels
-  float A[36], b[6];
-  for (int i = 0; i < 6; i++) {
-    b[i] = ne.AtB[i];
-    for (int j = 0; j < 6; j++) A[i + j * 6] = ne.AtA[i * 6 + j];
-  }
-  float Aq[36];
-  std::memcpy(Aq, A, sizeof A);
-  loamb::colpiv_qr_solve<6, 6>(Aq, b, x);
+  loamb::GnState g;
+  std::memcpy(g.P, P, sizeof P);
+  g.degenerate = isDegenerate ? 1 : 0;
+  loamb::gn_solve(ne.AtA, ne.AtB, firstIteration, eigenThreshold, g, x);  // csrc/lmstep.cuh: same source as the device loop
+  std::memcpy(P, g.P, sizeof P);
+  isDegenerate = g.degenerate != 0;
+}
 
-  if (firstIteration) {
-    float E[6], V[36], V2[36];
-    loamb::sym_eigen<6>(A, E, V);  // ascending eigenvalues, V column-major (column = eigenvector)
-    std::memcpy(V2, V, sizeof V);
-    isDegenerate = false;
-    for (int i = 0; i < 6; i++) {
-      if (E[i] < eigenThreshold) {
-        for (int j = 0; j < 6; j++) V2[i + j * 6] = 0.f;  // zero ROW i
-        isDegenerate = true;
-      } else {
-        break;
-      }
-    }
-    float Vinv[36];
-    loamb::lu_inverse<6>(V, Vinv);
-    // P = V^-1 * V2, stored row-major
-    for (int i = 0; i < 6; i++)
-      for (int j = 0; j < 6; j++) {
-        float acc = 0.f;
-        for (int k = 0; k < 6; k++) acc += Vinv[i + k * 6] * V2[k + j * 6];
-        P[i * 6 + j] = acc;
-      }
-  }
-  if (isDegenerate) {
-    float x2[6];
-    for (int i = 0; i < 6; i++) x2[i] = x[i];
-    for (int i = 0; i < 6; i++) {
-      float acc = 0.f;
-      for (int k = 0; k < 6; k++) acc += P[i * 6 + k] * x2[k];
-      x[i] = acc;
-    }
-  }
+bool deviceResidentLoops() {
+  static const bool on = [] {
+    const char* e = std::getenv("LOAM_B200_DEVICE_LOOP");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 void voxelFilter(Context& ctx, const Cloud& in, float leaf, Cloud& out, std::vector<float>& sin, std::vector<float>& sout) {

@@ -119,6 +119,11 @@ struct GaussNewtonSolver {
   void solve(const loam_b200_normal_eq& ne, bool firstIteration, float eigenThreshold, float x[6]);
 };
 
+// LOAM_B200_DEVICE_LOOP=1: run the Gauss-Newton loops through loam_b200_odom_solve / loam_b200_map_solve (pose kept on
+// the device, csrc/lmstep.cuh) instead of one kernel + host solve per iteration.  Off by default: on B200 the one-warp
+// step kernel (~15 us) costs more than the 128-byte readback + host solve it replaces.
+bool deviceResidentLoops();
+
 // host-side pcl::VoxelGrid replacement: one GPU call
 void voxelFilter(Context& ctx, const Cloud& in, float leaf, Cloud& out, std::vector<float>& scratchIn,
                  std::vector<float>& scratchOut);

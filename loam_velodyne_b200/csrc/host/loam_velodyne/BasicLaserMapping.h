@@ -128,6 +128,7 @@ class BasicLaserMapping {
   pcl::VoxelGrid<pcl::PointXYZI> _downSizeFilterCorner, _downSizeFilterSurf, _downSizeFilterMap;
   bool _downsizedMapCreated = false;
   bool _retainFromMap = false;
+  bool _sharded = false;
 
   b200::Context* _gpu;
   b200::GaussNewtonSolver* _solver;

@@ -228,63 +228,10 @@ int upload_points(loam_b200_ctx* c, DevBuf<float4>& dst, const float* src, int n
   return LOAM_B200_OK;
 }
 
-void fill_map_args(const loam_b200_pose* p, MapIterArgs& a) {
-  const float srx = p->sin_[0], crx = p->cos_[0], sry = p->sin_[1], cry = p->cos_[1], srz = p->sin_[2],
-              crz = p->cos_[2];
-  a.srx = srx; a.crx = crx; a.sry = sry; a.cry = cry; a.srz = srz; a.crz = crz;
-  a.tx = p->pos[0]; a.ty = p->pos[1]; a.tz = p->pos[2];
-  // Jacobian coefficient products, formed left to right exactly like BasicLaserMapping.cpp:842-853
-  a.A[0] = crx * sry * srz;      a.A[1] = crx * crz * sry;        a.A[2] = -(srx * sry);
-  a.A[3] = -srx * srz;           a.A[4] = -(crz * srx);           a.A[5] = -crx;
-  a.A[6] = crx * cry * srz;      a.A[7] = crx * cry * crz;        a.A[8] = -(cry * srx);
-  a.B[0] = cry * srx * srz - crz * sry;
-  a.B[1] = sry * srz + cry * crz * srx;
-  a.B[2] = crx * cry;
-  a.B[3] = a.B[4] = a.B[5] = 0.f;
-  a.B[6] = -cry * crz - srx * sry * srz;
-  a.B[7] = cry * srz - crz * srx * sry;
-  a.B[8] = -(crx * sry);
-  a.C[0] = crz * srx * sry - cry * srz;
-  a.C[1] = -cry * crz - srx * sry * srz;
-  a.C[2] = 0.f;
-  a.C[3] = crx * crz;
-  a.C[4] = -(crx * srz);
-  a.C[5] = 0.f;
-  a.C[6] = sry * srz + cry * crz * srx;
-  a.C[7] = crz * sry - cry * srx * srz;
-  a.C[8] = 0.f;
-}
+void fill_map_args(const loam_b200_pose* p, MapIterArgs& a) { map_args_from(p->sin_, p->cos_, p->pos, a); }
 
 void fill_odom_args(const loam_b200_odom_pose* p, OdomIterArgs& a) {
-  const float srx = p->sin_[0], crx = p->cos_[0], sry = p->sin_[1], cry = p->cos_[1], srz = p->sin_[2],
-              crz = p->cos_[2];
-  const float tx = p->pos[0], ty = p->pos[1], tz = p->pos[2];
-  a.rx = p->rot[0]; a.ry = p->rot[1]; a.rz = p->rot[2];
-  a.tx = tx; a.ty = ty; a.tz = tz;
-  a.inv_sp = p->inv_scan_period;
-  a.iter = p->iter;
-  // BasicLaserOdometry.cpp:514-543 with s = 1 (every `s *` is an exact multiplication by one)
-  a.g1a = -crx * sry * srz;  a.g1b = crx * crz * sry;  a.g1c = srx * sry;
-  a.k1 = tx * crx * sry * srz;  a.k2 = ty * crx * crz * sry;  a.k3 = tz * srx * sry;
-  a.t1 = srx * srz;  a.t2 = crz * srx;  a.t3 = crx;
-  a.k4 = ty * crz * srx;  a.k5 = tz * crx;  a.k6 = tx * srx * srz;
-  a.u1 = crx * cry * srz;  a.u2 = crx * cry * crz;  a.u3 = cry * srx;
-  a.k7 = tz * cry * srx;  a.k8 = ty * crx * cry * crz;  a.k9 = tx * crx * cry * srz;
-  a.e1 = -crz * sry - cry * srx * srz;
-  a.e2 = cry * crz * srx - sry * srz;
-  a.e3 = crx * cry;
-  a.e4 = crz * sry + cry * srx * srz;
-  a.e5 = sry * srz - cry * crz * srx;
-  a.k10 = tz * crx * cry;
-  a.f1 = cry * crz - srx * sry * srz;
-  a.f2 = cry * srz + crz * srx * sry;
-  a.f3 = crx * sry;
-  a.k11 = tz * crx * sry;
-  a.g1 = -cry * srz - crz * srx * sry;
-  a.h1 = -crx * crz;  a.h2 = crx * srz;
-  a.k12 = ty * crx * srz;  a.k13 = tx * crx * crz;
-  a.atx_y = crx * srz;  a.aty_y = crx * crz;
-  a.atz_x = crx * sry;  a.atz_y = srx;  a.atz_z = crx * cry;
+  odom_args_from(p->rot, p->sin_, p->cos_, p->pos, p->inv_scan_period, p->iter, a);
 }
 
 // BVHs of the last clouds are rebuilt asynchronously on lanes 1 / 2 (loam_b200_odom_rebuild_last)
@@ -436,7 +383,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
     st.e_state.release(); st.e_keys.release(); st.e_vals.release();
   }
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
-  c->dbg_sel.release(); c->result_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -789,11 +736,11 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
   prof_begin(c, LOAM_B200_K_ODOM_ITER);
   if (pose->iter % 5 == 0) {
     const int warps = nsh + nfl;
-    odom_search_kernel<<<blocks_for((long long)warps * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
+    odom_search_kernel<false><<<blocks_for((long long)warps * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
         view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, a, c->od_ind.p);
     LB_LAUNCH_CHECK(c);
   }
-  odom_iterate_kernel<<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh,
+  odom_iterate_kernel<false><<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh,
                                                         nfl, cb, a, c->od_ind.p, c->partials.p, c->result.p,
                                                         c->ticket.p, dbg ? c->dbg_coeff.p : nullptr,
                                                         dbg ? c->dbg_sel.p : nullptr);
@@ -819,6 +766,122 @@ int loam_b200_odom_iterate_debug(loam_b200_ctx* c, const loam_b200_odom_pose* po
                                  float* coeff, int8_t* selected, int32_t* ind) {
   if (!coeff) return LOAM_B200_ERR_ARG;
   return odom_iterate_impl(c, pose, out, coeff, selected, ind);
+}
+
+// ------------------------------------------------------------------------------------------------ device-resident loops
+// Whole Gauss-Newton loops with the pose kept on the device (lmstep.cuh).  Iteration kernels are enqueued in chunks;
+// after a chunk the 48-byte header of the state block is read back once.  Kernels behind the converged iteration return
+// immediately.  Not available with a communicator (the all-reduce sits between kernel and solve): ERR_STATE.
+static int lm_read_header(loam_b200_ctx* c, const void* d_state, LmHeader* h) {
+  LB_CUDA(c, c->result_host.reserve(NEQ));
+  LB_CUDA(c, cudaMemcpyAsync(c->result_host.p, d_state, sizeof(LmHeader), cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(h, c->result_host.p, sizeof(LmHeader));
+  return LOAM_B200_OK;
+}
+
+int loam_b200_odom_solve(loam_b200_ctx* c, const float rot[3], const float pos[3], float inv_scan_period, int max_iterations,
+                         float delta_t_abort, float delta_r_abort, loam_b200_lm_result* out) {
+  CHECK_CTX(c);
+  if (!rot || !pos || !out || max_iterations < 0) return LOAM_B200_ERR_ARG;
+  if (!c->od_last_set) return LOAM_B200_ERR_STATE;
+  LB_CUDA(c, odom_join_rebuild(c));
+  const int nsh = c->od_nsharp, nfl = c->od_nflat;
+  memset(out, 0, sizeof *out);
+  for (int i = 0; i < 3; i++) { out->rot[i] = rot[i]; out->pos[i] = pos[i]; }
+  if (nsh + nfl == 0 || max_iterations == 0) return LOAM_B200_OK;
+  const Tree& tc = c->tree[LOAM_B200_TREE_ODOM_CORNER];
+  const Tree& ts = c->tree[LOAM_B200_TREE_ODOM_SURF];
+  const int cb = blocks_for(nsh, LM_THREADS), sb = blocks_for(nfl, LM_THREADS);
+  const int nb = cb + sb;
+  LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
+  LB_CUDA(c, c->lm_state.reserve(sizeof(OdomLmState) + sizeof(MapLmState)));
+  OdomLmState* st = reinterpret_cast<OdomLmState*>(c->lm_state.p);
+  odom_lm_init_kernel<<<1, 32, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], inv_scan_period,
+                                               delta_t_abort, delta_r_abort, max_iterations, tc.m, ts.m);
+  LB_LAUNCH_CHECK(c);
+  const OdomIterArgs unused{};
+  LmHeader h{};
+  prof_begin(c, LOAM_B200_K_ODOM_ITER);
+  for (int it = 0; it < max_iterations;) {
+    const int chunk_end = std::min(max_iterations, it + 5);  // one correspondence search per chunk
+    for (; it < chunk_end; it++) {
+      if (it % 5 == 0) {
+        odom_search_kernel<true><<<blocks_for((long long)(nsh + nfl) * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
+            view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, unused, c->od_ind.p, st);
+        LB_LAUNCH_CHECK(c);
+      }
+      odom_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p,
+                                                            nsh, nfl, cb, unused, c->od_ind.p, c->partials.p, c->result.p,
+                                                            c->ticket.p, nullptr, nullptr, st);
+      LB_LAUNCH_CHECK(c);
+      odom_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p);
+      LB_LAUNCH_CHECK(c);
+    }
+    const int rc = lm_read_header(c, st, &h);
+    if (rc) return rc;
+    if (h.done) break;
+  }
+  prof_end(c);
+  for (int i = 0; i < 3; i++) { out->rot[i] = h.rot[i]; out->pos[i] = h.pos[i]; }
+  out->iterations = h.iters_run;
+  out->converged = h.done && h.iter < max_iterations ? 1 : (h.done ? 1 : 0);
+  return LOAM_B200_OK;
+}
+
+int loam_b200_map_solve(loam_b200_ctx* c, const float rot[3], const float pos[3], int max_iterations, float delta_t_abort,
+                        float delta_r_abort, loam_b200_lm_result* out) {
+  CHECK_CTX(c);
+  if (!rot || !pos || !out || max_iterations < 0) return LOAM_B200_ERR_ARG;
+  if (c->shard_world > 1 && !c->comm) return LOAM_B200_ERR_STATE;  // a shard without a communicator only yields partials
+  const int nc = c->map_nc, ns = c->map_ns;
+  memset(out, 0, sizeof *out);
+  for (int i = 0; i < 3; i++) { out->rot[i] = rot[i]; out->pos[i] = pos[i]; }
+  if (nc + ns == 0 || max_iterations == 0) return LOAM_B200_OK;
+  // this rank's contiguous slice of each query kind (everything when not sharded)
+  const int W = c->shard_world, R = c->shard_rank;
+  const int c0 = (int)((long long)nc * R / W), c1 = (int)((long long)nc * (R + 1) / W);
+  const int s0 = (int)((long long)ns * R / W), s1 = (int)((long long)ns * (R + 1) / W);
+  const int lc = c1 - c0, ls = s1 - s0;
+  const int cb = blocks_for(lc, MAP_Q_PER_BLOCK), sb = blocks_for(ls, MAP_Q_PER_BLOCK);
+  const int nb = std::max(cb + sb, 1);
+  LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
+  LB_CUDA(c, c->lm_state.reserve(sizeof(OdomLmState) + sizeof(MapLmState)));
+  MapLmState* st = reinterpret_cast<MapLmState*>(c->lm_state.p + sizeof(OdomLmState));
+  map_lm_init_kernel<<<1, 32, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], delta_t_abort,
+                                              delta_r_abort, max_iterations);
+  LB_LAUNCH_CHECK(c);
+  const MapIterArgs unused{};
+  LmHeader h{};
+  prof_begin(c, LOAM_B200_K_MAP_ITER);
+  for (int it = 0; it < max_iterations;) {
+    const int chunk_end = std::min(max_iterations, it + 3);  // 2-3 iterations is the usual case
+    for (; it < chunk_end; it++) {
+      if (c->map_use_store)
+        map_iterate_kernel<false, MapCellLookup, true><<<nb, MAP_THREADS, 0, c->stream>>>(
+            store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, unused, c->partials.p,
+            c->result.p, c->ticket.p, nullptr, nullptr, nullptr, st);
+      else
+        map_iterate_kernel<false, GridCellLookup, true><<<nb, MAP_THREADS, 0, c->stream>>>(
+            GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
+            cb, unused, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, nullptr, st);
+      LB_LAUNCH_CHECK(c);
+      {
+        const int rcc = allreduce_result(c);  // no-op without a communicator; every rank then takes the same step
+        if (rcc) return rcc;
+      }
+      map_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p);
+      LB_LAUNCH_CHECK(c);
+    }
+    const int rc = lm_read_header(c, st, &h);
+    if (rc) return rc;
+    if (h.done) break;
+  }
+  prof_end(c);
+  for (int i = 0; i < 3; i++) { out->rot[i] = h.rot[i]; out->pos[i] = h.pos[i]; }
+  out->iterations = h.iters_run;
+  out->converged = h.done ? 1 : 0;
+  return LOAM_B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ bulk transforms

@@ -10,6 +10,7 @@
 #include "gridnn.cuh"
 #include "lbvh.cuh"
 #include "linalg.cuh"
+#include "lmstep.cuh"
 
 namespace loamb {
 
@@ -21,6 +22,110 @@ struct MapIterArgs {
   float tx, ty, tz;
   float A[9], B[9], C[9];              // Jacobian coefficient matrices, products formed on the host in reference order
 };
+
+// sin / cos of the pose angles -> kernel arguments (BasicLaserMapping.cpp:842-853), host and device
+LOAMB_HD inline void map_args_from(const float sin_[3], const float cos_[3], const float pos[3], MapIterArgs& a) {
+  const float srx = sin_[0], crx = cos_[0], sry = sin_[1], cry = cos_[1], srz = sin_[2],
+              crz = cos_[2];
+  a.srx = srx; a.crx = crx; a.sry = sry; a.cry = cry; a.srz = srz; a.crz = crz;
+  a.tx = pos[0]; a.ty = pos[1]; a.tz = pos[2];
+  // Jacobian coefficient products, formed left to right exactly like BasicLaserMapping.cpp:842-853
+  a.A[0] = crx * sry * srz;      a.A[1] = crx * crz * sry;        a.A[2] = -(srx * sry);
+  a.A[3] = -srx * srz;           a.A[4] = -(crz * srx);           a.A[5] = -crx;
+  a.A[6] = crx * cry * srz;      a.A[7] = crx * cry * crz;        a.A[8] = -(cry * srx);
+  a.B[0] = cry * srx * srz - crz * sry;
+  a.B[1] = sry * srz + cry * crz * srx;
+  a.B[2] = crx * cry;
+  a.B[3] = a.B[4] = a.B[5] = 0.f;
+  a.B[6] = -cry * crz - srx * sry * srz;
+  a.B[7] = cry * srz - crz * srx * sry;
+  a.B[8] = -(crx * sry);
+  a.C[0] = crz * srx * sry - cry * srz;
+  a.C[1] = -cry * crz - srx * sry * srz;
+  a.C[2] = 0.f;
+  a.C[3] = crx * crz;
+  a.C[4] = -(crx * srz);
+  a.C[5] = 0.f;
+  a.C[6] = sry * srz + cry * crz * srx;
+  a.C[7] = crz * sry - cry * srx * srz;
+  a.C[8] = 0.f;
+}
+
+// ---- device-resident Gauss-Newton loop (lmstep.cuh)
+struct MapLmState {
+  LmHeader h;
+  GnState gn;
+  float delta_t_abort, delta_r_abort;
+  int max_iter;
+  MapIterArgs args;  // arguments of iteration h.iter
+};
+
+#if defined(__CUDACC__)
+__device__ inline void map_lm_refresh_args(MapLmState* st) {
+  float sn[3], cs[3];
+  for (int i = 0; i < 3; i++) {
+    double sd, cd;
+    sincos((double)st->h.rot[i], &sd, &cd);  // rounded once: agrees with the host's float libm except in rare cases
+    sn[i] = (float)sd;
+    cs[i] = (float)cd;
+  }
+  MapIterArgs a;
+  map_args_from(sn, cs, st->h.pos, a);
+  st->args = a;
+}
+
+__global__ void map_lm_init_kernel(MapLmState* st, float rx, float ry, float rz, float tx, float ty, float tz,
+                                   float delta_t_abort, float delta_r_abort, int max_iter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->h.rot[0] = rx; st->h.rot[1] = ry; st->h.rot[2] = rz;
+  st->h.pos[0] = tx; st->h.pos[1] = ty; st->h.pos[2] = tz;
+  st->h.iter = 0;
+  st->h.done = max_iter <= 0 ? 1 : 0;
+  st->h.iters_run = 0;
+  st->gn.degenerate = 0;
+  st->delta_t_abort = delta_t_abort;
+  st->delta_r_abort = delta_r_abort;
+  st->max_iter = max_iter;
+  map_lm_refresh_args(st);
+}
+
+// One thread, after the normal equations of iteration h.iter are complete in result[0..31]
+// (BasicLaserMapping.cpp:826-828 skip, :867-922 solve / update / convergence)
+__device__ inline void map_lm_step(MapLmState* st, const float* __restrict__ result) {
+  LmHeader& h = st->h;
+  h.iters_run = h.iter + 1;
+  bool converged = false;
+  if ((int)(result[27] + 0.5f) >= 50) {
+    float AtA[36], AtB[6], x[6];
+    int k = 0;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        AtA[i * 6 + j] = result[k];
+        AtA[j * 6 + i] = result[k];
+        k++;
+      }
+    for (int i = 0; i < 6; i++) AtB[i] = result[21 + i];
+    gn_solve(AtA, AtB, h.iter == 0, 100.f, st->gn, x);
+    for (int i = 0; i < 3; i++) {
+      h.rot[i] = h.rot[i] + x[i];
+      h.pos[i] += x[3 + i];
+    }
+    double r2 = 0.0, t2 = 0.0;
+    for (int i = 0; i < 3; i++) {
+      const double rd = (double)(float)((double)x[i] * 180.0 / 3.14159265358979323846);  // rad2deg returns float
+      r2 += rd * rd;
+      const double td = (double)(x[3 + i] * 100.f);
+      t2 += td * td;
+    }
+    const float deltaR = (float)sqrt(r2), deltaT = (float)sqrt(t2);
+    converged = deltaR < st->delta_r_abort && deltaT < st->delta_t_abort;
+  }
+  h.iter++;
+  if (converged || h.iter >= st->max_iter) h.done = 1;
+  map_lm_refresh_args(st);
+  __threadfence();
+}
+#endif
 
 __device__ __forceinline__ void associate_to_map(const MapIterArgs& a, const float4& pi, float& x, float& y, float& z) {
   // rotateZXY(po, rot_z, rot_x, rot_y) then translate (math_utils.h:196-238)
@@ -145,7 +250,7 @@ __device__ __forceinline__ void accumulate_row(float* acc, const float* row, flo
 
 // block reduction of NEQ accumulators -> partials[block]; the last block to finish folds all partials in block
 // order (double accumulation) into result[NEQ] and resets the ticket for the next launch.
-__device__ __forceinline__ void reduce_normal_equations(float* acc, float* __restrict__ partials,
+__device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __restrict__ partials,
                                                         float* __restrict__ result, unsigned int* ticket) {
   __shared__ float s_part[LM_THREADS / 32][NEQ];
   __shared__ bool s_last;
@@ -186,6 +291,7 @@ __device__ __forceinline__ void reduce_normal_equations(float* acc, float* __res
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
+  return s_last;
 }
 
 constexpr int MAP_THREADS = 256;
@@ -200,13 +306,24 @@ static_assert(MAP_Q_PER_BLOCK == 32, "the fit phase maps one query to one lane o
 //            partial written straight from registers; the last CTA folds all partials in fixed order.
 // 64 registers / thread -> 4 CTAs per SM, so the ~550 CTAs of an HDL-64 sweep are a single wave on 148 SMs (at 72
 // registers the 8-lane kernel ran 1.06 waves: half of the kernel's time was a second wave of 63 CTAs).
-template <bool STATS, typename LOOKUP>
+template <bool STATS, typename LOOKUP, bool DEVLOOP = false>
 __global__ void __launch_bounds__(MAP_THREADS, 4)
 map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restrict__ queries, int n_corner_total,
-                   int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a,
+                   int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a_param,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
-                   unsigned long long* __restrict__ walk_totals) {
+                   unsigned long long* __restrict__ walk_totals, const MapLmState* __restrict__ lm = nullptr) {
+  // DEVLOOP (device-resident loop, lmstep.cuh): the arguments of the current iteration come from the state block
+  // (staged in shared memory; the by-value `a_param` of the per-iteration API stays in the constant bank), and there
+  // is nothing to do once the loop has converged
+  __shared__ MapIterArgs s_args;
+  if (DEVLOOP) {
+    if (lm->h.done) return;
+    if (threadIdx.x < (int)(sizeof(MapIterArgs) / 4))
+      reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
+    __syncthreads();
+  }
+  const MapIterArgs& a = DEVLOOP ? s_args : a_param;
   __shared__ float4 s_nn[MAP_Q_PER_BLOCK][5];                 // xyz of the five neighbours, w = index bits (< 0: none)
   __shared__ unsigned s_pre[MAP_Q_PER_BLOCK][GRID_SLOTS + 1];
   __shared__ unsigned s_first[MAP_Q_PER_BLOCK][GRID_SLOTS];
@@ -341,6 +458,11 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
+}
+
+__global__ void map_lm_step_kernel(MapLmState* st, const float* __restrict__ result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || st->h.done) return;
+  map_lm_step(st, result);
 }
 
 }  // namespace loamb

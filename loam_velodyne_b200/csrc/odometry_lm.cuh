@@ -27,6 +27,40 @@ struct OdomIterArgs {
   float atx_y, aty_y, atz_x, atz_y, atz_z;  // crx*srz, crx*crz, crx*sry, srx, crx*cry
 };
 
+// pose -> kernel arguments (BasicLaserOdometry.cpp:514-543), host and device
+LOAMB_HD inline void odom_args_from(const float rot[3], const float sin_[3], const float cos_[3], const float pos[3],
+                                    float inv_scan_period, int iter, OdomIterArgs& a) {
+  const float srx = sin_[0], crx = cos_[0], sry = sin_[1], cry = cos_[1], srz = sin_[2],
+              crz = cos_[2];
+  const float tx = pos[0], ty = pos[1], tz = pos[2];
+  a.rx = rot[0]; a.ry = rot[1]; a.rz = rot[2];
+  a.tx = tx; a.ty = ty; a.tz = tz;
+  a.inv_sp = inv_scan_period;
+  a.iter = iter;
+  // BasicLaserOdometry.cpp:514-543 with s = 1 (every `s *` is an exact multiplication by one)
+  a.g1a = -crx * sry * srz;  a.g1b = crx * crz * sry;  a.g1c = srx * sry;
+  a.k1 = tx * crx * sry * srz;  a.k2 = ty * crx * crz * sry;  a.k3 = tz * srx * sry;
+  a.t1 = srx * srz;  a.t2 = crz * srx;  a.t3 = crx;
+  a.k4 = ty * crz * srx;  a.k5 = tz * crx;  a.k6 = tx * srx * srz;
+  a.u1 = crx * cry * srz;  a.u2 = crx * cry * crz;  a.u3 = cry * srx;
+  a.k7 = tz * cry * srx;  a.k8 = ty * crx * cry * crz;  a.k9 = tx * crx * cry * srz;
+  a.e1 = -crz * sry - cry * srx * srz;
+  a.e2 = cry * crz * srx - sry * srz;
+  a.e3 = crx * cry;
+  a.e4 = crz * sry + cry * srx * srz;
+  a.e5 = sry * srz - cry * crz * srx;
+  a.k10 = tz * crx * cry;
+  a.f1 = cry * crz - srx * sry * srz;
+  a.f2 = cry * srz + crz * srx * sry;
+  a.f3 = crx * sry;
+  a.k11 = tz * crx * sry;
+  a.g1 = -cry * srz - crz * srx * sry;
+  a.h1 = -crx * crz;  a.h2 = crx * srz;
+  a.k12 = ty * crx * srz;  a.k13 = tx * crx * crz;
+  a.atx_y = crx * srz;  a.aty_y = crx * crz;
+  a.atz_x = crx * sry;  a.atz_y = srx;  a.atz_z = crx * cry;
+}
+
 // cos / sin evaluated in double and rounded once: agrees with a correctly rounded float libm (the reference
 // calls std::cos / std::sin on float, Angle.h:23-26) except in rare double-rounding cases.
 __device__ __forceinline__ void sincos_f(float a, float& s, float& c) {
@@ -34,6 +68,85 @@ __device__ __forceinline__ void sincos_f(float a, float& s, float& c) {
   sincos((double)a, &sd, &cd);
   s = (float)sd;
   c = (float)cd;
+}
+
+// ---- device-resident Gauss-Newton loop (lmstep.cuh): state block + the step the last CTA of an iteration runs
+struct OdomLmState {
+  LmHeader h;
+  GnState gn;
+  float inv_sp, delta_t_abort, delta_r_abort;
+  int max_iter, n_last_corner, n_last_surf;
+  OdomIterArgs args;  // arguments of iteration h.iter
+};
+
+__device__ inline void odom_lm_refresh_args(OdomLmState* st) {
+  float sn[3], cs[3];
+  for (int i = 0; i < 3; i++) sincos_f(st->h.rot[i], sn[i], cs[i]);
+  OdomIterArgs a;
+  odom_args_from(st->h.rot, sn, cs, st->h.pos, st->inv_sp, st->h.iter, a);
+  a.n_last_corner = st->n_last_corner;
+  a.n_last_surf = st->n_last_surf;
+  st->args = a;
+}
+
+__global__ void odom_lm_init_kernel(OdomLmState* st, float rx, float ry, float rz, float tx, float ty, float tz, float inv_sp,
+                                    float delta_t_abort, float delta_r_abort, int max_iter, int n_last_corner,
+                                    int n_last_surf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->h.rot[0] = rx; st->h.rot[1] = ry; st->h.rot[2] = rz;
+  st->h.pos[0] = tx; st->h.pos[1] = ty; st->h.pos[2] = tz;
+  st->h.iter = 0;
+  st->h.done = max_iter <= 0 ? 1 : 0;
+  st->h.iters_run = 0;
+  st->gn.degenerate = 0;
+  st->inv_sp = inv_sp;
+  st->delta_t_abort = delta_t_abort;
+  st->delta_r_abort = delta_r_abort;
+  st->max_iter = max_iter;
+  st->n_last_corner = n_last_corner;
+  st->n_last_surf = n_last_surf;
+  odom_lm_refresh_args(st);
+}
+
+// One thread, after the normal equations of iteration h.iter are complete in result[0..31]
+// (BasicLaserOdometry.cpp:484-488 skip, :559-622 solve / update / NaN reset / convergence)
+__device__ inline void odom_lm_step(OdomLmState* st, const float* __restrict__ result) {
+  LmHeader& h = st->h;
+  h.iters_run = h.iter + 1;
+  bool converged = false;
+  if ((int)(result[27] + 0.5f) >= 10) {
+    float AtA[36], AtB[6], x[6];
+    int k = 0;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        AtA[i * 6 + j] = result[k];
+        AtA[j * 6 + i] = result[k];
+        k++;
+      }
+    for (int i = 0; i < 6; i++) AtB[i] = result[21 + i];
+    gn_solve(AtA, AtB, h.iter == 0, 10.f, st->gn, x);
+    for (int i = 0; i < 3; i++) {
+      h.rot[i] = h.rot[i] + x[i];
+      h.pos[i] += x[3 + i];
+    }
+    for (int i = 0; i < 3; i++) {
+      if (!isfinite(h.rot[i])) h.rot[i] = 0.f;
+      if (!isfinite(h.pos[i])) h.pos[i] = 0.f;
+    }
+    double r2 = 0.0, t2 = 0.0;
+    for (int i = 0; i < 3; i++) {
+      const double rd = (double)(float)((double)x[i] * 180.0 / 3.14159265358979323846);  // rad2deg returns float
+      r2 += rd * rd;
+      const double td = (double)(x[3 + i] * 100.f);
+      t2 += td * td;
+    }
+    const float deltaR = (float)sqrt(r2), deltaT = (float)sqrt(t2);
+    converged = deltaR < st->delta_r_abort && deltaT < st->delta_t_abort;
+  }
+  h.iter++;
+  if (converged || h.iter >= st->max_iter) h.done = 1;
+  odom_lm_refresh_args(st);
+  __threadfence();
 }
 
 __device__ __forceinline__ void rot_zxy(float& x, float& y, float& z, float sz, float cz, float sx, float cx,
@@ -101,10 +214,21 @@ __device__ __forceinline__ void scan_best_warp(ScanBest& a) {
   }
 }
 
+// DEVLOOP (device-resident loop, lmstep.cuh): arguments of the current iteration from the state block (staged in
+// shared memory; the by-value argument of the per-iteration API stays in the constant bank); no work once converged
+template <bool DEVLOOP>
 __global__ void __launch_bounds__(LM_THREADS)
 odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
                    const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
-                   OdomIterArgs a, int* __restrict__ ind) {
+                   OdomIterArgs a_param, int* __restrict__ ind, const OdomLmState* __restrict__ lm = nullptr) {
+  __shared__ OdomIterArgs s_args;
+  if (DEVLOOP) {
+    if (lm->h.done) return;
+    if (threadIdx.x < (int)(sizeof(OdomIterArgs) / 4))
+      reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
+    __syncthreads();
+  }
+  const OdomIterArgs& a = DEVLOOP ? s_args : a_param;
   const int lane = threadIdx.x & 31;
   const int qi = (blockIdx.x * LM_THREADS + threadIdx.x) >> 5;  // one warp per query
   if (qi >= n_sharp + n_flat) return;
@@ -210,12 +334,21 @@ odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
   }
 }
 
+template <bool DEVLOOP>
 __global__ void __launch_bounds__(LM_THREADS)
 odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
                     const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
-                    int sharp_blocks, OdomIterArgs a, int* __restrict__ ind, float* __restrict__ partials,
+                    int sharp_blocks, OdomIterArgs a_param, int* __restrict__ ind, float* __restrict__ partials,
                     float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
-                    int8_t* __restrict__ dbg_sel) {
+                    int8_t* __restrict__ dbg_sel, const OdomLmState* __restrict__ lm = nullptr) {
+  __shared__ OdomIterArgs s_args;
+  if (DEVLOOP) {
+    if (lm->h.done) return;
+    if (threadIdx.x < (int)(sizeof(OdomIterArgs) / 4))
+      reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
+    __syncthreads();
+  }
+  const OdomIterArgs& a = DEVLOOP ? s_args : a_param;
   float acc[29];
 #pragma unroll
   for (int k = 0; k < 29; k++) acc[k] = 0.f;
@@ -286,6 +419,11 @@ odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __re
     }
   }
   reduce_normal_equations(acc, partials, result, ticket);
+}
+
+__global__ void odom_lm_step_kernel(OdomLmState* st, const float* __restrict__ result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || st->h.done) return;
+  odom_lm_step(st, result);
 }
 
 // BasicLaserOdometry::transformToEnd without IMU terms (BasicLaserOdometry.cpp:57-87): in place on a device cloud.

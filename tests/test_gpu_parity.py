@@ -199,6 +199,82 @@ def test_odom_iteration_per_correspondence(ctx, oracle, scene):
         assert _rel(ne["AtB"], ref["AtB"]) <= 2e-4
 
 
+def test_device_resident_odometry_loop(ctx, oracle, scene):
+    """loam_b200_odom_solve (whole Gauss-Newton loop on the device) against the loop driven from the host through the
+    per-iteration entry point + the oracle's own 6x6 solve: same iteration count, pose within 2e-6; deterministic."""
+    from loam_velodyne_b200 import synth
+    from oracle import pydriver
+    lidar = synth.Lidar.vlp16()
+    p0, r0 = synth.make_sweep(scene, lidar, 0, yaw_rate=math.radians(5.0))
+    p1, r1 = synth.make_sweep(scene, lidar, 1, yaw_rate=math.radians(5.0))
+    s = oracle.scanreg()
+    s.process(p0, r0)
+    last_c, last_s = s.cloud("less_sharp").copy(), s.cloud("less_flat").copy()
+    last_c[:, 3] = np.floor(last_c[:, 3])
+    last_s[:, 3] = np.floor(last_s[:, 3])
+    s.process(p1, r1)
+    sharp, flat = s.cloud("sharp"), s.cloud("flat")
+    ctx.odom_set_last(last_c, last_s)
+    ctx.odom_set_current(sharp, flat)
+    tf_dev, iters = ctx.odom_solve(np.zeros(6, np.float32))
+    tf_dev2, iters2 = ctx.odom_solve(np.zeros(6, np.float32))
+    np.testing.assert_array_equal(tf_dev, tf_dev2)
+    assert iters == iters2 and 1 <= iters <= 25
+    # host-driven loop: GPU normal equations per iteration, solve by the oracle driver (reference arithmetic)
+    tf = np.zeros(6, np.float32)
+    P, degenerate, n_it = None, False, 0
+    for it in range(25):
+        n_it = it + 1
+        ne = ctx.odom_iterate(tf, it)
+        if ne["n_selected"] < 10:
+            continue
+        x = oracle.qr_solve6(ne["AtA"], ne["AtB"]).astype(np.float32)
+        if it == 0:
+            w, V = oracle.eig_sym(ne["AtA"])
+            assert w.min() > 10.0  # the synthetic scene is well conditioned: no degeneracy projection
+        tf = (tf + x).astype(np.float32)
+        dr = math.sqrt(sum(float(np.float32(math.degrees(float(v)))) ** 2 for v in x[:3]))
+        dt = math.sqrt(sum(float(np.float32(v) * np.float32(100)) ** 2 for v in x[3:]))
+        if dr < 0.1 and dt < 0.1:
+            break
+    assert n_it == iters
+    np.testing.assert_allclose(tf_dev, tf, rtol=0, atol=5e-6)
+
+
+def test_device_resident_mapping_loop(ctx, oracle, scene, map_200k):
+    """loam_b200_map_solve against the same loop driven from the host (per-iteration kernel + the oracle's 6x6 solve)."""
+    from loam_velodyne_b200 import api, synth
+    corner, surf = map_200k
+    pts, rs = synth.make_sweep(scene, synth.Lidar.vlp16(), 5, yaw_rate=math.radians(5.0))
+    s = oracle.scanreg()
+    s.process(pts, rs)
+    cq = oracle.voxel_grid(s.cloud("less_sharp"), 0.2)
+    sq = oracle.voxel_grid(s.cloud("less_flat"), 0.4)
+    pos, yaw = synth.pose_at(0.6, np.array([0.0, 0.0, 1.0]), math.radians(5.0))
+    start = np.asarray((0.002, yaw + 0.004, -0.003, pos[0] + 0.05, pos[1] - 0.02, pos[2] + 0.08), np.float32)
+    ctx.tree_build(api.TREE_MAP_CORNER, corner)
+    ctx.tree_build(api.TREE_MAP_SURF, surf)
+    ctx.map_set_queries(cq, sq)
+    tf_dev, iters = ctx.map_solve(start)
+    tf, n_it = start.copy(), 0
+    for it in range(10):
+        n_it = it + 1
+        ne = ctx.map_iterate(tf)
+        if ne["n_selected"] < 50:
+            continue
+        x = oracle.qr_solve6(ne["AtA"], ne["AtB"]).astype(np.float32)
+        if it == 0:
+            assert oracle.eig_sym(ne["AtA"])[0].min() > 100.0
+        tf = (tf + x).astype(np.float32)
+        dr = math.sqrt(sum(float(np.float32(math.degrees(float(v)))) ** 2 for v in x[:3]))
+        dt = math.sqrt(sum(float(np.float32(v) * np.float32(100)) ** 2 for v in x[3:]))
+        if dr < 0.05 and dt < 0.05:
+            break
+    assert n_it == iters and 1 <= iters <= 10
+    np.testing.assert_allclose(tf_dev, tf, rtol=0, atol=5e-6)
+    assert np.abs(tf_dev - start).max() > 1e-3  # the loop did move the pose
+
+
 def test_transforms(ctx, checker, scene):
     from loam_velodyne_b200 import synth
     pts, rs = synth.make_sweep(scene, synth.Lidar.vlp16(), 3)
