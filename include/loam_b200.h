@@ -215,6 +215,14 @@ int loam_b200_cloud_swap(loam_b200_ctx* ctx, int slot_a, int slot_b);
 /* copy a cloud between slots, possibly of two different contexts on the same device (stream-ordered, no host hop) */
 int loam_b200_cloud_copy(loam_b200_ctx* dst_ctx, int dst_slot, loam_b200_ctx* src_ctx, int src_slot);
 
+/* Ring-binning front end = MultiScanRegistration::process up to the processScanlines call
+ * (MultiScanRegistration.cpp:160-238, mapper :44-67): n unordered sensor-frame points (xyz, 3 floats each, arrival order;
+ * host memory, or device memory when on_device != 0) -> LOAM_B200_C_REG_FULL holds the ring-ordered cloud
+ * (x <- y, y <- z, z <- x, intensity = ring + relTime), ring_sizes[n_rings] the points per ring; rejected points
+ * (non-finite, |p|^2 < 1e-4, ring outside [0, n_rings)) are dropped.  Follow with loam_b200_reg_run. */
+int loam_b200_reg_bin(loam_b200_ctx* ctx, const float* xyz, int n, int on_device, float lower_bound_deg,
+                      float upper_bound_deg, int n_rings, float scan_period, int32_t* ring_sizes, int* n_kept);
+
 /* Scan registration on the cloud in LOAM_B200_C_REG_FULL (already uploaded): fills the REG_SHARP / LESS_SHARP / FLAT /
  * LESS_FLAT slots; counts_out[4] = their sizes.  Index lists and labels of this sweep stay readable until the next run. */
 int loam_b200_reg_run(loam_b200_ctx* ctx, const int32_t* ring_start, const int32_t* ring_end, int n_rings,

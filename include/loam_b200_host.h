@@ -26,6 +26,10 @@ int loam_b200_scanreg_configure(void* h, float scanPeriod, int nFeatureRegions, 
                                 int maxSurfaceFlat, float lessFlatFilterSize, float surfaceCurvatureThreshold);
 /* processScanlines: ring r = ring_sizes[r] consecutive points */
 int loam_b200_scanreg_process(void* h, const float* pts, const int* ring_sizes, int n_rings);
+/* processUnorderedSweep: MultiScanRegistration::process (MultiScanRegistration.cpp:160-238) -- n unordered sensor-frame
+ * xyz points (3 floats each) binned into rings on the GPU with MultiScanMapper(lower, upper, n_rings), then extraction */
+int loam_b200_scanreg_process_unordered(void* h, const float* xyz, int n, float lower_bound_deg, float upper_bound_deg,
+                                        int n_rings);
 /* which: 0 laserCloud, 1 cornerPointsSharp, 2 cornerPointsLessSharp, 3 surfacePointsFlat, 4 surfacePointsLessFlat */
 int loam_b200_scanreg_cloud_size(void* h, int which);
 int loam_b200_scanreg_cloud_copy(void* h, int which, float* out);

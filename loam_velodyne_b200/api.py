@@ -120,6 +120,7 @@ def lib():
         "loam_b200_cloud_size": (C.c_int, [vp, C.c_int]),
         "loam_b200_cloud_swap": (C.c_int, [vp, C.c_int, C.c_int]),
         "loam_b200_cloud_copy": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "loam_b200_reg_bin": (C.c_int, [vp, _F, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _I, _I]),
         "loam_b200_reg_run": (C.c_int, [vp, _I, _I, C.c_int, C.POINTER(RegParams), _I]),
         "loam_b200_reg_indices": (C.c_int, [vp, C.c_int, _I, C.c_int, _I]),
         "loam_b200_reg_labels": (C.c_int, [vp, _B, C.c_int]),
@@ -147,6 +148,7 @@ def lib():
         "loam_b200_scanreg_create": (vp, []),
         "loam_b200_scanreg_destroy": (None, [vp]),
         "loam_b200_scanreg_configure": (C.c_int, [vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
+        "loam_b200_scanreg_process_unordered": (C.c_int, [vp, _F, C.c_int, C.c_float, C.c_float, C.c_int]),
         "loam_b200_scanreg_process": (C.c_int, [vp, _F, _I, C.c_int]),
         "loam_b200_scanreg_cloud_size": (C.c_int, [vp, C.c_int]),
         "loam_b200_scanreg_cloud_copy": (C.c_int, [vp, C.c_int, _F]),
@@ -264,6 +266,18 @@ class Ctx:
         if rc != 0:
             detail = self.L.loam_b200_last_error(self.h).decode()
             raise LoamB200Error(f"{what}: {self.L.loam_b200_strerror(rc).decode()} {detail}")
+
+    def reg_bin(self, xyz, lower_deg, upper_deg, n_rings, scan_period=0.1):
+        """Ring-binning front end (loam_b200_reg_bin) -> (ring-ordered n_kept x 4 cloud, ring sizes)."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        sizes = np.zeros(n_rings, np.int32)
+        kept = C.c_int(0)
+        self._ck(self.L.loam_b200_reg_bin(self.h, _fp(a), a.shape[0], 0, lower_deg, upper_deg, n_rings, scan_period,
+                                          _ip(sizes), C.byref(kept)), "reg_bin")
+        out = np.empty((max(kept.value, 1), 4), np.float32)
+        got = C.c_int(0)
+        self._ck(self.L.loam_b200_cloud_download(self.h, 0, _fp(out), out.shape[0], C.byref(got)), "cloud_download")  # C_REG_FULL
+        return out[:got.value].copy(), sizes
 
     def extract_features(self, pts, ring_sizes, params: RegParams | None = None):
         pts = _pts(pts)
@@ -448,6 +462,12 @@ class ScanRegistration(_Handle):
         pts = _pts(pts)
         rs = np.ascontiguousarray(ring_sizes, dtype=np.int32)
         self._ck(self.L.loam_b200_scanreg_process(self.h, _fp(pts), _ip(rs), rs.shape[0]), "processScanlines")
+
+    def process_unordered(self, xyz, lower_deg, upper_deg, n_rings):
+        """MultiScanRegistration::process: unordered sensor-frame xyz (n x 3) -> ring binning on the GPU -> extraction."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        self._ck(self.L.loam_b200_scanreg_process_unordered(self.h, _fp(a), a.shape[0], lower_deg, upper_deg, n_rings),
+                 "processUnorderedSweep")
 
     def cloud(self, name):
         return self._cloud(self.L.loam_b200_scanreg_cloud_size, self.L.loam_b200_scanreg_cloud_copy, self.NAMES[name])

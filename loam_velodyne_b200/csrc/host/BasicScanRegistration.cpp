@@ -102,6 +102,21 @@ void BasicScanRegistration::processPackedSweep(const Time& scanTime, const float
   updateIMUTransform();
 }
 
+void BasicScanRegistration::processUnorderedSweep(const Time& scanTime, const float* xyz, int n, MultiScanMapper mapper,
+                                                  bool onDevice) {
+  reset(scanTime);
+  const int nRings = (int)mapper.getNumberOfScanRings();
+  std::vector<int32_t> ringSizes((size_t)nRings, 0);
+  int kept = 0;
+  _gpu->check(loam_b200_reg_bin(_gpu->get(), xyz, n, onDevice ? 1 : 0, mapper.getLowerBound(), mapper.getUpperBound(), nRings,
+                                _config.scanPeriod, ringSizes.data(), &kept),
+              "loam_b200_reg_bin");
+  size_t cloudSize = 0;
+  for (int i = 0; i < nRings; i++) appendRange(_scanIndices, cloudSize, (size_t)ringSizes[i]);
+  runExtraction((int)cloudSize);
+  updateIMUTransform();
+}
+
 void BasicScanRegistration::processDeviceSweep(const Time& scanTime, const void* deviceXyzi, const int* ringSizes, int nRings) {
   reset(scanTime);
   size_t cloudSize = 0;

@@ -124,6 +124,14 @@ int loam_b200_scanreg_configure(void* h, float scanPeriod, int nFeatureRegions, 
 int loam_b200_scanreg_process(void* h, const float* pts, const int* ring_sizes, int n_rings) {
   return guarded([&] { ((RegH*)h)->process(pts, ring_sizes, n_rings); return 0; });
 }
+int loam_b200_scanreg_process_unordered(void* h, const float* xyz, int n, float lower_bound_deg, float upper_bound_deg,
+                                        int n_rings) {
+  return guarded([&] {
+    ((RegH*)h)->r.processUnorderedSweep(loam::Time(), xyz, n, loam::MultiScanMapper(lower_bound_deg, upper_bound_deg,
+                                                                                     (uint16_t)n_rings));
+    return 0;
+  });
+}
 int loam_b200_scanreg_cloud_size(void* h, int which) { return (int)((RegH*)h)->cloud(which).size(); }
 int loam_b200_scanreg_cloud_copy(void* h, int which, float* out) { dump(((RegH*)h)->cloud(which), out); return 0; }
 int loam_b200_scanreg_index_size(void* h, int which) { return (int)((RegH*)h)->index(which).size(); }

@@ -4,6 +4,8 @@
 // compiling; the feature extraction itself (extractFeatures / setScanBuffersFor / setRegionBuffersFor /
 // markAsPicked, BasicScanRegistration.cpp:155-254,284-386) runs on the GPU through loam_b200_extract_features.
 #pragma once
+#include <cmath>
+#include <cstdint>
 
 #include <utility>
 #include <vector>
@@ -54,6 +56,33 @@ typedef struct IMUState {
   static void interpolate(const IMUState& start, const IMUState& end, const float& ratio, IMUState& result);
 } IMUState;
 
+/** Linear vertical-angle -> ring mapper, same class as the reference's (declared there in the ROS-bound
+ *  MultiScanRegistration.h:47-103; MultiScanRegistration.cpp:44-66).  Used by processUnorderedSweep(). */
+class MultiScanMapper {
+ public:
+  MultiScanMapper(const float& lowerBound = -15, const float& upperBound = 15, const uint16_t& nScanRings = 16)
+      : _lowerBound(lowerBound), _upperBound(upperBound), _nScanRings(nScanRings),
+        _factor((nScanRings - 1) / (upperBound - lowerBound)) {}
+  const float& getLowerBound() { return _lowerBound; }
+  const float& getUpperBound() { return _upperBound; }
+  const uint16_t& getNumberOfScanRings() { return _nScanRings; }
+  void set(const float& lowerBound, const float& upperBound, const uint16_t& nScanRings) {
+    _lowerBound = lowerBound;
+    _upperBound = upperBound;
+    _nScanRings = nScanRings;
+    _factor = (nScanRings - 1) / (upperBound - lowerBound);
+  }
+  int getRingForAngle(const float& angle) { return int(((angle * 180 / M_PI) - _lowerBound) * _factor + 0.5); }
+  static inline MultiScanMapper Velodyne_VLP_16() { return MultiScanMapper(-15, 15, 16); }
+  static inline MultiScanMapper Velodyne_HDL_32() { return MultiScanMapper(-30.67f, 10.67f, 32); }
+  static inline MultiScanMapper Velodyne_HDL_64E() { return MultiScanMapper(-24.9f, 2, 64); }
+
+ private:
+  float _lowerBound, _upperBound;
+  uint16_t _nScanRings;
+  float _factor;
+};
+
 class BasicScanRegistration {
  public:
   BasicScanRegistration();
@@ -81,6 +110,11 @@ class BasicScanRegistration {
   // (x, y, z, intensity) float quadruples; skips the per-ring pcl clouds
   void processPackedSweep(const Time& scanTime, const float* xyzi, const int* ringSizes, int nRings);
   // ... or already resident in GPU memory (device pointer to the packed points)
+  /** Extension: the ring-binning front end of MultiScanRegistration::process (MultiScanRegistration.cpp:160-238) on the
+   *  GPU, followed by the regular extraction: `xyz` = n unordered sensor-frame points (3 floats each, arrival order;
+   *  host memory, or device memory when `onDevice`).  Equivalent to building the per-ring clouds on the host and
+   *  calling processScanlines(). */
+  void processUnorderedSweep(const Time& scanTime, const float* xyz, int n, MultiScanMapper mapper, bool onDevice = false);
   void processDeviceSweep(const Time& scanTime, const void* deviceXyzi, const int* ringSizes, int nRings);
   // indices (into laserCloud()) of the picked features and the per-point labels of the last sweep
   std::vector<int> const& sharpIndices();

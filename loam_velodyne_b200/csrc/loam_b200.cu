@@ -12,6 +12,7 @@
 #include "mappool.cuh"
 #include "clustersort.cuh"
 #include "mapstore.cuh"
+#include "frontend.cuh"
 
 using namespace loamb;
 
@@ -383,7 +384,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
     st.e_state.release(); st.e_keys.release(); st.e_vals.release();
   }
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
-  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);

@@ -178,7 +178,7 @@ inline int voxel_grid_async(loam_b200_ctx* c, const float4* d_in, int n, float l
 inline int voxel_grid_device(loam_b200_ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* count) {
   *count = 0;
   if (n <= 0) return LOAM_B200_OK;
-  LB_CUDA(c, c->dcount.reserve(64));
+  LB_CUDA(c, c->dcount.reserve(512));  // one allocation for every stage counter (stages.inc: D_NUM)
   int rc = voxel_grid_async(c, d_in, n, leaf, d_out, c->dcount.p + 63);
   if (rc) return rc;
   LB_CUDA(c, cudaMemcpyAsync(count, c->dcount.p + 63, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -188,6 +188,38 @@ def make_sweep(scene: Scene, lidar: Lidar, sweep_idx: int, scan_period: float = 
     return np.ascontiguousarray(pts, dtype=np.float32), ring_sizes
 
 
+def raw_cloud_from_sweep(pts, ring_sizes, n_bad: int = 0, seed: int = 0, elev_jitter_deg: float = 0.0):
+    """Unordered sensor-frame cloud (n, 3) as a spinning lidar driver delivers it (the input of
+    MultiScanRegistration::process): the ring-ordered sweep of make_sweep() re-ordered by firing time (all rings of an
+    azimuth together), axes swapped back to the sensor frame (loam x <- y, y <- z, z <- x), intensity dropped.
+    n_bad NaN / inf / zero points are inserted at deterministic places; elev_jitter_deg tilts every point a little
+    (a real sensor's beams are not exactly equally spaced)."""
+    p = np.asarray(pts, np.float32)
+    rel = p[:, 3] - np.floor(p[:, 3])
+    order = np.argsort(rel, kind="stable")  # firing time; ties (same azimuth) keep ring order
+    q = p[order]
+    x, y, z = q[:, 0].astype(np.float64), q[:, 1].astype(np.float64), q[:, 2].astype(np.float64)
+    rng = np.random.RandomState(seed)
+    if elev_jitter_deg > 0:
+        h = np.sqrt(x * x + z * z)
+        el = np.arctan2(y, h) + np.radians(rng.uniform(-elev_jitter_deg, elev_jitter_deg, size=y.shape))
+        r = np.sqrt(h * h + y * y)
+        y = r * np.sin(el)
+        s = r * np.cos(el) / np.maximum(h, 1e-9)
+        x, z = x * s, z * s
+    raw = np.stack([z, x, y], axis=1).astype(np.float32)  # sensor x = loam z, sensor y = loam x, sensor z = loam y
+    if n_bad > 0 and raw.shape[0] > 10:
+        where = np.sort(rng.choice(np.arange(1, raw.shape[0] - 1), size=n_bad, replace=False))
+        bad = np.zeros((n_bad, 3), np.float32)
+        kinds = rng.randint(0, 4, size=n_bad)
+        bad[kinds == 0] = np.nan
+        bad[kinds == 1, 0] = np.inf
+        bad[kinds == 2] = 0.0
+        bad[kinds == 3] = np.float32(0.004)  # |p|^2 = 4.8e-5 < 1e-4
+        raw = np.insert(raw, where, bad, axis=0)
+    return np.ascontiguousarray(raw, dtype=np.float32)
+
+
 def _lattice_rect(origin, u, v, lu, lv, step, rng, jitter):
     nu = max(int(lu / step), 1)
     nv = max(int(lv / step), 1)

@@ -31,6 +31,19 @@ int loamdrv_scanreg_process(void* h, const float* pts, const int* ring_sizes, in
 int loamdrv_scanreg_cloud_size(void* h, int which);
 void loamdrv_scanreg_cloud_copy(void* h, int which, float* out);
 
+/* ---- ring binning front end (MultiScanRegistration.cpp:44-67 mapper, :160-238 process): an unordered sensor-frame xyz
+ * cloud -> axis swap, NaN / near-zero rejection, ring from the vertical angle, relative time from the azimuth (with the
+ * half-sweep bookkeeping), intensity = ring + relTime, stable binning per ring -> then the regular registration ---- */
+void* loamdrv_multiscan_create(float lower_bound_deg, float upper_bound_deg, int n_rings);
+void loamdrv_multiscan_destroy(void* h);
+/* xyz: n x 3 floats in the sensor frame; returns the number of points kept */
+int loamdrv_multiscan_process(void* h, const float* xyz, int n);
+/* ring-ordered cloud as handed to processScanlines: out_pts4 (kept x 4 floats), ring_sizes (n_rings ints) */
+void loamdrv_multiscan_binned(void* h, float* out_pts4, int* ring_sizes);
+/* registration results, same ids as loamdrv_scanreg_cloud_* */
+int loamdrv_multiscan_cloud_size(void* h, int which);
+void loamdrv_multiscan_cloud_copy(void* h, int which, float* out);
+
 /* ---- laser odometry (BasicLaserOdometry.cpp:196-666) ---- */
 void* loamdrv_odom_create(float scanPeriod, int maxIterations);
 void loamdrv_odom_destroy(void* h);

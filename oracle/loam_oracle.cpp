@@ -1022,6 +1022,64 @@ struct RegH {
     r.process(rings);
   }
 };
+// Ring binning front end: MultiScanMapper (MultiScanRegistration.cpp:44-67) + MultiScanRegistration::process (:160-238).
+// Plain float libm calls like the reference (std::atan / std::atan2 / std::sqrt on floats); IMU projection is the
+// identity without IMU data (BasicScanRegistration.cpp:100-112).
+struct MultiScan {
+  float lower, upper, factor;
+  int nRings;
+  RegH reg;
+  std::vector<Cloud> scans;
+  MultiScan(float lo, float hi, int n) : lower(lo), upper(hi), factor((n - 1) / (hi - lo)), nRings(n) {}
+  int ringForAngle(const float& angle) const { return int(((angle * 180 / M_PI) - lower) * factor + 0.5); }
+  int process(const float* xyz, int n) {
+    scans.assign(nRings, Cloud());
+    if (n <= 0) return 0;
+    float startOri = -std::atan2(xyz[1], xyz[0]);
+    float endOri = -std::atan2(xyz[3 * (size_t)(n - 1) + 1], xyz[3 * (size_t)(n - 1) + 0]) + 2 * float(M_PI);
+    if (endOri - startOri > 3 * M_PI) {
+      endOri -= 2 * M_PI;
+    } else if (endOri - startOri < M_PI) {
+      endOri += 2 * M_PI;
+    }
+    bool halfPassed = false;
+    Pt point;
+    for (int i = 0; i < n; i++) {
+      point.x = xyz[3 * (size_t)i + 1];
+      point.y = xyz[3 * (size_t)i + 2];
+      point.z = xyz[3 * (size_t)i + 0];
+      if (!std::isfinite(point.x) || !std::isfinite(point.y) || !std::isfinite(point.z)) continue;
+      if (point.x * point.x + point.y * point.y + point.z * point.z < 0.0001) continue;
+      float angle = std::atan(point.y / std::sqrt(point.x * point.x + point.z * point.z));
+      int scanID = ringForAngle(angle);
+      if (scanID >= nRings || scanID < 0) continue;
+      float ori = -std::atan2(point.x, point.z);
+      if (!halfPassed) {
+        if (ori < startOri - M_PI / 2) {
+          ori += 2 * M_PI;
+        } else if (ori > startOri + M_PI * 3 / 2) {
+          ori -= 2 * M_PI;
+        }
+        if (ori - startOri > M_PI) halfPassed = true;
+      } else {
+        ori += 2 * M_PI;
+        if (ori < endOri - M_PI * 3 / 2) {
+          ori += 2 * M_PI;
+        } else if (ori > endOri + M_PI / 2) {
+          ori -= 2 * M_PI;
+        }
+      }
+      float relTime = reg.r.cfg.scanPeriod * (ori - startOri) / (endOri - startOri);
+      point.intensity = scanID + relTime;
+      scans[scanID].push_back(point);
+    }
+    reg.r.process(scans);
+    size_t kept = 0;
+    for (auto& s : scans) kept += s.size();
+    return (int)kept;
+  }
+};
+
 struct Pipe {
   RegH reg;
   Odom odom;
@@ -1052,6 +1110,21 @@ int loamdrv_scanreg_process(void* h, const float* pts, const int* ring_sizes, in
 }
 int loamdrv_scanreg_cloud_size(void* h, int which) { return (int)((RegH*)h)->cloud(which).size(); }
 void loamdrv_scanreg_cloud_copy(void* h, int which, float* out) { dump(((RegH*)h)->cloud(which), out); }
+
+void* loamdrv_multiscan_create(float lo, float hi, int n) { return new MultiScan(lo, hi, n); }
+void loamdrv_multiscan_destroy(void* h) { delete (MultiScan*)h; }
+int loamdrv_multiscan_process(void* h, const float* xyz, int n) { return ((MultiScan*)h)->process(xyz, n); }
+void loamdrv_multiscan_binned(void* h, float* out, int* ring_sizes) {
+  MultiScan* ms = (MultiScan*)h;
+  size_t off = 0;
+  for (size_t r = 0; r < ms->scans.size(); r++) {
+    dump(ms->scans[r], out + 4 * off);
+    ring_sizes[r] = (int)ms->scans[r].size();
+    off += ms->scans[r].size();
+  }
+}
+int loamdrv_multiscan_cloud_size(void* h, int which) { return (int)((MultiScan*)h)->reg.cloud(which).size(); }
+void loamdrv_multiscan_cloud_copy(void* h, int which, float* out) { dump(((MultiScan*)h)->reg.cloud(which), out); }
 
 void* loamdrv_odom_create(float scanPeriod, int maxIterations) { return new Odom(scanPeriod, maxIterations); }
 void loamdrv_odom_destroy(void* h) { delete (Odom*)h; }

@@ -72,6 +72,12 @@ class Driver:
             "loamdrv_scanreg_process": (C.c_int, [vp, _F, _I, C.c_int]),
             "loamdrv_scanreg_cloud_size": (C.c_int, [vp, C.c_int]),
             "loamdrv_scanreg_cloud_copy": (None, [vp, C.c_int, _F]),
+            "loamdrv_multiscan_create": (vp, [C.c_float, C.c_float, C.c_int]),
+            "loamdrv_multiscan_destroy": (None, [vp]),
+            "loamdrv_multiscan_process": (C.c_int, [vp, _F, C.c_int]),
+            "loamdrv_multiscan_binned": (None, [vp, _F, _I]),
+            "loamdrv_multiscan_cloud_size": (C.c_int, [vp, C.c_int]),
+            "loamdrv_multiscan_cloud_copy": (None, [vp, C.c_int, _F]),
             "loamdrv_odom_create": (vp, [C.c_float, C.c_int]),
             "loamdrv_odom_destroy": (None, [vp]),
             "loamdrv_odom_set_inputs": (None, [vp, _F, C.c_int, _F, C.c_int, _F, C.c_int, _F, C.c_int, _F, C.c_int]),
@@ -169,6 +175,9 @@ class Driver:
         return x
 
     # ---- objects
+    def multiscan(self, lower_deg, upper_deg, n_rings):
+        return MultiScan(self, lower_deg, upper_deg, n_rings)
+
     def scanreg(self):
         return ScanReg(self)
 
@@ -207,6 +216,34 @@ class ScanReg:
 
     def cloud(self, name):
         return self.d._cloud(self.d.L.loamdrv_scanreg_cloud_size, self.d.L.loamdrv_scanreg_cloud_copy, self.h,
+                             self.NAMES[name])
+
+
+class MultiScan:
+    """Ring-binning front end (MultiScanRegistration::process, MultiScanRegistration.cpp:160-238) + registration."""
+    NAMES = ScanReg.NAMES
+
+    def __init__(self, drv, lower_deg, upper_deg, n_rings):
+        self.d = drv
+        self.n_rings = n_rings
+        self.h = drv.L.loamdrv_multiscan_create(lower_deg, upper_deg, n_rings)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.d.L.loamdrv_multiscan_destroy(self.h)
+            self.h = None
+
+    def process(self, xyz):
+        """xyz: n x 3 sensor-frame points in arrival order -> (ring-ordered n_kept x 4 cloud, ring sizes)."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        kept = self.d.L.loamdrv_multiscan_process(self.h, _fp(a), a.shape[0])
+        out = np.empty((kept, 4), np.float32)
+        sizes = np.zeros(self.n_rings, np.int32)
+        self.d.L.loamdrv_multiscan_binned(self.h, _fp(out), _ip(sizes))
+        return out, sizes
+
+    def cloud(self, name):
+        return self.d._cloud(self.d.L.loamdrv_multiscan_cloud_size, self.d.L.loamdrv_multiscan_cloud_copy, self.h,
                              self.NAMES[name])
 
 

@@ -12,6 +12,7 @@
 #include "loam_velodyne/BasicLaserMapping.h"
 #include "loam_velodyne/BasicLaserOdometry.h"
 #include "loam_velodyne/BasicScanRegistration.h"
+#include "loam_velodyne/MultiScanRegistration.h"
 #include "loam_velodyne/nanoflann_pcl.h"
 #include <Eigen/Eigenvalues>
 #include <Eigen/QR>
@@ -110,6 +111,22 @@ struct RegH {
   }
 };
 
+// the reference's ring-binning adapter (ROS names resolved by oracle/shim/ros etc.; no node is ever set up)
+struct MsH {
+  loam::MultiScanRegistration m;
+  MsH(float lo, float hi, int n) : m(loam::MultiScanMapper(lo, hi, (uint16_t)n)) {}
+  loam::BasicScanRegistration& base() { return (loam::BasicScanRegistration&)m; }
+  const Cloud& cloud(int which) {
+    switch (which) {
+      case 0: return base().laserCloud();
+      case 1: return base().cornerPointsSharp();
+      case 2: return base().cornerPointsLessSharp();
+      case 3: return base().surfacePointsFlat();
+      default: return base().surfacePointsLessFlat();
+    }
+  }
+};
+
 struct PipeH {
   RegH reg;
   OdomH odom;
@@ -151,6 +168,36 @@ int loamdrv_scanreg_process(void* h, const float* pts, const int* ring_sizes, in
 }
 int loamdrv_scanreg_cloud_size(void* h, int which) { return (int)((RegH*)h)->cloud(which).size(); }
 void loamdrv_scanreg_cloud_copy(void* h, int which, float* out) { dump(((RegH*)h)->cloud(which), out); }
+
+void* loamdrv_multiscan_create(float lo, float hi, int n) { return new MsH(lo, hi, n); }
+void loamdrv_multiscan_destroy(void* h) { delete (MsH*)h; }
+int loamdrv_multiscan_process(void* h, const float* xyz, int n) {
+  pcl::PointCloud<pcl::PointXYZ> in;
+  in.points.resize(n);
+  for (int i = 0; i < n; i++) {
+    in.points[i].x = xyz[3 * i + 0];
+    in.points[i].y = xyz[3 * i + 1];
+    in.points[i].z = xyz[3 * i + 2];
+  }
+  in.width = n;
+  in.height = 1;
+  MsH* ms = (MsH*)h;
+  ms->m.process(in, loam::Time());
+  size_t kept = 0;
+  for (auto& r : ms->m._laserCloudScans) kept += r.size();
+  return (int)kept;
+}
+void loamdrv_multiscan_binned(void* h, float* out, int* ring_sizes) {
+  MsH* ms = (MsH*)h;
+  size_t off = 0;
+  for (size_t r = 0; r < ms->m._laserCloudScans.size(); r++) {
+    dump(ms->m._laserCloudScans[r], out + 4 * off);
+    ring_sizes[r] = (int)ms->m._laserCloudScans[r].size();
+    off += ms->m._laserCloudScans[r].size();
+  }
+}
+int loamdrv_multiscan_cloud_size(void* h, int which) { return (int)((MsH*)h)->cloud(which).size(); }
+void loamdrv_multiscan_cloud_copy(void* h, int which, float* out) { dump(((MsH*)h)->cloud(which), out); }
 
 void* loamdrv_odom_create(float scanPeriod, int maxIterations) { return new OdomH(scanPeriod, maxIterations); }
 void loamdrv_odom_destroy(void* h) { delete (OdomH*)h; }

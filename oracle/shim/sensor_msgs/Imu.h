@@ -1,0 +1,15 @@
+// TEST INFRASTRUCTURE (oracle/shim): see ros/ros.h
+#pragma once
+#include <sensor_msgs/PointCloud2.h>
+namespace geometry_msgs_shim {
+struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
+struct Vector3 { double x = 0, y = 0, z = 0; };
+}  // namespace geometry_msgs_shim
+namespace sensor_msgs {
+struct Imu {
+  std_msgs_shim::Header header;
+  geometry_msgs_shim::Quaternion orientation;
+  geometry_msgs_shim::Vector3 linear_acceleration;
+  typedef boost::shared_ptr<Imu const> ConstPtr;
+};
+}  // namespace sensor_msgs

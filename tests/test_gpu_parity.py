@@ -275,6 +275,35 @@ def test_device_resident_mapping_loop(ctx, oracle, scene, map_200k):
     assert np.abs(tf_dev - start).max() > 1e-3  # the loop did move the pose
 
 
+def test_ring_binning_front_end(ctx, checker, scene):
+    """loam_b200_reg_bin / BasicScanRegistration::processUnorderedSweep against MultiScanRegistration::process of the
+    oracle: ring sizes and point order bit-exact, xyz bit-exact, intensity (ring + relTime) within one float ulp at 64
+    (the azimuth goes through a double atan2 rounded once instead of the host's float libm)."""
+    from loam_velodyne_b200 import api, synth
+    for lidar, bounds, jitter in ((synth.Lidar.vlp16(), (-15.0, 15.0, 16), 0.0), (synth.Lidar.hdl64(), (-24.9, 2.0, 64), 0.15)):
+        pts, rs = synth.make_sweep(scene, lidar, 2, yaw_rate=math.radians(5.0))
+        raw = synth.raw_cloud_from_sweep(pts, rs, n_bad=37, seed=5, elev_jitter_deg=jitter)
+        ref = checker.multiscan(*bounds)
+        p_ref, s_ref = ref.process(raw)
+        p_gpu, s_gpu = ctx.reg_bin(raw, *bounds)
+        np.testing.assert_array_equal(s_gpu, s_ref)
+        np.testing.assert_array_equal(p_gpu[:, :3], p_ref[:, :3])
+        np.testing.assert_allclose(p_gpu[:, 3], p_ref[:, 3], rtol=0, atol=8e-6)
+        # the drop-in class: same feature sets as the oracle's full MultiScanRegistration::process
+        reg = api.ScanRegistration()
+        reg.process_unordered(raw, *bounds)
+        for name in ("sharp", "less_sharp", "flat"):
+            g, r = reg.cloud(name), ref.cloud(name)
+            assert g.shape == r.shape
+            np.testing.assert_array_equal(g[:, :3], r[:, :3])
+            np.testing.assert_allclose(g[:, 3], r[:, 3], rtol=0, atol=8e-6)
+    # empty and all-rejected inputs
+    p0, s0 = ctx.reg_bin(np.zeros((0, 3), np.float32), -15.0, 15.0, 16)
+    assert p0.shape[0] == 0 and s0.sum() == 0
+    p1, s1 = ctx.reg_bin(np.full((100, 3), np.nan, np.float32), -15.0, 15.0, 16)
+    assert p1.shape[0] == 0 and s1.sum() == 0
+
+
 def test_transforms(ctx, checker, scene):
     from loam_velodyne_b200 import synth
     pts, rs = synth.make_sweep(scene, synth.Lidar.vlp16(), 3)
