@@ -173,6 +173,8 @@ struct loam_b200_ctx {
   loamb::DevBuf<float4> dbg_coeff;
   loamb::DevBuf<int8_t> dbg_sel;
   loamb::PinBuf<float> result_host;
+  loamb::PinBuf<float> result_mailbox;   // mapped pinned memory the iteration kernels post their sums to (ResultMailbox)
+  int result_seq = 0;
   loamb::DevBuf<float> bin_xyz;           // raw xyz of the ring-binning front end (frontend.cuh)
   loamb::DevBuf<unsigned char> lm_state;  // OdomLmState + MapLmState (lmstep.cuh): pose of the device-resident loops
 

@@ -213,27 +213,46 @@ __device__ __forceinline__ void grid_knn5_group8(LOOKUP& lk, float qx, float qy,
     if (sub == 7) pre[GRID_SLOTS] = total;
     __syncwarp(gmask);
     if (STATS && sub == 0) stats[1] += total;
-    // walk the flattened list with stride 8, two loads in flight
-    unsigned f = 0, lo = 0, hi = pre[1];
-    for (unsigned j = sub; j < total; j += 16) {
-      while (j >= hi) { f++; lo = hi; hi = pre[f + 1]; }
-      const int i0 = (int)(first[f] + (j - lo));
-      const float4 p0 = __ldg(sorted + i0);
-      const unsigned j1 = j + 8;
-      int i1 = -1;
-      float4 p1 = p0;
-      if (j1 < total) {
-        while (j1 >= hi) { f++; lo = hi; hi = pre[f + 1]; }
-        i1 = (int)(first[f] + (j1 - lo));
-        p1 = __ldg(sorted + i1);
-      }
-      {
-        const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;
-        cand5_offer(mine, dx * dx + dy * dy + dz * dz, i0);
-      }
-      if (i1 >= 0) {
-        const float dx = qx - p1.x, dy = qy - p1.y, dz = qz - p1.z;
-        cand5_offer(mine, dx * dx + dy * dy + dz * dz, i1);
+    // lane s takes the CONTIGUOUS range [T s / 8, T (s + 1) / 8) of the flattened list (two loads in flight): its start
+    // slot is found by a 5-step binary search, after that the cursor only advances when a cell's run ends.  (A stride-8
+    // assignment made every lane walk all 32 slots: 20 % of the kernel's instructions, profiles/r1_v5_*.md.)
+    const unsigned j_begin = (total * (unsigned)sub) >> 3, j_end = (total * (unsigned)(sub + 1)) >> 3;
+    if (j_begin < j_end) {
+      unsigned f = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (pre[f + step] <= j_begin) f += step;  // last slot whose exclusive prefix is <= j_begin
+      unsigned hi = pre[f + 1];
+      while (j_begin >= hi) { f++; hi = pre[f + 1]; }  // skip empty slots with the same prefix
+      int idx = (int)(first[f] + (j_begin - pre[f]));
+      unsigned j = j_begin;
+      while (j < j_end) {
+        const int i0 = idx;
+        const float4 p0 = __ldg(sorted + i0);
+        j++; idx++;
+        if (j < j_end && j >= hi) {
+          do { f++; hi = pre[f + 1]; } while (j >= hi);
+          idx = (int)first[f];
+        }
+        int i1 = -1;
+        float4 p1 = p0;
+        if (j < j_end) {
+          i1 = idx;
+          p1 = __ldg(sorted + i1);
+          j++; idx++;
+          if (j < j_end && j >= hi) {
+            do { f++; hi = pre[f + 1]; } while (j >= hi);
+            idx = (int)first[f];
+          }
+        }
+        {
+          const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;
+          cand5_offer(mine, dx * dx + dy * dy + dz * dz, i0);
+        }
+        if (i1 >= 0) {
+          const float dx = qx - p1.x, dy = qy - p1.y, dz = qz - p1.z;
+          cand5_offer(mine, dx * dx + dy * dy + dz * dz, i1);
+        }
       }
     }
   }

@@ -1,5 +1,6 @@
 // libloam_b200.so -- extern "C" entry points (include/loam_b200.h) over the sm_100a kernels.
 // There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point fails loudly.
+#include <atomic>
 #include <chrono>
 #include <cmath>
 
@@ -242,11 +243,7 @@ cudaError_t odom_join_rebuild(loam_b200_ctx* c) {
   return lanes_join(c, 2);
 }
 
-int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
-  LB_CUDA(c, c->result_host.reserve(NEQ));
-  LB_CUDA(c, cudaMemcpyAsync(c->result_host.p, c->result.p, NEQ * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  LB_CUDA(c, cudaStreamSynchronize(c->stream));
-  const float* r = c->result_host.p;
+static void unpack_normal_eq(const float* r, loam_b200_normal_eq* out) {
   int k = 0;
   for (int i = 0; i < 6; i++)
     for (int j = i; j < 6; j++) {
@@ -257,6 +254,49 @@ int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
   for (int i = 0; i < 6; i++) out->AtB[i] = r[21 + i];
   out->n_selected = (int)(r[27] + 0.5f);
   out->n_corner_selected = (int)(r[28] + 0.5f);
+}
+
+bool getenv_no_mailbox() {
+  static const bool off = getenv("LOAM_B200_NO_MAILBOX") != nullptr;
+  return off;
+}
+
+// mailbox of the next iteration kernel: mapped pinned memory + a fresh sequence number (mapping_lm.cuh: ResultMailbox)
+ResultMailbox next_mailbox(loam_b200_ctx* c) {
+  if (c->result_mailbox.reserve(64) != cudaSuccess) {
+    cudaGetLastError();
+    return ResultMailbox{nullptr, 0};
+  }
+  c->result_seq = c->result_seq == 0x7fffffff ? 1 : c->result_seq + 1;
+  return ResultMailbox{c->result_mailbox.p, c->result_seq};
+}
+
+// wait for the kernel launched with next_mailbox() to post its sums; falls back to a stream synchronise (which also
+// surfaces launch failures) when nothing arrives for a long time
+int fetch_normal_eq_mailbox(loam_b200_ctx* c, loam_b200_normal_eq* out) {
+  volatile int* seq = reinterpret_cast<volatile int*>(c->result_mailbox.p + 32);
+  const auto t0 = std::chrono::steady_clock::now();
+  long long spins = 0;
+  while (*seq != c->result_seq) {
+    if ((++spins & 0xfff) == 0 &&
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) {
+      LB_CUDA(c, cudaStreamSynchronize(c->stream));  // error or a very long kernel: by now the post is visible
+      if (*seq != c->result_seq) return LOAM_B200_ERR_CUDA;
+      break;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  float r[NEQ];
+  for (int i = 0; i < NEQ; i++) r[i] = reinterpret_cast<volatile float*>(c->result_mailbox.p)[i];
+  unpack_normal_eq(r, out);
+  return LOAM_B200_OK;
+}
+
+int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
+  LB_CUDA(c, c->result_host.reserve(NEQ));
+  LB_CUDA(c, cudaMemcpyAsync(c->result_host.p, c->result.p, NEQ * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  unpack_normal_eq(c->result_host.p, out);
   return LOAM_B200_OK;
 }
 
@@ -384,7 +424,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
     st.e_state.release(); st.e_keys.release(); st.e_vals.release();
   }
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
-  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->result_mailbox.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -616,6 +656,8 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   const int nb = std::max(cb + sb, 1);
   LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
   const bool dbg = coeff != nullptr;
+  const bool use_mailbox = !c->comm && c->shard_world == 1 && !c->prof_on && !walk_totals_host && !getenv_no_mailbox();
+  ResultMailbox mb{nullptr, 0};
   if (dbg) {
     LB_CUDA(c, c->dbg_coeff.reserve(nc + ns));
     LB_CUDA(c, c->dbg_sel.reserve(nc + ns));
@@ -639,16 +681,19 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     LB_CUDA(c, cudaMemcpyAsync(walk_totals_host, c->walk_totals.p, 2 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, c->stream));
   } else {
+    // single GPU: the folding CTA posts the sums straight into mapped host memory (no memcpy + synchronise); with a
+    // shard / communicator the all-reduce has to run first, so the result is fetched the classic way
+    if (use_mailbox) mb = next_mailbox(c);
     prof_begin(c, LOAM_B200_K_MAP_ITER);
     if (c->map_use_store)
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
           store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
-          c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr);
+          c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, nullptr, mb);
     else
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
           GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
           cb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
-          nullptr);
+          nullptr, nullptr, mb);
     LB_LAUNCH_CHECK(c);
     prof_end(c);
   }
@@ -656,7 +701,7 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     const int rcc = allreduce_result(c);  // no-op without a communicator
     if (rcc) return rcc;
   }
-  int rc = fetch_normal_eq(c, out);
+  int rc = mb.host ? fetch_normal_eq_mailbox(c, out) : fetch_normal_eq(c, out);
   if (rc) return rc;
   if (dbg) {
     LB_CUDA(c, cudaMemcpyAsync(coeff, c->dbg_coeff.p, (size_t)(nc + ns) * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -741,13 +786,15 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
         view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, a, c->od_ind.p);
     LB_LAUNCH_CHECK(c);
   }
+  ResultMailbox mb{nullptr, 0};
+  if (!c->prof_on && !getenv_no_mailbox()) mb = next_mailbox(c);
   odom_iterate_kernel<false><<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh,
                                                         nfl, cb, a, c->od_ind.p, c->partials.p, c->result.p,
                                                         c->ticket.p, dbg ? c->dbg_coeff.p : nullptr,
-                                                        dbg ? c->dbg_sel.p : nullptr);
+                                                        dbg ? c->dbg_sel.p : nullptr, nullptr, mb);
   LB_LAUNCH_CHECK(c);
   prof_end(c);
-  int rc = fetch_normal_eq(c, out);
+  int rc = mb.host ? fetch_normal_eq_mailbox(c, out) : fetch_normal_eq(c, out);
   if (rc) return rc;
   if (dbg) {
     LB_CUDA(c, cudaMemcpyAsync(coeff, c->dbg_coeff.p, (size_t)(nsh + nfl) * 16, cudaMemcpyDeviceToHost, c->stream));

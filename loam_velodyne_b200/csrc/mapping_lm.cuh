@@ -248,10 +248,32 @@ __device__ __forceinline__ void accumulate_row(float* acc, const float* row, flo
   if (is_corner) acc[28] += 1.f;
 }
 
+// Result mailbox in mapped pinned host memory: the CTA that folds the partials also posts the 32 sums across PCIe and
+// then a sequence number; the host spins on the sequence number instead of paying a memcpy + stream synchronise per
+// Gauss-Newton iteration (~10 us each, 7-9 per sweep).  host[0..31] = sums, host[32] = sequence.  nullptr = not used.
+struct ResultMailbox {
+  float* host;
+  int seq;
+};
+__device__ __forceinline__ void mailbox_post_value(const ResultMailbox& mb, int k, float v) {
+  if (mb.host) {
+    mb.host[k] = v;
+    __threadfence_system();
+  }
+}
+// call after a __syncthreads() that follows every mailbox_post_value of the block
+__device__ __forceinline__ void mailbox_post_seq(const ResultMailbox& mb) {
+  if (mb.host && threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(mb.host + 32) = mb.seq;
+  }
+}
+
 // block reduction of NEQ accumulators -> partials[block]; the last block to finish folds all partials in block
 // order (double accumulation) into result[NEQ] and resets the ticket for the next launch.
 __device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __restrict__ partials,
-                                                        float* __restrict__ result, unsigned int* ticket) {
+                                                        float* __restrict__ result, unsigned int* ticket,
+                                                        ResultMailbox mb = ResultMailbox{nullptr, 0}) {
   __shared__ float s_part[LM_THREADS / 32][NEQ];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,8 +310,11 @@ __device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __res
       double v = 0.0;
       for (int wv = 0; wv < LM_THREADS / 32; wv++) v += s_fold[wv][threadIdx.x];
       result[threadIdx.x] = (float)v;
+      mailbox_post_value(mb, threadIdx.x, (float)v);
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    __syncthreads();
+    mailbox_post_seq(mb);
   }
   return s_last;
 }
@@ -312,7 +337,8 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
                    int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a_param,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
-                   unsigned long long* __restrict__ walk_totals, const MapLmState* __restrict__ lm = nullptr) {
+                   unsigned long long* __restrict__ walk_totals, const MapLmState* __restrict__ lm = nullptr,
+                   ResultMailbox mb = ResultMailbox{nullptr, 0}) {
   // DEVLOOP (device-resident loop, lmstep.cuh): the arguments of the current iteration come from the state block
   // (staged in shared memory; the by-value `a_param` of the per-iteration API stays in the constant bank), and there
   // is nothing to do once the loop has converged
@@ -455,8 +481,11 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
       double r = 0.0;
       for (unsigned wv = 0; wv < NW; wv++) r += s_fold[wv][threadIdx.x];
       result[threadIdx.x] = (float)r;
+      mailbox_post_value(mb, threadIdx.x, (float)r);
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    __syncthreads();
+    mailbox_post_seq(mb);
   }
 }
 

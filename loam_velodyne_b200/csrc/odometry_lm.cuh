@@ -340,7 +340,8 @@ odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __re
                     const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
                     int sharp_blocks, OdomIterArgs a_param, int* __restrict__ ind, float* __restrict__ partials,
                     float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
-                    int8_t* __restrict__ dbg_sel, const OdomLmState* __restrict__ lm = nullptr) {
+                    int8_t* __restrict__ dbg_sel, const OdomLmState* __restrict__ lm = nullptr,
+                    ResultMailbox mb = ResultMailbox{nullptr, 0}) {
   __shared__ OdomIterArgs s_args;
   if (DEVLOOP) {
     if (lm->h.done) return;
@@ -418,7 +419,7 @@ odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __re
       accumulate_row(acc, row, b, is_corner);
     }
   }
-  reduce_normal_equations(acc, partials, result, ticket);
+  reduce_normal_equations(acc, partials, result, ticket, mb);
 }
 
 __global__ void odom_lm_step_kernel(OdomLmState* st, const float* __restrict__ result) {
