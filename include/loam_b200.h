@@ -259,6 +259,9 @@ int loam_b200_map_begin_sweep(loam_b200_ctx* ctx, const loam_b200_pose* predicte
 /* insert the stack points with the optimised pose, voxel-filter every valid cube (BasicLaserMapping.cpp:536-593) and
  * move MAP_FULL into the map frame (:595) */
 int loam_b200_map_end_sweep(loam_b200_ctx* ctx, const loam_b200_pose* optimised);
+/* Same, but issued by a helper thread of the context: returns at once; the next call on this context (any entry point)
+ * first waits for the update to be issued and returns its status if it failed. */
+int loam_b200_map_end_sweep_async(loam_b200_ctx* ctx, const loam_b200_pose* optimised);
 /* createDownsizedMap (:242-264): VoxelGrid(leaf) over the corner + surface points of the surround cubes -> MAP_SURROUND_DS */
 int loam_b200_map_surround(loam_b200_ctx* ctx, const int cen[3], const int32_t* surround_cubes, int n, float leaf);
 /* Debug / test switch: loam_b200_map_begin_sweep additionally materialises the reference's laserCloud*FromMap

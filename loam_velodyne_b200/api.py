@@ -131,6 +131,7 @@ def lib():
         "loam_b200_map_pool_append": (C.c_int, [vp, C.c_int, _F, C.c_int]),
         "loam_b200_map_begin_sweep": (C.c_int, [vp, C.POINTER(Pose), C.POINTER(MapWindow), _I]),
         "loam_b200_map_end_sweep": (C.c_int, [vp, C.POINTER(Pose)]),
+        "loam_b200_map_end_sweep_async": (C.c_int, [vp, C.POINTER(Pose)]),
         "loam_b200_map_surround": (C.c_int, [vp, _I, _I, C.c_int, C.c_float]),
         "loam_b200_map_debug_from_map": (C.c_int, [vp, C.c_int]),
         "loam_b200_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),

@@ -4,11 +4,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -124,9 +129,22 @@ struct SortScratch {
 
 }  // namespace loamb
 
+// One helper thread per context for work whose ISSUE time (tens of launches) would otherwise sit on the caller's critical
+// path although nothing waits for its result: the end-of-sweep map update (28 launches, ~70 us of host time) is posted
+// here and the caller returns at once; every later API call on the context first waits for the job (async_join).
+struct AsyncWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, busy = false, stop = false;
+  int last_rc = 0;
+};
+
 struct loam_b200_ctx {
   int device = 0;
   int sm_count = 0;
+  AsyncWorker* worker = nullptr;
   bool cluster_ok = false;  // single-launch cluster kernels of clustersort.cuh usable (LOAM_B200_NO_CLUSTER=1 disables)
   cudaStream_t stream = nullptr;
   std::string last_error;
@@ -175,6 +193,9 @@ struct loam_b200_ctx {
   loamb::PinBuf<float> result_host;
   loamb::PinBuf<float> result_mailbox;   // mapped pinned memory the iteration kernels post their sums to (ResultMailbox)
   int result_seq = 0;
+  loamb::PinBuf<int> int_mailbox;        // same for small integer results (stage counts); [511] = sequence
+  int int_seq = 0;
+  loamb::PinBuf<int> ring_table_host;
   loamb::DevBuf<float> bin_xyz;           // raw xyz of the ring-binning front end (frontend.cuh)
   loamb::DevBuf<unsigned char> lm_state;  // OdomLmState + MapLmState (lmstep.cuh): pose of the device-resident loops
 
@@ -268,12 +289,12 @@ inline int fail_cuda(loam_b200_ctx* c, cudaError_t e, const char* what, int line
     if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, #expr, __LINE__); \
   } while (0)
 
-extern long long g_total_launches;
+extern std::atomic<long long> g_total_launches;
 
 #define LB_LAUNCH_CHECK(ctx)                                                            \
   do {                                                                                  \
     (ctx)->launches++;                                                                  \
-    loamb::g_total_launches++;                                                          \
+    loamb::g_total_launches.fetch_add(1, std::memory_order_relaxed);                                                      \
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess) return loamb::fail_cuda(ctx, _e, "kernel launch", __LINE__); \
   } while (0)

@@ -285,7 +285,8 @@ bool BasicLaserMapping::process(Time const& laserOdometryTime) {
   // full-resolution cloud into the map frame (upstream :536-595)
   loam_b200_pose optimised;
   b200::fillPose(_transformTobeMapped, optimised);
-  _gpu->check(loam_b200_map_end_sweep(_gpu->get(), &optimised), "loam_b200_map_end_sweep");
+  // issued by the context's helper thread: nothing below depends on it, the next call on the context joins it
+  _gpu->check(loam_b200_map_end_sweep_async(_gpu->get(), &optimised), "loam_b200_map_end_sweep_async");
   _c[M_FULL].deviceWritten((int)_c[M_FULL].size());
   const double tp3 = now();
 

@@ -18,11 +18,17 @@
 using namespace loamb;
 
 namespace loamb {
-long long g_total_launches = 0;
+std::atomic<long long> g_total_launches{0};  // helper threads launch too
 }
 
-#define CHECK_CTX(c) \
-  if (!(c)) return LOAM_B200_ERR_ARG
+// every entry point first waits for the context's helper thread (ctx.cuh: AsyncWorker) and reports its status
+static int async_join(loam_b200_ctx* c);
+#define CHECK_CTX(c)                      \
+  if (!(c)) return LOAM_B200_ERR_ARG;     \
+  {                                       \
+    const int _rcj = async_join(c);       \
+    if (_rcj) return _rcj;                \
+  }
 
 namespace {
 
@@ -300,9 +306,114 @@ int fetch_normal_eq(loam_b200_ctx* c, loam_b200_normal_eq* out) {
   return LOAM_B200_OK;
 }
 
+// Small integer results (stage counts) take the same route as the normal equations: one 32-thread kernel behind the
+// producers copies them into mapped host memory and posts a sequence number; the host spins (no memcpy + synchronise).
+__global__ void post_ints_kernel(const int* __restrict__ src, int n, int* host, int seq) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) host[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(host + 511) = seq;
+  }
+}
+
+int fetch_ints(loam_b200_ctx* c, const int* d_src, int n, int* h_dst) {
+  if (n > 500 || getenv_no_mailbox() || c->int_mailbox.reserve(512) != cudaSuccess) {
+    cudaGetLastError();
+    LB_CUDA(c, c->hcount.reserve(512));
+    LB_CUDA(c, cudaMemcpyAsync(c->hcount.p, d_src, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h_dst != c->hcount.p) memcpy(h_dst, c->hcount.p, (size_t)n * sizeof(int));
+    return LOAM_B200_OK;
+  }
+  c->int_seq = c->int_seq == 0x7fffffff ? 1 : c->int_seq + 1;
+  post_ints_kernel<<<1, 32, 0, c->stream>>>(d_src, n, c->int_mailbox.p, c->int_seq);
+  LB_LAUNCH_CHECK(c);
+  volatile int* seq = reinterpret_cast<volatile int*>(c->int_mailbox.p + 511);
+  const auto t0 = std::chrono::steady_clock::now();
+  long long spins = 0;
+  while (*seq != c->int_seq) {
+    if ((++spins & 0xfff) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) {
+      LB_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (*seq != c->int_seq) return LOAM_B200_ERR_CUDA;
+      break;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  for (int i = 0; i < n; i++) h_dst[i] = reinterpret_cast<volatile int*>(c->int_mailbox.p)[i];
+  return LOAM_B200_OK;
+}
+
 }  // namespace
 
 #include "comm.inc"
+
+static thread_local bool tl_in_worker = false;
+
+static int async_join(loam_b200_ctx* c) {
+  AsyncWorker* w = c->worker;
+  if (!w || tl_in_worker) return LOAM_B200_OK;
+  std::unique_lock<std::mutex> lk(w->m);
+  w->cv.wait(lk, [w] { return !w->busy && !w->has_job; });
+  const int rc = w->last_rc;
+  w->last_rc = LOAM_B200_OK;
+  return rc;
+}
+
+static void async_worker_main(loam_b200_ctx* c) {
+  cudaSetDevice(c->device);
+  tl_in_worker = true;
+  AsyncWorker* w = c->worker;
+  for (;;) {
+    std::function<int()> job;
+    {
+      std::unique_lock<std::mutex> lk(w->m);
+      w->cv.wait(lk, [w] { return w->has_job || w->stop; });
+      if (w->stop && !w->has_job) return;
+      job = std::move(w->job);
+      w->has_job = false;
+      w->busy = true;
+    }
+    const int rc = job();
+    {
+      std::lock_guard<std::mutex> lk(w->m);
+      w->busy = false;
+      if (rc) w->last_rc = rc;
+    }
+    w->cv.notify_all();
+  }
+}
+
+// post a job; the previous one has been joined by the caller's CHECK_CTX
+static int async_post(loam_b200_ctx* c, std::function<int()> job) {
+  if (!c->worker) {
+    c->worker = new AsyncWorker();
+    c->worker->th = std::thread(async_worker_main, c);
+  }
+  AsyncWorker* w = c->worker;
+  {
+    std::lock_guard<std::mutex> lk(w->m);
+    w->job = std::move(job);
+    w->has_job = true;
+  }
+  w->cv.notify_all();
+  return LOAM_B200_OK;
+}
+
+static void async_shutdown(loam_b200_ctx* c) {
+  AsyncWorker* w = c->worker;
+  if (!w) return;
+  {
+    std::unique_lock<std::mutex> lk(w->m);
+    w->cv.wait(lk, [w] { return !w->busy && !w->has_job; });
+    w->stop = true;
+  }
+  w->cv.notify_all();
+  w->th.join();
+  delete w;
+  c->worker = nullptr;
+}
 
 extern "C" {
 
@@ -390,7 +501,8 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
 }
 
 int loam_b200_destroy(loam_b200_ctx* c) {
-  CHECK_CTX(c);
+  if (!c) return LOAM_B200_ERR_ARG;
+  async_shutdown(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->reg_pts.release(); c->reg_ring_start.release(); c->reg_ring_end.release(); c->reg_picks.release();
@@ -424,7 +536,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
     st.e_state.release(); st.e_keys.release(); st.e_vals.release();
   }
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
-  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->result_mailbox.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -497,8 +609,12 @@ static int run_features(loam_b200_ctx* c, const float4* d_pts, int n, const int3
   LB_CUDA(c, c->cloud[LOAM_B200_C_REG_LESS_SHARP].reserve((size_t)n_rings * fp.cap_less + 1));
   LB_CUDA(c, c->cloud[LOAM_B200_C_REG_FLAT].reserve((size_t)n_rings * fp.cap_flat + 1));
   LB_CUDA(c, c->cloud[LOAM_B200_C_REG_LESS_FLAT].reserve(n));
-  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_start.p, ring_start, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
-  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_end.p, ring_end, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
+  // ring table through a context-owned pinned buffer (the previous use finished: every run ends with a result fetch)
+  LB_CUDA(c, c->ring_table_host.reserve(2 * (size_t)n_rings));
+  memcpy(c->ring_table_host.p, ring_start, (size_t)n_rings * 4);
+  memcpy(c->ring_table_host.p + n_rings, ring_end, (size_t)n_rings * 4);
+  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_start.p, c->ring_table_host.p, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
+  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_end.p, c->ring_table_host.p + n_rings, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
 
   prof_begin(c, LOAM_B200_K_FEATURES);
   feature_ring_kernel<<<n_rings, FEAT_THREADS, smem, c->stream>>>(d_pts, c->reg_ring_start.p, c->reg_ring_end.p, fp,
@@ -514,8 +630,10 @@ static int run_features(loam_b200_ctx* c, const float4* d_pts, int n, const int3
       c->cloud[LOAM_B200_C_REG_LESS_FLAT].p, totals);
   LB_LAUNCH_CHECK(c);
   prof_end(c);
-  LB_CUDA(c, cudaMemcpyAsync(c->reg_totals, totals, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  {
+    const int rcf = fetch_ints(c, totals, 4, c->reg_totals);
+    if (rcf) return rcf;
+  }
   c->cloud_n[LOAM_B200_C_REG_SHARP] = c->reg_totals[0];
   c->cloud_n[LOAM_B200_C_REG_LESS_SHARP] = c->reg_totals[1];
   c->cloud_n[LOAM_B200_C_REG_FLAT] = c->reg_totals[2];
