@@ -214,6 +214,8 @@ int loam_b200_cloud_size(loam_b200_ctx* ctx, int slot);
 int loam_b200_cloud_swap(loam_b200_ctx* ctx, int slot_a, int slot_b);
 /* copy a cloud between slots, possibly of two different contexts on the same device (stream-ordered, no host hop) */
 int loam_b200_cloud_copy(loam_b200_ctx* dst_ctx, int dst_slot, loam_b200_ctx* src_ctx, int src_slot);
+/* count copies dst[i] <- src[i] with one stream hand-shake per direction */
+int loam_b200_cloud_copy_many(loam_b200_ctx* dst_ctx, const int* dst, loam_b200_ctx* src_ctx, const int* src, int count);
 
 /* Ring-binning front end = MultiScanRegistration::process up to the processScanlines call
  * (MultiScanRegistration.cpp:160-238, mapper :44-67): n unordered sensor-frame points (xyz, 3 floats each, arrival order;
@@ -264,6 +266,9 @@ int loam_b200_map_end_sweep(loam_b200_ctx* ctx, const loam_b200_pose* optimised)
 int loam_b200_map_end_sweep_async(loam_b200_ctx* ctx, const loam_b200_pose* optimised);
 /* createDownsizedMap (:242-264): VoxelGrid(leaf) over the corner + surface points of the surround cubes -> MAP_SURROUND_DS */
 int loam_b200_map_surround(loam_b200_ctx* ctx, const int cen[3], const int32_t* surround_cubes, int n, float leaf);
+/* Same on an auxiliary context with its own stream and helper thread: returns at once, ordered behind the pending
+ * end-of-sweep update; loam_b200_cloud_size / _download of MAP_SURROUND_DS wait for it. */
+int loam_b200_map_surround_async(loam_b200_ctx* ctx, const int cen[3], const int32_t* surround_cubes, int n, float leaf);
 /* Debug / test switch: loam_b200_map_begin_sweep additionally materialises the reference's laserCloud*FromMap
  * (BasicLaserMapping.cpp:503-509: the map points of the cubes in view) in the *_FROM_MAP cloud slots.  Off by default:
  * the persistent cell-sorted map never needs that copy, only its size (sizes_out[0..1]). */

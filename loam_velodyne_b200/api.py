@@ -119,6 +119,7 @@ def lib():
         "loam_b200_cloud_download": (C.c_int, [vp, C.c_int, _F, C.c_int, _I]),
         "loam_b200_cloud_size": (C.c_int, [vp, C.c_int]),
         "loam_b200_cloud_swap": (C.c_int, [vp, C.c_int, C.c_int]),
+        "loam_b200_cloud_copy_many": (C.c_int, [vp, _I, vp, _I, C.c_int]),
         "loam_b200_cloud_copy": (C.c_int, [vp, C.c_int, vp, C.c_int]),
         "loam_b200_reg_bin": (C.c_int, [vp, _F, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _I, _I]),
         "loam_b200_reg_run": (C.c_int, [vp, _I, _I, C.c_int, C.POINTER(RegParams), _I]),
@@ -133,6 +134,7 @@ def lib():
         "loam_b200_map_end_sweep": (C.c_int, [vp, C.POINTER(Pose)]),
         "loam_b200_map_end_sweep_async": (C.c_int, [vp, C.POINTER(Pose)]),
         "loam_b200_map_surround": (C.c_int, [vp, _I, _I, C.c_int, C.c_float]),
+        "loam_b200_map_surround_async": (C.c_int, [vp, _I, _I, C.c_int, C.c_float]),
         "loam_b200_map_debug_from_map": (C.c_int, [vp, C.c_int]),
         "loam_b200_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),

@@ -145,6 +145,8 @@ struct loam_b200_ctx {
   int device = 0;
   int sm_count = 0;
   AsyncWorker* worker = nullptr;
+  loam_b200_ctx* aux = nullptr;       // auxiliary context of the asynchronous surround cloud (stages.inc)
+  bool surround_in_aux = false;
   bool cluster_ok = false;  // single-launch cluster kernels of clustersort.cuh usable (LOAM_B200_NO_CLUSTER=1 disables)
   cudaStream_t stream = nullptr;
   std::string last_error;

@@ -66,13 +66,16 @@ void BasicLaserMapping::retainFromMapClouds(bool on) {
 
 void BasicLaserMapping::adopt(BasicLaserOdometry& odom) {
   static const int to[3] = {M_CORNER_LAST, M_SURF_LAST, M_FULL};
+  int dstSlots[3], srcSlots[3];
   for (int i = 0; i < 3; i++) {
     b200::DualCloud& src = odom.deviceCloud(i);
     src.ensureDevice();
-    _gpu->check(loam_b200_cloud_copy(_gpu->get(), _c[to[i]].slot(), odom.deviceContext()->get(), src.slot()),
-                "loam_b200_cloud_copy");
-    _c[to[i]].deviceWritten((int)src.size());
+    dstSlots[i] = _c[to[i]].slot();
+    srcSlots[i] = src.slot();
   }
+  _gpu->check(loam_b200_cloud_copy_many(_gpu->get(), dstSlots, odom.deviceContext()->get(), srcSlots, 3),
+              "loam_b200_cloud_copy_many");
+  for (int i = 0; i < 3; i++) _c[to[i]].deviceWritten((int)odom.deviceCloud(i).size());
   updateOdometry(odom.transformSum());
 }
 
@@ -177,9 +180,12 @@ bool BasicLaserMapping::createDownsizedMap() {
   // _downSizeFilterMap is configurable but never used there either)
   std::vector<int32_t> cubes(_laserCloudSurroundInd.begin(), _laserCloudSurroundInd.end());
   const int cen[3] = {_laserCloudCenWidth, _laserCloudCenHeight, _laserCloudCenDepth};
-  _gpu->check(loam_b200_map_surround(_gpu->get(), cen, cubes.data(), (int)cubes.size(), b200::leafOf(_downSizeFilterCorner)),
-              "loam_b200_map_surround");
-  _c[M_SURROUND_DS].deviceWritten(loam_b200_cloud_size(_gpu->get(), LOAM_B200_C_MAP_SURROUND_DS));
+  // computed asynchronously on an auxiliary context (it is a visualisation product and costs half a sweep); the
+  // accessor laserCloudSurroundDS() waits for it
+  _gpu->check(loam_b200_map_surround_async(_gpu->get(), cen, cubes.data(), (int)cubes.size(),
+                                           b200::leafOf(_downSizeFilterCorner)),
+              "loam_b200_map_surround_async");
+  _c[M_SURROUND_DS].deviceWrittenLazy();
   return true;
 }
 

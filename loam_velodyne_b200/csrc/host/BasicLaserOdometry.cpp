@@ -2,6 +2,10 @@
 // (src/lib/BasicLaserOdometry.cpp:196-666); per-point work happens in loam_b200_odom_iterate.
 #include "loam_velodyne/BasicLaserOdometry.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cassert>
 #include <cmath>
 
@@ -57,13 +61,16 @@ void BasicLaserOdometry::adopt(BasicScanRegistration& reg) {
   // reg clouds: 0 full, 1 sharp, 2 less sharp, 3 flat, 4 less flat
   static const int from[5] = {1, 2, 3, 4, 0};
   static const int to[5] = {C_SHARP, C_LESS_SHARP, C_FLAT, C_LESS_FLAT, C_FULL};
+  int dstSlots[5], srcSlots[5];
   for (int i = 0; i < 5; i++) {
     b200::DualCloud& src = reg.deviceCloud(from[i]);
     src.ensureDevice();
-    _gpu->check(loam_b200_cloud_copy(_gpu->get(), _c[to[i]].slot(), reg.deviceContext()->get(), src.slot()),
-                "loam_b200_cloud_copy");
-    _c[to[i]].deviceWritten((int)src.size());
+    dstSlots[i] = _c[to[i]].slot();
+    srcSlots[i] = src.slot();
   }
+  _gpu->check(loam_b200_cloud_copy_many(_gpu->get(), dstSlots, reg.deviceContext()->get(), srcSlots, 5),
+              "loam_b200_cloud_copy_many");
+  for (int i = 0; i < 5; i++) _c[to[i]].deviceWritten((int)reg.deviceCloud(from[i]).size());
   updateIMU(reg.imuTransform());
 }
 
@@ -139,6 +146,10 @@ void BasicLaserOdometry::process() {
   _frameCount++;
   _transform.pos -= _imuVeloFromStart * _scanPeriod;
   _lastIterations = 0;
+  static const bool trace = std::getenv("LOAM_B200_TRACE") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tr0 = tnow();
+  double tr1 = tr0, tr2 = tr0;
 
   size_t lastCornerCloudSize = _c[C_LAST_CORNER].size();
   size_t lastSurfaceCloudSize = _c[C_LAST_SURF].size();
@@ -148,6 +159,7 @@ void BasicLaserOdometry::process() {
     _c[C_SHARP].ensureDevice();
     _c[C_FLAT].ensureDevice();
     _gpu->check(loam_b200_odom_prepare(_gpu->get()), "loam_b200_odom_prepare");
+    tr1 = tnow();
 
     if (b200::deviceResidentLoops()) {
       // optional: the whole iteration loop (:246-622) on the device (loam_b200_odom_solve, csrc/lmstep.cuh)
@@ -196,6 +208,7 @@ void BasicLaserOdometry::process() {
     }
   }
 
+  tr2 = tnow();
   Angle rx, ry, rz;
   accumulateRotation(_transformSum.rot_x, _transformSum.rot_y, _transformSum.rot_z, -_transform.rot_x,
                      -_transform.rot_y.rad() * 1.05, -_transform.rot_z, rx, ry, rz);
@@ -228,7 +241,11 @@ void BasicLaserOdometry::process() {
 
   lastCornerCloudSize = _c[C_LAST_CORNER].size();
   lastSurfaceCloudSize = _c[C_LAST_SURF].size();
+  const double tr3 = tnow();
   if (lastCornerCloudSize > 10 && lastSurfaceCloudSize > 100) uploadLast();
+  if (trace)
+    fprintf(stderr, "[odom] prepare %.0f us, loop %.0f us (%zu it), to-end %.0f us, rebuild issue %.0f us\n", tr1 - tr0, tr2 - tr1,
+            _lastIterations, tr3 - tr2, tnow() - tr3);
 }
 
 // Euler-angle composition helpers: closed-form products of ZXY rotations, as published with LOAM

@@ -48,8 +48,17 @@ void DualCloud::ensureDevice() {
   devN_ = (int)host_->points.size();
 }
 
+int DualCloud::deviceCount() const {
+  if (devN_ < 0) {  // produced asynchronously (deviceWrittenLazy): the context knows the size once the producer is done
+    const int n = loam_b200_cloud_size(ctx_->get(), slot_);
+    const_cast<DualCloud*>(this)->devN_ = n < 0 ? 0 : n;
+  }
+  return devN_;
+}
+
 void DualCloud::materialise() {
   if (hostValid_) return;
+  deviceCount();
   buf_.resize((std::size_t)devN_ * 4 + 4);
   int n = 0;
   ctx_->check(loam_b200_cloud_download(ctx_->get(), slot_, buf_.data(), devN_, &n), "loam_b200_cloud_download");

@@ -54,8 +54,11 @@ class DualCloud {
   const Cloud::Ptr& hostPtr() const { const_cast<DualCloud*>(this)->materialise(); return host_; }
   const Cloud& host() const { const_cast<DualCloud*>(this)->materialise(); return *host_; }
 
-  std::size_t size() const { return hostValid_ ? host_->points.size() : (std::size_t)devN_; }
+  std::size_t size() const { return hostValid_ ? host_->points.size() : (std::size_t)deviceCount(); }
   void deviceWritten(int n) { devValid_ = true; hostValid_ = false; devN_ = n; }
+  // the device copy is being produced asynchronously: its size is asked from the context on first use
+  void deviceWrittenLazy() { devValid_ = true; hostValid_ = false; devN_ = -1; }
+  int deviceCount() const;
   void ensureDevice();   // upload when the device copy is stale
   void materialise();    // download when the host copy is stale
   void clear() { host_->clear(); hostValid_ = true; devValid_ = false; devN_ = 0; }

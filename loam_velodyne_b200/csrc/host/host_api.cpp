@@ -248,14 +248,23 @@ static int pipeline_sweep_impl(PipeH* h, const float* pts, const void* d_pts, co
   // here a device-to-device hand-off
   auto& o = h->odom.o;
   o.adopt(h->reg.r);
+  const double t1b = now();
   o.process();
   const double t2 = now();
   o.transformLaserCloudToEnd();  // LaserOdometry::publishResult, LaserOdometry.cpp:326 upstream
   const double t3 = now();
   auto& m = h->map.m;
   m.adopt(o);                    // LaserOdometry::publishResult -> LaserMapping::*Handler upstream
+  const double t3b = now();
   const int ok = m.process(loam::Time()) ? 1 : 0;
   const double t4 = now();
+  static const bool trace = std::getenv("LOAM_B200_TRACE") != nullptr;
+  if (trace) {
+    const double* ph = m.lastPhaseSeconds();
+    fprintf(stderr, "[pipe] reg %.0f | adopt %.0f odom %.0f | to-end %.0f | adopt %.0f map %.0f (begin %.0f lm %.0f end %.0f surround %.0f) us\n",
+            (t1 - t0) * 1e6, (t1b - t1) * 1e6, (t2 - t1b) * 1e6, (t3 - t2) * 1e6, (t3b - t3) * 1e6, (t4 - t3b) * 1e6, ph[0] * 1e6,
+            ph[1] * 1e6, ph[2] * 1e6, ph[3] * 1e6);
+  }
   twist6(o.transformSum(), odom_sum6);
   twist6(m.transformAftMapped(), map_aft6);
   if (st) { st[0] = t1 - t0; st[1] = t2 - t1; st[2] = t3 - t2; st[3] = t4 - t3; st[4] = t4 - t0; }

@@ -502,6 +502,10 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
 
 int loam_b200_destroy(loam_b200_ctx* c) {
   if (!c) return LOAM_B200_ERR_ARG;
+  if (c->aux) {
+    loam_b200_destroy(c->aux);
+    c->aux = nullptr;
+  }
   async_shutdown(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
