@@ -207,6 +207,7 @@ struct loam_b200_ctx {
   loamb::DevBuf<int> od_ind;   // (n_sharp + n_flat) x 3 persisted correspondence indices
   bool od_last_set = false;
   bool od_rebuild_pending = false;
+  loamb::DevBuf<int> od_ring_off[2];  // ring offset tables of the last corner / surface clouds (odometry_lm.cuh)
 
   // device-resident clouds of the stage API
   loamb::DevBuf<float4> cloud[LOAM_B200_NUM_CLOUDS];

@@ -173,6 +173,17 @@ int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m, con
   return LOAM_B200_OK;
 }
 
+// ring offset table of an odometry last-sweep cloud (odometry_lm.cuh: ring_offsets_kernel)
+int odom_ring_offsets(loam_b200_ctx* c, int kind, const float4* d_pts, int m) {
+  LB_CUDA(c, c->od_ring_off[kind].reserve(RING_OFF_WORDS));
+  LB_CUDA(c, cudaMemsetAsync(c->od_ring_off[kind].p, 0, RING_OFF_WORDS * sizeof(int), c->stream));
+  if (m > 0) {
+    ring_offsets_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, m, c->od_ring_off[kind].p);
+    LB_LAUNCH_CHECK(c);
+  }
+  return LOAM_B200_OK;
+}
+
 // build the BVH of tree t from t.pts (device, m points)
 int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
   t.m = m;
@@ -540,7 +551,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
     st.e_state.release(); st.e_keys.release(); st.e_vals.release();
   }
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
-  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->od_ring_off[1].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -699,6 +710,7 @@ int loam_b200_tree_build(loam_b200_ctx* c, int slot, const float* pts, int m) {
   if (rc) return rc;
   prof_begin(c, LOAM_B200_K_TREE_BUILD);
   rc = tree_build_device(c, t, m);
+  if (rc == LOAM_B200_OK && slot < LOAM_B200_TREE_MAP_CORNER) rc = odom_ring_offsets(c, slot, t.points(), m);
   // the scan-to-map kernels search the two map slots through the 1 m grid
   if (rc == LOAM_B200_OK && slot >= LOAM_B200_TREE_MAP_CORNER) {
     rc = grid_build_device(c, c->grid[slot - LOAM_B200_TREE_MAP_CORNER], t.points(), m);
@@ -905,7 +917,8 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
   if (pose->iter % 5 == 0) {
     const int warps = nsh + nfl;
     odom_search_kernel<false><<<blocks_for((long long)warps * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
-        view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, a, c->od_ind.p);
+        view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, a, c->od_ind.p, nullptr,
+        c->od_ring_off[0].p, c->od_ring_off[1].p);
     LB_LAUNCH_CHECK(c);
   }
   ResultMailbox mb{nullptr, 0};
@@ -978,7 +991,8 @@ int loam_b200_odom_solve(loam_b200_ctx* c, const float rot[3], const float pos[3
     for (; it < chunk_end; it++) {
       if (it % 5 == 0) {
         odom_search_kernel<true><<<blocks_for((long long)(nsh + nfl) * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
-            view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, unused, c->od_ind.p, st);
+            view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, unused, c->od_ind.p, st,
+            c->od_ring_off[0].p, c->od_ring_off[1].p);
         LB_LAUNCH_CHECK(c);
       }
       odom_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p,

@@ -188,6 +188,25 @@ __device__ __forceinline__ float sqdiff3(const float4& a, float bx, float by, fl
   return dx * dx + dy * dy + dz * dz;
 }
 
+// ---- ring offsets of a last-sweep cloud: off[r] = first index whose ring id (int(intensity)) is >= r, r = 0 .. 256;
+// off[257] != 0 flags a cloud that is not ring-ordered or has ring ids outside [0, 255].  For a ring-ordered cloud the
+// reference's scan loops with their ring `break` (:262-276, :281-296) visit exactly an index range given by two of
+// these offsets, which removes the only dependency between the steps of the scan.
+constexpr int RING_OFF_WORDS = 258;
+__global__ void ring_offsets_kernel(const float4* __restrict__ last, int n, int* __restrict__ off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = (int)last[i].w;
+  const int prev = i > 0 ? (int)last[i - 1].w : -1;
+  if (r < 0 || r > 255 || prev > r) {
+    off[257] = 1;
+    return;
+  }
+  for (int rr = max(prev, -1) + 1; rr <= r; rr++) off[rr] = i;
+  if (i == n - 1)
+    for (int rr = r + 1; rr <= 256; rr++) off[rr] = n;
+}
+
 // ---- correspondence search, every 5th iteration (BasicLaserOdometry.cpp:250-302, :368-435): one WARP per feature
 // point.  Lane 0 walks the BVH for the closest point (d^2 < 25 gate); then the whole warp scans the ring-ordered last
 // cloud forwards and backwards 32 candidates at a time.  The reference's sequential loops are reproduced exactly:
@@ -220,7 +239,8 @@ template <bool DEVLOOP>
 __global__ void __launch_bounds__(LM_THREADS)
 odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
                    const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
-                   OdomIterArgs a_param, int* __restrict__ ind, const OdomLmState* __restrict__ lm = nullptr) {
+                   OdomIterArgs a_param, int* __restrict__ ind, const OdomLmState* __restrict__ lm = nullptr,
+                   const int* __restrict__ ring_off_corner = nullptr, const int* __restrict__ ring_off_surf = nullptr) {
   __shared__ OdomIterArgs s_args;
   if (DEVLOOP) {
     if (lm->h.done) return;
@@ -250,6 +270,38 @@ odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
     const int scan = (int)last[i1].w;
     ScanBest b2{25.f, 0x7fffffff, -1}, b3{25.f, 0x7fffffff, -1};
     int ord = 0;
+    const int* ring_off = is_corner ? ring_off_corner : ring_off_surf;
+    if (ring_off && ring_off[257] == 0 && scan >= 0 && scan <= 252) {
+      // ring-ordered cloud: both scans are plain index ranges (no `break` to resolve between steps, the loads pipeline).
+      // Visiting order of the serial loops = forward ascending, then backward descending: `ord` encodes it for ties.
+      const int fend = min(min(is_corner ? n_sharp : n_flat, n_last), ring_off[scan + 3]);  // ring <= scan + 2.5
+#pragma unroll 4
+      for (int j = i1 + 1 + lane; j < fend; j += 32) {
+        const float4 p = last[j];
+        const int r = (int)p.w;
+        const float d = sqdiff3(p, sx, sy, sz);
+        if (is_corner) {
+          if (r > scan) scan_best_min(b2, d, j - (i1 + 1), j);
+        } else {
+          if (r <= scan) scan_best_min(b2, d, j - (i1 + 1), j);
+          else scan_best_min(b3, d, j - (i1 + 1), j);
+        }
+      }
+      const int lo = ring_off[max(scan - 2, 0)];  // ring >= scan - 2.5
+#pragma unroll 4
+      for (int j = i1 - 1 - lane; j >= lo; j -= 32) {
+        const float4 p = last[j];
+        const int r = (int)p.w;
+        const float d = sqdiff3(p, sx, sy, sz);
+        const int o2 = 0x20000000 + (i1 - 1 - j);
+        if (is_corner) {
+          if (r < scan) scan_best_min(b2, d, o2, j);
+        } else {
+          if (r >= scan) scan_best_min(b2, d, o2, j);
+          else scan_best_min(b3, d, o2, j);
+        }
+      }
+    } else {
     // Both scans visit 32 x SCAN_UNROLL candidates per step: the loads of a step are independent (issued together),
     // the ring `break` is then resolved chunk by chunk in visiting order, so the result is that of the serial loop.
     // (One chunk per step made the kernel a chain of ~60 dependent global loads per direction on the surface cloud:
@@ -319,6 +371,7 @@ odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
       }
       ord += 32 * SCAN_UNROLL;
       if (stop_all) break;
+    }
     }
     scan_best_warp(b2);
     i2 = b2.idx;
