@@ -44,6 +44,7 @@ __device__ __forceinline__ void mark_as_picked_warp(const float4* P, int8_t* pic
   const unsigned bm = __ballot_sync(0xffffffffu, bgap) >> 16;
   const int fext = fm ? (__ffs(fm) - 1) - 1 : cr;  // lanes are 1-based: first gap at lane g -> extent g-1
   const int bext = bm ? (__ffs(bm) - 1) - 1 : cr;
+  __syncwarp();  // every lane's read of picked[] for this pick (the caller's eligibility test) precedes the marks
   if (lane == 0) picked[li] = 1;
   if (lane >= 1 && lane <= fext) picked[li + lane] = 1;
   if (bl >= 1 && bl <= bext) picked[li - bl] = 1;
