@@ -53,7 +53,24 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.t = None
 
-    def _run(self):
+    def _run_nvml(self):
+        """NVML polling (a few ms per sample): the timed region of this bench lasts tens of milliseconds."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self._stop.is_set():
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for nm, b in bits.items():
+                if r & b:
+                    self.reasons.add(nm)
+            self._stop.wait(0.004)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -70,6 +87,12 @@ class ClockSampler:
             except Exception:
                 pass
             self._stop.wait(0.2)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def start(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -263,9 +286,17 @@ def kernel_roofline(args, api, corner, surf, sweep, pipe):
     # here (three private contexts); the kernel ABI context exposes its own launch counter instead
     launches_per_sweep = estimate_launches(api, pipe)
     ctx.close()
+    # DRAM bytes per launch from the committed ncu --set full capture of this kernel on this workload (a number printed
+    # under a profiler is never measured here); only quoted for the workload it was captured on
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_map_iterate_traffic.json")
+    if args.workload == "hdl64_1m" and os.path.exists(tp):
+        with open(tp) as fh:
+            tj = json.load(fh)
+        traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj["source"]
     return ({"bound": "hbm", "kernel": "map_iterate_kernel (fused fixed-radius 5-NN + line/plane fit + Jacobian + 6x6 reduction)",
              "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-             "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes),
+             "traffic": traffic, "traffic_source": traffic_src, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes),
              "avg_launch_us": round(dur_s * 1e6, 2), "queries": int(nq), "table_probes_per_query": round(probes / max(nq, 1), 2),
              "candidate_points_per_query": round(cands / max(nq, 1), 2),
              "note": "1M-pt map + nodes fit in the 126 MB L2, so DRAM traffic is structurally far below the algorithmic bytes"},
@@ -334,8 +365,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="hdl64_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sweeps", type=int, default=12, help="sweeps timed for the cpu_baseline sample")
