@@ -106,6 +106,48 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def pin_to_gpu_cores(local_rank, world):
+    """Bind this rank (and the library's helper threads it will spawn) to CPU cores on its GPU's NUMA node, split evenly
+    between the ranks whose GPUs share that node: the pipeline hand-shakes with the GPU dozens of times per sweep through
+    mapped host memory, so cross-socket latency and ranks stacked on the same cores show up directly in sweeps/s.
+    Returns a short description for the JSON line (None when the platform offers no affinity information)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+
+        def cpus_of(i):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words)
+            return frozenset(c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1)
+
+        def first_sibling(c):  # one hardware thread per core: the main thread spins, a sibling would starve
+            try:
+                with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as fh:
+                    txt = fh.read().strip()
+                sib = []
+                for part in txt.split(","):
+                    lo, _, hi = part.partition("-")
+                    sib += list(range(int(lo), int(hi or lo) + 1))
+                return c == min(sib)
+            except Exception:
+                return True
+
+        mine = cpus_of(local_rank)
+        allowed = sorted(mine & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        allowed = [c for c in allowed if first_sibling(c)] or allowed
+        peers = [r for r in range(world) if cpus_of(r) == mine] if world > 1 else [local_rank]
+        k, idx = max(len(peers), 1), (peers.index(local_rank) if local_rank in peers else 0)
+        per = max(len(allowed) // k, 1)
+        chunk = allowed[idx * per:(idx + 1) * per] or allowed
+        if len(chunk) < 4:  # main thread spins on the mailbox, two helper threads issue work: do not squeeze them
+            return None
+        os.sched_setaffinity(0, chunk)
+        return f"{len(chunk)} cores of the GPU's NUMA node (cpus {chunk[0]}-{chunk[-1]})"
+    except Exception:
+        return None
+
+
 def make_workload(name, n_sweeps, rank=0):
     from loam_velodyne_b200 import synth
     lidar_name, m, _ = WORKLOADS[name]
@@ -135,6 +177,7 @@ def run_cuda(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     api.set_device(local_rank)
+    pinned_cores = pin_to_gpu_cores(local_rank, world)
     n_total = args.warmup + args.steps
     sharded = world > 1 and args.mode == "sharded"
     lidar, corner, surf, sweeps = make_workload(args.workload, n_total, 0 if sharded else rank)
@@ -225,7 +268,7 @@ def run_cuda(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * el_dev / args.steps, 3),
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": n_pts,
+            "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": n_pts, "cpu_binding": pinned_cores,
                        "map_points": int(corner.shape[0] + surf.shape[0]),
                        "mode": ("sharded: one stream, query slices + NCCL all-reduce of AtA/AtB per LM iteration" if sharded
                                 else "replicas: one independent sweep stream and map per GPU, no data-path collective"
