@@ -1,14 +1,8 @@
-// Device-resident surrounding map: the reference keeps 21 x 11 x 21 cubes of 50 m as
-// separate host clouds, concatenates the cubes in the field of view every sweep, inserts the new stack points and
-// voxel-filters every visible cube (BasicLaserMapping.cpp:300-509, 536-593).  Here each map kind (corner / surface)
-// is ONE flat point pool in HBM; a point's cube is a pure function of its position and the grid centre
-// (:540-553), so rolling the grid is just a change of three integers, "concatenate the valid cubes" is a stream
-// compaction and "filter every valid cube" is one sort by (cube rank, voxel z, y, x) + run means:
-//   classify  -> per point: rank of its cube in this sweep's valid list, KEEP (cube not visible), or DROP (left grid)
-//   compact   -> from-map cloud (rank < n_valid) for the k-NN BVH
-//   filter    -> key = rank<<24 | vz<<16 | vy<<8 | vx over (valid old points + inserted points) -> radix sort ->
-//                centroid per run (pcl::VoxelGrid grouping: absolute lattice cell floor(x / leaf) per cube, output in
-//                ascending voxel index per cube) ; pool' = filtered ++ kept
+// Cube bookkeeping shared by the map code: the reference keeps 21 x 11 x 21 cubes of 50 m as separate host clouds
+// (BasicLaserMapping.cpp:300-509, 536-593); here a point's cube is a pure function of its position and the grid centre
+// (:540-553).  This header holds the cube index arithmetic, the cube classification + stream compaction used by the
+// surround cloud (createDownsizedMap) and by the from-map debug clouds, and the stack round-trip transform.  The map
+// itself (persistent, cell-sorted, incrementally maintained) lives in mapstore.cuh.
 #pragma once
 
 #include "lbvh.cuh"
@@ -105,46 +99,12 @@ __global__ void compact_scatter_kernel(const float4* __restrict__ src, const uns
   if (dst_cls) dst_cls[d] = cls[i];
 }
 
-// voxel key inside a valid cube: rank << 24 | vz << 16 | vy << 8 | vx, voxel coordinates relative to a base half a
-// metre below the cube's lower corner so they stay within 8 bits (<= 253 cells at the 0.2 m leaf)
-__global__ void cube_voxel_key_kernel(const float4* __restrict__ p, const unsigned char* __restrict__ cls, int n,
-                                      CubeGrid g, float inv_leaf, unsigned* __restrict__ keys, int* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 q = p[i];
-  int ci, cj, ck;
-  cube_index(q, g, ci, cj, ck);
-  const float bx = 50.0f * (float)(ci - g.cen_w) - 25.5f;
-  const float by = 50.0f * (float)(cj - g.cen_h) - 25.5f;
-  const float bz = 50.0f * (float)(ck - g.cen_d) - 25.5f;
-  const int vx = (int)floorf(q.x * inv_leaf) - (int)floorf(bx * inv_leaf);
-  const int vy = (int)floorf(q.y * inv_leaf) - (int)floorf(by * inv_leaf);
-  const int vz = (int)floorf(q.z * inv_leaf) - (int)floorf(bz * inv_leaf);
-  keys[i] = ((unsigned)cls[i] << 24) | ((unsigned)(vz & 255) << 16) | ((unsigned)(vy & 255) << 8) | (unsigned)(vx & 255);
-  vals[i] = i;
-}
-
 // stack points: pointAssociateToMap with the predicted pose then pointAssociateTobeMapped back into the sensor
 // frame (BasicLaserMapping.cpp:282-292 and :512-516; the round trip is not an identity in fp32 and is reproduced)
-struct ToSensorArgs {
-  float srx, crx, sry, cry, srz, crz;  // of the SAME pose; negated angles flip the sine only (Angle.h:47-53)
-  float tx, ty, tz;
-};
 __global__ void stack_roundtrip_kernel(const float4* __restrict__ in, int n, MapIterArgs a, float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = stack_roundtrip(a, in[i]);
-}
-
-// new map points: pointAssociateToMap(stackDS) with the optimised pose (:536-577)
-__global__ void insert_points_kernel(const float4* __restrict__ stack_ds, int n, MapIterArgs a,
-                                     float4* __restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 q = stack_ds[i];
-  float x, y, z;
-  associate_to_map(a, q, x, y, z);
-  dst[i] = make_float4(x, y, z, q.w);
 }
 
 }  // namespace loamb

@@ -12,18 +12,6 @@ namespace loamb {
 int radix_sort_pairs(loam_b200_ctx* c, int m, int key_bits, unsigned** keys_out = nullptr, int** vals_out = nullptr,
                      const int* n_dev = nullptr);
 
-__global__ void voxel_key_kernel(const float4* __restrict__ p, int n, float inv, int minb0, int minb1, int minb2,
-                                 int div0, int div1, unsigned* __restrict__ keys, int* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 q = p[i];
-  const int i0 = (int)(floorf(q.x * inv) - (float)minb0);
-  const int i1 = (int)(floorf(q.y * inv) - (float)minb1);
-  const int i2 = (int)(floorf(q.z * inv) - (float)minb2);
-  keys[i] = (unsigned)(i0 + i1 * div0 + i2 * div0 * div1);
-  vals[i] = i;
-}
-
 // heads[i] = 1 when sorted key i starts a run; per-block totals for the scan
 constexpr int SCAN_BS = 1024;
 __global__ void __launch_bounds__(SCAN_BS)
@@ -118,12 +106,6 @@ __global__ void voxel_key_meta_kernel(const float4* __restrict__ p, int n, float
   keys[i] = voxel_key_of(p[i], inv, m, i);
 }
 
-__global__ void copy_u32_kernel(const unsigned* __restrict__ src, int* __restrict__ dst) {
-  if (threadIdx.x == 0) *dst = (int)*src;
-}
-
-// Stream-ordered voxel filter without host round trips: d_in (n points, n known on the host) -> d_out (capacity n);
-// the number of occupied voxels is written to *d_count (device memory).
 // defined in loam_b200.cu: the single-launch cluster filter of clustersort.cuh (n <= CS_MAX_N); roundtrip = optional
 // MapIterArgs* of the to-map-and-back transform applied to the input first (d_tmp then receives the transformed cloud)
 int voxel_filter_cluster(loam_b200_ctx* c, const float4* d_in, int n, float leaf, const void* roundtrip, float4* d_tmp,
