@@ -19,6 +19,13 @@ const char* loam_b200_host_last_error(void);
 /* CUDA device used by objects created afterwards (default: $LOAM_B200_DEVICE, else $LOCAL_RANK, else 0) */
 void loam_b200_host_set_device(int device);
 
+/* The 6 x 6 Gauss-Newton step of both loops (BasicLaserOdometry.cpp:559-600, BasicLaserMapping.cpp:867-908) as the
+ * library solves it on host and device (csrc/lmstep.cuh: gn_solve): x = colPivHouseholderQr(AtA).solve(AtB); on the first
+ * iteration eigenvalues of AtA below eigen_threshold switch the degeneracy projection on.  Pure host arithmetic (no GPU):
+ * exposed for the parity tests.  AtA row-major 36 floats; *degenerate_out receives 0 / 1. */
+int loam_b200_host_gn_solve(const float* AtA, const float* AtB, int first_iteration, float eigen_threshold, float* x_out6,
+                            int* degenerate_out);
+
 /* ---- loam::BasicScanRegistration ---- */
 void* loam_b200_scanreg_create(void);
 void loam_b200_scanreg_destroy(void* h);

@@ -151,6 +151,7 @@ def lib():
         "loam_b200_scanreg_create": (vp, []),
         "loam_b200_scanreg_destroy": (None, [vp]),
         "loam_b200_scanreg_configure": (C.c_int, [vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
+        "loam_b200_host_gn_solve": (C.c_int, [_F, _F, C.c_int, C.c_float, _F, _I]),
         "loam_b200_scanreg_process_unordered": (C.c_int, [vp, _F, C.c_int, C.c_float, C.c_float, C.c_int]),
         "loam_b200_scanreg_process": (C.c_int, [vp, _F, _I, C.c_int]),
         "loam_b200_scanreg_cloud_size": (C.c_int, [vp, C.c_int]),
@@ -625,6 +626,18 @@ class Pipeline(_Handle):
                                                              _fp(odom), _fp(aft), st.ctypes.data_as(_D)),
                       "pipeline_sweep_device")
         return bool(ok), odom, aft, st
+
+
+def gn_solve(AtA, AtB, first_iteration=True, eigen_threshold=10.0):
+    """The library's 6 x 6 Gauss-Newton step (host arithmetic, same source as the device loop) -> (x, degenerate)."""
+    L = lib()
+    a = np.ascontiguousarray(AtA, dtype=np.float32).reshape(36)
+    b = np.ascontiguousarray(AtB, dtype=np.float32).reshape(6)
+    x = np.zeros(6, np.float32)
+    deg = C.c_int(0)
+    if L.loam_b200_host_gn_solve(_fp(a), _fp(b), 1 if first_iteration else 0, eigen_threshold, _fp(x), C.byref(deg)) != 0:
+        raise LoamB200Error("gn_solve: invalid arguments")
+    return x, bool(deg.value)
 
 
 def nccl_unique_id() -> bytes:

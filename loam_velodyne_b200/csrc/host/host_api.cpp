@@ -111,6 +111,19 @@ extern "C" {
 const char* loam_b200_host_last_error(void) { return g_err.c_str(); }
 void loam_b200_host_set_device(int device) { loam::b200::setDefaultDevice(device); }
 
+int loam_b200_host_gn_solve(const float* AtA, const float* AtB, int first_iteration, float eigen_threshold, float* x_out6,
+                            int* degenerate_out) {
+  if (!AtA || !AtB || !x_out6) return -1;
+  loam_b200_normal_eq ne;
+  std::memset(&ne, 0, sizeof ne);
+  std::memcpy(ne.AtA, AtA, sizeof ne.AtA);
+  std::memcpy(ne.AtB, AtB, sizeof ne.AtB);
+  loam::b200::GaussNewtonSolver solver;
+  solver.solve(ne, first_iteration != 0, eigen_threshold, x_out6);
+  if (degenerate_out) *degenerate_out = solver.isDegenerate ? 1 : 0;
+  return 0;
+}
+
 void* loam_b200_scanreg_create(void) { return new RegH(); }
 void loam_b200_scanreg_destroy(void* h) { delete (RegH*)h; }
 int loam_b200_scanreg_configure(void* h, float scanPeriod, int nFeatureRegions, int curvatureRegion, int maxCornerSharp,

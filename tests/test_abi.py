@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -67,3 +69,42 @@ def test_ring_ranges_match_reference_convention():
     # BasicScanRegistration.cpp:38-41: (cloudSize_before, cloudSize_after - 1) with 0 when the cloud is still empty
     np.testing.assert_array_equal(s, [0, 0, 5, 5])
     np.testing.assert_array_equal(e, [0, 4, 4, 7])
+
+
+def test_gauss_newton_step_matches_reference_arithmetic(oracle):
+    """gn_solve (csrc/lmstep.cuh, host build): the plain solve is the reference's colPivHouseholderQr bit for bit; the
+    Cholesky shortcut never hides a degenerate direction; the projected step equals V^-1 V2 applied to the plain step."""
+    from loam_velodyne_b200 import api
+    rng = np.random.RandomState(3)
+    for trial in range(20):
+        J = rng.normal(size=(400, 6)).astype(np.float32) * np.array([3, 3, 3, 1, 1, 1], np.float32)
+        r = rng.normal(size=400).astype(np.float32)
+        AtA = (J.T @ J).astype(np.float32)
+        AtB = (J.T @ r).astype(np.float32)
+        x, deg = api.gn_solve(AtA, AtB, True, 10.0)
+        assert not deg
+        np.testing.assert_array_equal(x, oracle.qr_solve6(AtA, AtB))
+    # a scene that does not constrain one direction (e.g. a corridor): eigenvalue below the threshold
+    for thr in (10.0, 100.0):
+        J = rng.normal(size=(400, 6)).astype(np.float32)
+        J[:, 4] = 1e-3 * rng.normal(size=400)  # y translation barely observable
+        AtA = (J.T @ J).astype(np.float32)
+        AtB = (J.T @ rng.normal(size=400)).astype(np.float32)
+        w, V = oracle.eig_sym(AtA)
+        assert w.min() < thr < np.sort(w)[1]
+        x, deg = api.gn_solve(AtA, AtB, True, thr)
+        assert deg
+        x_plain = oracle.qr_solve6(AtA, AtB).astype(np.float64)
+        # reference (:567-590 / :875-898): matV = esolver.eigenvectors() (COLUMNS are eigenvectors, ascending eigenvalues),
+        # matV2 = matV with ROW i zeroed for every leading eigenvalue below the threshold (the upstream code indexes
+        # matV2(i, j) -- rows -- which is what the library reproduces), matP = matV^-1 * matV2, x = matP * x
+        Vc = V.astype(np.float64)
+        V2 = Vc.copy()
+        V2[w < thr, :] = 0.0
+        P = np.linalg.inv(Vc) @ V2
+        np.testing.assert_allclose(x, P @ x_plain, rtol=0, atol=2e-4 * max(1.0, np.abs(x_plain).max()))
+        # later iterations keep projecting with the stored matrix only through the solver object; a fresh non-first
+        # call solves plainly
+        x2, deg2 = api.gn_solve(AtA, AtB, False, thr)
+        assert not deg2
+        np.testing.assert_array_equal(x2, oracle.qr_solve6(AtA, AtB))
