@@ -234,7 +234,8 @@ int loam_b200_reg_indices(loam_b200_ctx* ctx, int which, int32_t* out, int cap, 
 int loam_b200_reg_labels(loam_b200_ctx* ctx, int8_t* out, int n);
 
 /* Odometry stage on the ODOM_* slots: prepare = take ODOM_SHARP + ODOM_FLAT as this sweep's queries;
- * rebuild_last = BVHs over ODOM_LAST_CORNER / ODOM_LAST_SURF (setInputCloud, BasicLaserOdometry.cpp:203-204,662-663);
+ * rebuild_last = BVHs + ring-offset tables over ODOM_LAST_CORNER / ODOM_LAST_SURF (setInputCloud,
+ * BasicLaserOdometry.cpp:203-204,662-663), built asynchronously on side streams;
  * loam_b200_odom_iterate (above) then works on them. */
 int loam_b200_odom_prepare(loam_b200_ctx* ctx);
 int loam_b200_odom_rebuild_last(loam_b200_ctx* ctx);
@@ -242,8 +243,11 @@ int loam_b200_odom_rebuild_last(loam_b200_ctx* ctx);
 int loam_b200_cloud_transform_to_end(loam_b200_ctx* ctx, int slot, const loam_b200_odom_pose* pose);
 int loam_b200_cloud_transform_to_map(loam_b200_ctx* ctx, int slot, const loam_b200_pose* pose);
 
-/* Mapping stage.  The surrounding map is a flat point pool per kind (MAP_CORNER_POOL / MAP_SURF_POOL); the 21x11x21
- * cube grid of the reference is implicit (a point's cube follows from its position and the grid centre). */
+/* Mapping stage.  The surrounding map is one point pool per kind (MAP_CORNER_POOL / MAP_SURF_POOL), kept sorted by 1 m
+ * cell across sweeps together with its cell table (csrc/mapstore.cuh); the 21x11x21 cube grid of the reference is
+ * implicit (a point's cube follows from its position and the grid centre).  Between loam_b200_map_end_sweep and the next
+ * loam_b200_map_begin_sweep the host only knows an upper bound of the pool size; loam_b200_cloud_size / _download of
+ * the pool slots synchronise and return the exact contents. */
 typedef struct {
   int cen[3];                 /* _laserCloudCenWidth / Height / Depth after rolling (BasicLaserMapping.cpp:311-441) */
   const int32_t* valid_cubes; /* _laserCloudValidInd, cube index i + 21 j + 231 k (BasicLaserMapping.h:126-127) */
@@ -251,11 +255,14 @@ typedef struct {
   float corner_leaf, surf_leaf;
 } loam_b200_map_window;
 
-/* append points (map frame) to the pool of kind 0 corner / 1 surface */
+/* append points (map frame) to the pool of kind 0 corner / 1 surface (unfiltered until their cube is in view at the end
+ * of a sweep, like points the reference holds in a cube cloud; the pool is re-sorted at the next begin_sweep) */
 int loam_b200_map_pool_append(loam_b200_ctx* ctx, int kind, const float* pts, int n);
 /* stacks: MAP_CORNER_LAST / MAP_SURF_LAST -> to map -> back to sensor (predicted pose) -> VoxelGrid -> *_STACK_DS;
- * from-map clouds: pool points in valid cubes -> *_FROM_MAP + BVHs; queries set for loam_b200_map_iterate.
- * sizes_out[4] = corner_from_map, surf_from_map, corner_stack_ds, surf_stack_ds */
+ * the field-of-view cube table is uploaded (the search structure itself persists from the previous sweep); queries set
+ * for loam_b200_map_iterate / loam_b200_map_solve.
+ * sizes_out[4] = number of map points in the valid cubes (corner, surface: the sizes of the reference's
+ * laserCloudCornerFromMap / laserCloudSurfFromMap, BasicLaserMapping.cpp:503-509,628), corner_stack_ds, surf_stack_ds */
 int loam_b200_map_begin_sweep(loam_b200_ctx* ctx, const loam_b200_pose* predicted, const loam_b200_map_window* win,
                               int sizes_out[4]);
 /* insert the stack points with the optimised pose, voxel-filter every valid cube (BasicLaserMapping.cpp:536-593) and
