@@ -106,11 +106,26 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def partition_cores(local_rank, world, gpu_cpus, allowed, first_sibling=lambda c: True):
+    """Pure part of the CPU binding: gpu_cpus[i] = CPUs NVML recommends for GPU i, allowed = CPUs this process may use.
+    Returns the cores for `local_rank`: physical cores (one hardware thread each) of its GPU's NUMA node, split evenly
+    between the ranks whose GPUs share that node; None when fewer than 4 cores would be left (main thread spins on the
+    result mailbox, two helper threads issue work)."""
+    mine = gpu_cpus[local_rank]
+    cores = sorted(mine & set(allowed)) or sorted(allowed)
+    cores = [c for c in cores if first_sibling(c)] or cores
+    peers = [r for r in range(world) if gpu_cpus[r] == mine] or [local_rank]
+    k, idx = len(peers), peers.index(local_rank) if local_rank in peers else 0
+    per = max(len(cores) // k, 1)
+    chunk = cores[idx * per:(idx + 1) * per] or cores
+    return chunk if len(chunk) >= 4 else None
+
+
 def pin_to_gpu_cores(local_rank, world):
-    """Bind this rank (and the library's helper threads it will spawn) to CPU cores on its GPU's NUMA node, split evenly
-    between the ranks whose GPUs share that node: the pipeline hand-shakes with the GPU dozens of times per sweep through
-    mapped host memory, so cross-socket latency and ranks stacked on the same cores show up directly in sweeps/s.
-    Returns a short description for the JSON line (None when the platform offers no affinity information)."""
+    """Bind this rank (and the library's helper threads it will spawn) to CPU cores on its GPU's NUMA node: the pipeline
+    hand-shakes with the GPU dozens of times per sweep through mapped host memory, so cross-socket latency and ranks
+    stacked on the same cores show up directly in sweeps/s.  Returns a short description for the JSON line (None when
+    the platform offers no affinity information)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -133,14 +148,10 @@ def pin_to_gpu_cores(local_rank, world):
             except Exception:
                 return True
 
-        mine = cpus_of(local_rank)
-        allowed = sorted(mine & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
-        allowed = [c for c in allowed if first_sibling(c)] or allowed
-        peers = [r for r in range(world) if cpus_of(r) == mine] if world > 1 else [local_rank]
-        k, idx = max(len(peers), 1), (peers.index(local_rank) if local_rank in peers else 0)
-        per = max(len(allowed) // k, 1)
-        chunk = allowed[idx * per:(idx + 1) * per] or allowed
-        if len(chunk) < 4:  # main thread spins on the mailbox, two helper threads issue work: do not squeeze them
+        n_local = max(world, local_rank + 1)
+        chunk = partition_cores(local_rank, world, [cpus_of(i) for i in range(n_local)], os.sched_getaffinity(0),
+                                first_sibling)
+        if not chunk:
             return None
         os.sched_setaffinity(0, chunk)
         return f"{len(chunk)} cores of the GPU's NUMA node (cpus {chunk[0]}-{chunk[-1]})"

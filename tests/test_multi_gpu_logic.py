@@ -88,3 +88,31 @@ def test_shard_slice_properties():
             assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
             sizes = [b - a for a, b in sl]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_core_partition():
+    """bench.py binds every rank to physical cores of its GPU's NUMA node, split between the ranks of that node."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    node0 = frozenset(list(range(0, 32)) + list(range(64, 96)))     # 32 cores x 2 hardware threads
+    node1 = frozenset(list(range(32, 64)) + list(range(96, 128)))
+    gpus = [node0] * 4 + [node1] * 4
+    first = lambda c: c < 64                                       # cpu c + 64 is the sibling of cpu c
+    allowed = set(range(128))
+    seen = []
+    for r in range(8):
+        chunk = bench.partition_cores(r, 8, gpus, allowed, first)
+        assert chunk is not None and len(chunk) == 8 and all(c < 64 for c in chunk)
+        assert set(chunk) <= (node0 if r < 4 else node1)
+        seen += chunk
+    assert len(seen) == len(set(seen)) == 64                       # disjoint, every physical core used once
+    assert bench.partition_cores(0, 1, gpus, allowed, first) == list(range(32))
+    assert bench.partition_cores(0, 2, gpus, allowed, first) == list(range(16))
+    assert bench.partition_cores(1, 2, gpus, allowed, first) == list(range(16, 32))
+    # a container that only grants a few CPUs: no binding rather than squeezing the threads
+    assert bench.partition_cores(0, 8, gpus, {0, 1, 2, 3, 4, 5, 6, 7}, first) is None
+    # CPUs outside the GPU's node only: fall back to what is allowed
+    assert bench.partition_cores(0, 1, gpus, set(range(32, 48)), first) == list(range(32, 48))
