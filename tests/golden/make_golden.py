@@ -4,7 +4,8 @@ Run in the build container (needs /root/reference):   python tests/golden/make_g
 The fixtures are small on purpose (VLP-16 at 600 azimuth steps, 40 k-point map) so they can live in git; they pin
  * the feature clouds of BasicScanRegistration::processScanlines,
  * the odometry / mapping poses of a 6-sweep registration -> odometry -> mapping run,
- * k-NN, VoxelGrid and the dense solves on fixed inputs.
+ * k-NN, VoxelGrid and the dense solves on fixed inputs,
+ * the ring-binning front end (MultiScanRegistration::process) on a jittered, defect-laden raw cloud.
 """
 import math
 import os
@@ -61,6 +62,14 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pieces.npz"), knn_pts=surf, knn_corner=corner, knn_q=q, knn_idx5=idx5,
                         knn_d5=d5, knn_idx1=idx1, knn_d1=d1, vox_in=out["pts2"], vox_out=vox, A=A, b=b, x=x, ev=ev,
                         V=V, ev3=ev3, V3=V3, P5=P5, x53=x53)
+    # ring-binning front end: MultiScanRegistration::process (the reference's ROS adapter compiled against oracle/shim/ros)
+    lid = synth.Lidar(16, 600, -15.0, 15.0)
+    pts_f, rs_f = synth.make_sweep(scene, lid, 2, yaw_rate=math.radians(5.0))
+    raw = synth.raw_cloud_from_sweep(pts_f, rs_f, n_bad=25, seed=9, elev_jitter_deg=0.2)
+    ms = ref.multiscan(-15.0, 15.0, 16)
+    binned, sizes = ms.process(raw)
+    np.savez_compressed(os.path.join(HERE, "multiscan_vlp16_600.npz"), raw=raw, binned=binned, sizes=sizes,
+                        sharp=ms.cloud("sharp"), flat=ms.cloud("flat"))
     print("golden fixtures written:", [f for f in os.listdir(HERE) if f.endswith(".npz")])
 
 

@@ -161,3 +161,14 @@ def test_ring_binning_restatement_equals_compiled_reference(oracle, reference, s
             # exact ring geometry: every point returns to the ring it was cast from, in firing order
             np.testing.assert_array_equal(sa, rs)
             np.testing.assert_array_equal(np.floor(pa[:, 3]).astype(np.int32), np.repeat(np.arange(len(rs)), rs))
+
+
+def test_ring_binning_restatement_matches_golden(oracle):
+    """Committed output of the reference's own MultiScanRegistration::process (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(HERE, "golden", "multiscan_vlp16_600.npz"))
+    ms = oracle.multiscan(-15.0, 15.0, 16)
+    binned, sizes = ms.process(g["raw"])
+    np.testing.assert_array_equal(sizes, g["sizes"])
+    np.testing.assert_array_equal(binned, g["binned"])
+    np.testing.assert_array_equal(ms.cloud("sharp"), g["sharp"])
+    np.testing.assert_array_equal(ms.cloud("flat"), g["flat"])
