@@ -149,6 +149,7 @@ struct loam_b200_ctx {
   bool surround_in_aux = false;
   bool cluster_ok = false;  // single-launch cluster kernels of clustersort.cuh usable (LOAM_B200_NO_CLUSTER=1 disables)
   cudaStream_t stream = nullptr;
+  cudaStream_t main_stream = nullptr;  // == stream outside LaneScope; the copy other threads may read (never swapped)
   std::string last_error;
   long long launches = 0;
 

@@ -473,6 +473,7 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
     delete c;
     return LOAM_B200_ERR_CUDA;
   }
+  c->main_stream = c->stream;
   bool lanes_ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   for (auto& l : c->lanes)
     lanes_ok = lanes_ok && cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
