@@ -147,7 +147,7 @@ int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m, con
   LB_CUDA(c, g.sorted.reserve(m));
   LB_CUDA(c, g.meta.reserve(1));
   size_t tsize = 1024;
-  while (tsize < (size_t)m) tsize <<= 1;  // load factor = occupied cells / table <= 1, typically ~0.15
+  while (tsize < 2 * (size_t)m) tsize <<= 1;  // occupied cells <= points: load factor <= 0.5 (typically ~0.08), probes always end
   LB_CUDA(c, g.table.reserve(tsize));
   g.mask = (unsigned)(tsize - 1);
   LB_CUDA(c, cudaMemsetAsync(g.table.p, 0, tsize * sizeof(uint4), c->stream));

@@ -37,7 +37,7 @@ def main():
     ctx.profile(False)
     alg = nq * 16 + probes * 16 + cands * 16 + 36 * 4
     dur = ms / n * 1e-3
-    print(f"map {surf.shape[0]} pts ({surf.shape[0] * 16 / 1e6:.0f} MB points + {2 ** int(np.ceil(np.log2(surf.shape[0]))) * 16 / 1e6:.0f} MB table), "
+    print(f"map {surf.shape[0]} pts ({surf.shape[0] * 16 / 1e6:.0f} MB points + {2 ** int(np.ceil(np.log2(2 * surf.shape[0]))) * 16 / 1e6:.0f} MB table), "
           f"queries {nq}, selected {ne['n_selected']}")
     print(f"kernel {dur * 1e6:.1f} us  probes/query {probes / nq:.1f}  candidates/query {cands / nq:.1f}  "
           f"algorithmic {alg / 1e6:.1f} MB  -> {alg / dur / 1e9:.1f} GB/s  ({nq / dur / 1e6:.1f} M queries/s)")
