@@ -26,6 +26,12 @@ void loam_b200_host_set_device(int device);
 int loam_b200_host_gn_solve(const float* AtA, const float* AtB, int first_iteration, float eigen_threshold, float* x_out6,
                             int* degenerate_out);
 
+/* ---- loam::BasicTransformMaintenance (host-only pose fusion, BasicTransformMaintenance.cpp:45-178) ----
+ * sum / bef / aft: rot_x, rot_y, rot_z, x, y, z of the odometry pose, the odometry pose at the last mapping update and the
+ * mapped pose of that update (updateOdometry + updateMappingTransform); mapped_out6 = transformMapped() after
+ * transformAssociateToMap(). */
+int loam_b200_transform_maintenance(const float* sum6, const float* bef6, const float* aft6, float* mapped_out6);
+
 /* ---- loam::BasicScanRegistration ---- */
 void* loam_b200_scanreg_create(void);
 void loam_b200_scanreg_destroy(void* h);

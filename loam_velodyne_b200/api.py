@@ -151,6 +151,7 @@ def lib():
         "loam_b200_scanreg_create": (vp, []),
         "loam_b200_scanreg_destroy": (None, [vp]),
         "loam_b200_scanreg_configure": (C.c_int, [vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
+        "loam_b200_transform_maintenance": (C.c_int, [_F, _F, _F, _F]),
         "loam_b200_host_gn_solve": (C.c_int, [_F, _F, C.c_int, C.c_float, _F, _I]),
         "loam_b200_scanreg_process_unordered": (C.c_int, [vp, _F, C.c_int, C.c_float, C.c_float, C.c_int]),
         "loam_b200_scanreg_process": (C.c_int, [vp, _F, _I, C.c_int]),
@@ -626,6 +627,15 @@ class Pipeline(_Handle):
                                                              _fp(odom), _fp(aft), st.ctypes.data_as(_D)),
                       "pipeline_sweep_device")
         return bool(ok), odom, aft, st
+
+
+def transform_maintenance(sum6, bef6, aft6):
+    """loam::BasicTransformMaintenance: updateOdometry + updateMappingTransform + transformAssociateToMap -> mapped pose."""
+    a = [np.ascontiguousarray(v, dtype=np.float32).reshape(6) for v in (sum6, bef6, aft6)]
+    out = np.zeros(6, np.float32)
+    if lib().loam_b200_transform_maintenance(_fp(a[0]), _fp(a[1]), _fp(a[2]), _fp(out)) != 0:
+        raise LoamB200Error("transform_maintenance: invalid arguments")
+    return out
 
 
 def gn_solve(AtA, AtB, first_iteration=True, eigen_threshold=10.0):

@@ -10,6 +10,7 @@
 
 #include "b200_runtime.h"
 #include "host_math.h"
+#include "pose_algebra.h"
 #include "loam_velodyne/BasicLaserOdometry.h"
 
 namespace loam {
@@ -82,63 +83,7 @@ void BasicLaserMapping::adopt(BasicLaserOdometry& odom) {
 // Pose prediction: compose (Sum, BefMapped, AftMapped) into TobeMapped, closed-form ZXY Euler algebra as published
 // with LOAM (upstream :103-167).
 void BasicLaserMapping::transformAssociateToMap() {
-  _transformIncre.pos = _transformBefMapped.pos - _transformSum.pos;
-  hostmath::rotateYXZ(_transformIncre.pos, -(_transformSum.rot_y), -(_transformSum.rot_x), -(_transformSum.rot_z));
-
-  const float sbcx = _transformSum.rot_x.sin(), cbcx = _transformSum.rot_x.cos();
-  const float sbcy = _transformSum.rot_y.sin(), cbcy = _transformSum.rot_y.cos();
-  const float sbcz = _transformSum.rot_z.sin(), cbcz = _transformSum.rot_z.cos();
-  const float sblx = _transformBefMapped.rot_x.sin(), cblx = _transformBefMapped.rot_x.cos();
-  const float sbly = _transformBefMapped.rot_y.sin(), cbly = _transformBefMapped.rot_y.cos();
-  const float sblz = _transformBefMapped.rot_z.sin(), cblz = _transformBefMapped.rot_z.cos();
-  const float salx = _transformAftMapped.rot_x.sin(), calx = _transformAftMapped.rot_x.cos();
-  const float saly = _transformAftMapped.rot_y.sin(), caly = _transformAftMapped.rot_y.cos();
-  const float salz = _transformAftMapped.rot_z.sin(), calz = _transformAftMapped.rot_z.cos();
-
-  const float srx = -sbcx * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz) -
-                    cbcx * sbcy * (calx * calz * (cbly * sblz - cblz * sblx * sbly) -
-                                   calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) -
-                    cbcx * cbcy * (calx * salz * (cblz * sbly - cbly * sblx * sblz) -
-                                   calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx);
-  _transformTobeMapped.rot_x = -std::asin(srx);
-
-  const float srycrx = sbcx * (cblx * cblz * (caly * salz - calz * salx * saly) -
-                               cblx * sblz * (caly * calz + salx * saly * salz) + calx * saly * sblx) -
-                       cbcx * cbcy * ((caly * calz + salx * saly * salz) * (cblz * sbly - cbly * sblx * sblz) +
-                                      (caly * salz - calz * salx * saly) * (sbly * sblz + cbly * cblz * sblx) -
-                                      calx * cblx * cbly * saly) +
-                       cbcx * sbcy * ((caly * calz + salx * saly * salz) * (cbly * cblz + sblx * sbly * sblz) +
-                                      (caly * salz - calz * salx * saly) * (cbly * sblz - cblz * sblx * sbly) +
-                                      calx * cblx * saly * sbly);
-  const float crycrx = sbcx * (cblx * sblz * (calz * saly - caly * salx * salz) -
-                               cblx * cblz * (saly * salz + caly * calz * salx) + calx * caly * sblx) +
-                       cbcx * cbcy * ((saly * salz + caly * calz * salx) * (sbly * sblz + cbly * cblz * sblx) +
-                                      (calz * saly - caly * salx * salz) * (cblz * sbly - cbly * sblx * sblz) +
-                                      calx * caly * cblx * cbly) -
-                       cbcx * sbcy * ((saly * salz + caly * calz * salx) * (cbly * sblz - cblz * sblx * sbly) +
-                                      (calz * saly - caly * salx * salz) * (cbly * cblz + sblx * sbly * sblz) -
-                                      calx * caly * cblx * sbly);
-  _transformTobeMapped.rot_y = std::atan2(srycrx / _transformTobeMapped.rot_x.cos(), crycrx / _transformTobeMapped.rot_x.cos());
-
-  const float srzcrx = (cbcz * sbcy - cbcy * sbcx * sbcz) * (calx * salz * (cblz * sbly - cbly * sblx * sblz) -
-                                                             calx * calz * (sbly * sblz + cbly * cblz * sblx) +
-                                                             cblx * cbly * salx) -
-                       (cbcy * cbcz + sbcx * sbcy * sbcz) * (calx * calz * (cbly * sblz - cblz * sblx * sbly) -
-                                                             calx * salz * (cbly * cblz + sblx * sbly * sblz) +
-                                                             cblx * salx * sbly) +
-                       cbcx * sbcz * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz);
-  const float crzcrx = (cbcy * sbcz - cbcz * sbcx * sbcy) * (calx * calz * (cbly * sblz - cblz * sblx * sbly) -
-                                                             calx * salz * (cbly * cblz + sblx * sbly * sblz) +
-                                                             cblx * salx * sbly) -
-                       (sbcy * sbcz + cbcy * cbcz * sbcx) * (calx * salz * (cblz * sbly - cbly * sblx * sblz) -
-                                                             calx * calz * (sbly * sblz + cbly * cblz * sblx) +
-                                                             cblx * cbly * salx) +
-                       cbcx * cbcz * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz);
-  _transformTobeMapped.rot_z = std::atan2(srzcrx / _transformTobeMapped.rot_x.cos(), crzcrx / _transformTobeMapped.rot_x.cos());
-
-  Vector3 v = _transformIncre.pos;
-  hostmath::rotateZXY(v, _transformTobeMapped.rot_z, _transformTobeMapped.rot_x, _transformTobeMapped.rot_y);
-  _transformTobeMapped.pos = _transformAftMapped.pos - v;
+  hostmath::associateToMap(_transformSum, _transformBefMapped, _transformAftMapped, _transformIncre, _transformTobeMapped);
 }
 
 void BasicLaserMapping::transformUpdate() {

@@ -11,6 +11,7 @@
 #include "loam_velodyne/BasicLaserMapping.h"
 #include "loam_velodyne/BasicLaserOdometry.h"
 #include "loam_velodyne/BasicScanRegistration.h"
+#include "loam_velodyne/BasicTransformMaintenance.h"
 
 namespace {
 
@@ -121,6 +122,17 @@ int loam_b200_host_gn_solve(const float* AtA, const float* AtB, int first_iterat
   loam::b200::GaussNewtonSolver solver;
   solver.solve(ne, first_iteration != 0, eigen_threshold, x_out6);
   if (degenerate_out) *degenerate_out = solver.isDegenerate ? 1 : 0;
+  return 0;
+}
+
+int loam_b200_transform_maintenance(const float* sum6, const float* bef6, const float* aft6, float* mapped_out6) {
+  if (!sum6 || !bef6 || !aft6 || !mapped_out6) return -1;
+  loam::BasicTransformMaintenance tm;
+  tm.updateOdometry(sum6[0], sum6[1], sum6[2], sum6[3], sum6[4], sum6[5]);
+  tm.updateMappingTransform(aft6[0], aft6[1], aft6[2], aft6[3], aft6[4], aft6[5], bef6[0], bef6[1], bef6[2], bef6[3], bef6[4],
+                            bef6[5]);
+  tm.transformAssociateToMap();
+  for (int i = 0; i < 6; i++) mapped_out6[i] = tm.transformMapped()[i];
   return 0;
 }
 

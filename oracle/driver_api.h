@@ -44,6 +44,10 @@ void loamdrv_multiscan_binned(void* h, float* out_pts4, int* ring_sizes);
 int loamdrv_multiscan_cloud_size(void* h, int which);
 void loamdrv_multiscan_cloud_copy(void* h, int which, float* out);
 
+/* ---- transform maintenance (BasicTransformMaintenance.cpp:45-178): updateOdometry(sum) + updateMappingTransform(aft, bef)
+ * + transformAssociateToMap -> transformMapped ---- */
+void loamdrv_transform_maintenance(const float* sum6, const float* bef6, const float* aft6, float* mapped_out6);
+
 /* ---- laser odometry (BasicLaserOdometry.cpp:196-666) ---- */
 void* loamdrv_odom_create(float scanPeriod, int maxIterations);
 void loamdrv_odom_destroy(void* h);

@@ -1111,6 +1111,25 @@ int loamdrv_scanreg_process(void* h, const float* pts, const int* ring_sizes, in
 int loamdrv_scanreg_cloud_size(void* h, int which) { return (int)((RegH*)h)->cloud(which).size(); }
 void loamdrv_scanreg_cloud_copy(void* h, int which, float* out) { dump(((RegH*)h)->cloud(which), out); }
 
+// BasicTransformMaintenance.cpp:45-178.  transformAssociateToMap there is the same association of (sum, bef, aft) as
+// BasicLaserMapping.cpp:103-167 (restated in Mapping::predict above) written on float[6] arrays: the sines / cosines are
+// std::sin / std::cos of the float angles (what Ang caches), the translation steps are the same elementary rotations.
+void loamdrv_transform_maintenance(const float* sum, const float* bef, const float* aft, float* out) {
+  Mapping m(0.1f, 1);
+  const float* src[3] = {sum, bef, aft};
+  Pose* dst[3] = {&m.sum, &m.bef, &m.aft};
+  for (int k = 0; k < 3; k++) {
+    dst[k]->rx = Ang(src[k][0]);
+    dst[k]->ry = Ang(src[k][1]);
+    dst[k]->rz = Ang(src[k][2]);
+    dst[k]->t.x = src[k][3];
+    dst[k]->t.y = src[k][4];
+    dst[k]->t.z = src[k][5];
+  }
+  m.predict();
+  twist6(m.tobe, out);
+}
+
 void* loamdrv_multiscan_create(float lo, float hi, int n) { return new MultiScan(lo, hi, n); }
 void loamdrv_multiscan_destroy(void* h) { delete (MultiScan*)h; }
 int loamdrv_multiscan_process(void* h, const float* xyz, int n) { return ((MultiScan*)h)->process(xyz, n); }

@@ -72,6 +72,7 @@ class Driver:
             "loamdrv_scanreg_process": (C.c_int, [vp, _F, _I, C.c_int]),
             "loamdrv_scanreg_cloud_size": (C.c_int, [vp, C.c_int]),
             "loamdrv_scanreg_cloud_copy": (None, [vp, C.c_int, _F]),
+            "loamdrv_transform_maintenance": (None, [_F, _F, _F, _F]),
             "loamdrv_multiscan_create": (vp, [C.c_float, C.c_float, C.c_int]),
             "loamdrv_multiscan_destroy": (None, [vp]),
             "loamdrv_multiscan_process": (C.c_int, [vp, _F, C.c_int]),
@@ -175,6 +176,12 @@ class Driver:
         return x
 
     # ---- objects
+    def transform_maintenance(self, sum6, bef6, aft6):
+        a = [np.ascontiguousarray(v, dtype=np.float32).reshape(6) for v in (sum6, bef6, aft6)]
+        out = np.zeros(6, np.float32)
+        self.L.loamdrv_transform_maintenance(_fp(a[0]), _fp(a[1]), _fp(a[2]), _fp(out))
+        return out
+
     def multiscan(self, lower_deg, upper_deg, n_rings):
         return MultiScan(self, lower_deg, upper_deg, n_rings)
 

@@ -13,6 +13,7 @@
 #include "loam_velodyne/BasicLaserOdometry.h"
 #include "loam_velodyne/BasicScanRegistration.h"
 #include "loam_velodyne/MultiScanRegistration.h"
+#include "loam_velodyne/BasicTransformMaintenance.h"
 #include "loam_velodyne/nanoflann_pcl.h"
 #include <Eigen/Eigenvalues>
 #include <Eigen/QR>
@@ -168,6 +169,14 @@ int loamdrv_scanreg_process(void* h, const float* pts, const int* ring_sizes, in
 }
 int loamdrv_scanreg_cloud_size(void* h, int which) { return (int)((RegH*)h)->cloud(which).size(); }
 void loamdrv_scanreg_cloud_copy(void* h, int which, float* out) { dump(((RegH*)h)->cloud(which), out); }
+
+void loamdrv_transform_maintenance(const float* sum, const float* bef, const float* aft, float* out) {
+  loam::BasicTransformMaintenance tm;
+  tm.updateOdometry(sum[0], sum[1], sum[2], sum[3], sum[4], sum[5]);
+  tm.updateMappingTransform(aft[0], aft[1], aft[2], aft[3], aft[4], aft[5], bef[0], bef[1], bef[2], bef[3], bef[4], bef[5]);
+  tm.transformAssociateToMap();
+  for (int i = 0; i < 6; i++) out[i] = tm.transformMapped()[i];
+}
 
 void* loamdrv_multiscan_create(float lo, float hi, int n) { return new MsH(lo, hi, n); }
 void loamdrv_multiscan_destroy(void* h) { delete (MsH*)h; }

@@ -172,3 +172,21 @@ def test_ring_binning_restatement_matches_golden(oracle):
     np.testing.assert_array_equal(binned, g["binned"])
     np.testing.assert_array_equal(ms.cloud("sharp"), g["sharp"])
     np.testing.assert_array_equal(ms.cloud("flat"), g["flat"])
+
+
+def test_transform_maintenance(oracle, reference):
+    """BasicTransformMaintenance: restatement == compiled reference == the library's drop-in class, bit for bit
+    (host-only arithmetic; the drop-in shares its association routine with BasicLaserMapping's pose prediction)."""
+    from loam_velodyne_b200 import api
+    rng = np.random.RandomState(21)
+    for _ in range(200):
+        sum6 = np.concatenate([rng.uniform(-0.6, 0.6, 3), rng.uniform(-40, 40, 3)]).astype(np.float32)
+        bef6 = (sum6 + np.concatenate([rng.normal(0, 0.02, 3), rng.normal(0, 0.5, 3)])).astype(np.float32)
+        aft6 = (bef6 + np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.2, 3)])).astype(np.float32)
+        r = reference.transform_maintenance(sum6, bef6, aft6)
+        np.testing.assert_array_equal(oracle.transform_maintenance(sum6, bef6, aft6), r)
+        np.testing.assert_array_equal(api.transform_maintenance(sum6, bef6, aft6), r)
+        assert np.isfinite(r).all()
+    # identity correction: mapped == odometry pose
+    p = np.array([0.1, -0.2, 0.05, 1.0, 2.0, 3.0], np.float32)
+    np.testing.assert_allclose(reference.transform_maintenance(p, p, p), p, rtol=0, atol=2e-6)
