@@ -6,51 +6,44 @@
 namespace loam {
 
 namespace {
-Twist twistOf(const float t[6]) {
+// the reference keeps every pose as six floats: narrow first, then build the cached sines / cosines from the floats
+Twist narrowed(double rx, double ry, double rz, double x, double y, double z) {
   Twist w;
-  w.rot_x = t[0];
-  w.rot_y = t[1];
-  w.rot_z = t[2];
-  w.pos.x() = t[3];
-  w.pos.y() = t[4];
-  w.pos.z() = t[5];
+  w.rot_x = (float)rx;
+  w.rot_y = (float)ry;
+  w.rot_z = (float)rz;
+  w.pos.x() = (float)x;
+  w.pos.y() = (float)y;
+  w.pos.z() = (float)z;
   return w;
 }
 }  // namespace
 
 void BasicTransformMaintenance::updateOdometry(double pitch, double yaw, double roll, double x, double y, double z) {
-  const double v[6] = {pitch, yaw, roll, x, y, z};
-  for (int i = 0; i < 6; i++) _transformSum[i] = (float)v[i];
+  _odometry = narrowed(pitch, yaw, roll, x, y, z);
 }
 
 void BasicTransformMaintenance::updateMappingTransform(double pitch, double yaw, double roll, double x, double y, double z,
                                                        double twist_rot_x, double twist_rot_y, double twist_rot_z,
                                                        double twist_pos_x, double twist_pos_y, double twist_pos_z) {
-  const double a[6] = {pitch, yaw, roll, x, y, z};
-  const double b[6] = {twist_rot_x, twist_rot_y, twist_rot_z, twist_pos_x, twist_pos_y, twist_pos_z};
-  for (int i = 0; i < 6; i++) {
-    _transformAftMapped[i] = (float)a[i];
-    _transformBefMapped[i] = (float)b[i];
-  }
+  _mappedAtMapping = narrowed(pitch, yaw, roll, x, y, z);
+  _odometryAtMapping = narrowed(twist_rot_x, twist_rot_y, twist_rot_z, twist_pos_x, twist_pos_y, twist_pos_z);
 }
 
 void BasicTransformMaintenance::updateMappingTransform(Twist const& aft, Twist const& bef) {
-  updateMappingTransform(aft.rot_x.rad(), aft.rot_y.rad(), aft.rot_z.rad(), aft.pos.x(), aft.pos.y(), aft.pos.z(),
-                         bef.rot_x.rad(), bef.rot_y.rad(), bef.rot_z.rad(), bef.pos.x(), bef.pos.y(), bef.pos.z());
+  _mappedAtMapping = aft;
+  _odometryAtMapping = bef;
 }
 
 void BasicTransformMaintenance::transformAssociateToMap() {
-  Twist incre, mapped;
-  hostmath::associateToMap(twistOf(_transformSum), twistOf(_transformBefMapped), twistOf(_transformAftMapped), incre, mapped);
-  _transformIncre[3] = incre.pos.x();
-  _transformIncre[4] = incre.pos.y();
-  _transformIncre[5] = incre.pos.z();
-  _transformMapped[0] = mapped.rot_x.rad();
-  _transformMapped[1] = mapped.rot_y.rad();
-  _transformMapped[2] = mapped.rot_z.rad();
-  _transformMapped[3] = mapped.pos.x();
-  _transformMapped[4] = mapped.pos.y();
-  _transformMapped[5] = mapped.pos.z();
+  Twist increment, fused;
+  hostmath::associateToMap(_odometry, _odometryAtMapping, _mappedAtMapping, increment, fused);
+  _mapped[0] = fused.rot_x.rad();
+  _mapped[1] = fused.rot_y.rad();
+  _mapped[2] = fused.rot_z.rad();
+  _mapped[3] = fused.pos.x();
+  _mapped[4] = fused.pos.y();
+  _mapped[5] = fused.pos.z();
 }
 
 }  // namespace loam

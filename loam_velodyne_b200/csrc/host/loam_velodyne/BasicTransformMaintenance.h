@@ -1,7 +1,7 @@
-// Drop-in for the reference's include/loam_velodyne/BasicTransformMaintenance.h: fuses the high-rate odometry pose with the
-// low-rate mapping correction (upstream BasicTransformMaintenance.cpp:45-178).  O(1) host scalar math -- nothing here
-// touches the GPU; it is provided so that a node built on the three Basic* drop-ins finds the fourth class as well.
-// The association itself is the routine BasicLaserMapping uses for its pose prediction (host/pose_algebra.h).
+// Pose fusion between the odometry rate and the mapping rate -- the fourth ROS-free class of the reference
+// (include/loam_velodyne/BasicTransformMaintenance.h, src/lib/BasicTransformMaintenance.cpp:45-178), offered with the same
+// public calls so that a node built on the three GPU-backed Basic* drop-ins finds it too.  Host scalar arithmetic only:
+// the association is the routine the mapping stage uses for its pose prediction (host/pose_algebra.h).
 #pragma once
 
 #include "Twist.h"
@@ -10,23 +10,33 @@ namespace loam {
 
 class BasicTransformMaintenance {
  public:
-  void updateOdometry(double pitch, double yaw, double roll, double x, double y, double z);
-  void updateMappingTransform(Twist const& transformAftMapped, Twist const& transformBefMapped);
-  void updateMappingTransform(double pitch, double yaw, double roll, double x, double y, double z, double twist_rot_x,
-                              double twist_rot_y, double twist_rot_z, double twist_pos_x, double twist_pos_y,
-                              double twist_pos_z);
+  /** fused pose after transformAssociateToMap(): rot_x, rot_y, rot_z, x, y, z */
+  auto const& transformMapped() const { return _mapped; }
 
+  /** compose odometry pose, odometry pose at the last mapping update and mapped pose of that update */
   void transformAssociateToMap();
 
-  // result accessor: rot_x, rot_y, rot_z, x, y, z
-  auto const& transformMapped() const { return _transformMapped; }
+  /** latest odometry pose (angles in rad) */
+  void updateOdometry(double pitch, double yaw, double roll, double x, double y, double z);
+
+  /** latest mapping result: mapped pose (aft) and the odometry pose it was computed from (bef) */
+  void updateMappingTransform(Twist const& transformAftMapped, Twist const& transformBefMapped);
+  void updateMappingTransform(double pitch,
+                              double yaw,
+                              double roll,
+                              double x,
+                              double y,
+                              double z,
+                              double twist_rot_x,
+                              double twist_rot_y,
+                              double twist_rot_z,
+                              double twist_pos_x,
+                              double twist_pos_y,
+                              double twist_pos_z);
 
  private:
-  float _transformSum[6]{};
-  float _transformIncre[6]{};
-  float _transformMapped[6]{};
-  float _transformBefMapped[6]{};
-  float _transformAftMapped[6]{};
+  Twist _odometry, _odometryAtMapping, _mappedAtMapping;  // inputs, narrowed to float like the reference's arrays
+  float _mapped[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 };
 
 }  // namespace loam
