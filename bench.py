@@ -387,32 +387,101 @@ def cpu_baseline(args, corner, surf, sweeps):
             "stage_ms": {k: round(1e3 * s / len(times), 2) for k, s in zip(["registration", "odometry", "full_to_end", "mapping", "total"], stage)}}
 
 
+def reference_pipelined(drv, corner, surf, sweeps, warmup, steps):
+    """The reference as it is deployed: scan registration, odometry and mapping are three single-threaded ROS nodes that
+    work on consecutive sweeps at the same time.  Three threads, each owning one of the reference's classes, connected by
+    queues that carry the clouds the topics carry (ScanRegistration.cpp:187-199, LaserOdometry.cpp:286-330); ctypes
+    releases the GIL inside the C++ calls.  Returns (sweeps/s between the completion of sweep warmup-1 and the last
+    sweep, final mapped pose)."""
+    import queue
+    reg, odo, mp = drv.scanreg(), drv.odom(), drv.mapping()
+    mp.seed(corner, surf)
+    q1, q2 = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
+    n_total = warmup + steps
+    done_t = [0.0] * n_total
+    errors = []
+
+    def stage_reg():
+        try:
+            for i in range(n_total):
+                reg.process(*sweeps[i])
+                q1.put(tuple(reg.cloud(k) for k in ("sharp", "less_sharp", "flat", "less_flat", "full")))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            q1.put(None)
+
+    def stage_odom():
+        try:
+            for i in range(n_total):
+                item = q1.get()
+                if item is None:
+                    q2.put(None)
+                    return
+                odo.set_inputs(*item)
+                odo.process()
+                odo.full_to_end()
+                q2.put((odo.cloud("last_corner"), odo.cloud("last_surf"), odo.cloud("full"), odo.twist("sum")))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            q2.put(None)
+
+    def stage_map():
+        try:
+            for i in range(n_total):
+                item = q2.get()
+                if item is None:
+                    return
+                mp.set_inputs(item[0], item[1], item[2])
+                mp.update_odometry(item[3])
+                mp.process()
+                done_t[i] = time.perf_counter()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=f) for f in (stage_reg, stage_odom, stage_map)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return steps / (done_t[n_total - 1] - done_t[warmup - 1]), mp.twist("aft")
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, with all the
+    threads it can use: its three stages are single-threaded and run as three concurrent nodes (reference_pipelined);
+    the strictly sequential single-core figure is reported next to it."""
     if rank != 0:
         return None
     from oracle import pydriver
     drv = pydriver.best(fast=True)
     n_total = args.warmup + args.steps
     lidar, corner, surf, sweeps = make_workload(args.workload, n_total, 0)
+    v, aft_pipelined = reference_pipelined(drv, corner, surf, sweeps, args.warmup, args.steps)
+    # sequential run of the same sweeps on one core (the cpu_baseline figure of the cuda arm)
     pipe = drv.pipeline()
     pipe.seed_map(corner, surf)
+    n_seq = min(n_total, args.warmup + 10)
     for i in range(args.warmup):
         pipe.sweep(*sweeps[i])
     t0 = time.perf_counter()
-    for i in range(args.warmup, n_total):
-        pipe.sweep(*sweeps[i])
-    el = time.perf_counter() - t0
-    v = args.steps / el
+    aft_seq = None
+    for i in range(args.warmup, n_seq):
+        _, _, aft_seq, _ = pipe.sweep(*sweeps[i])
+    v_seq = (n_seq - args.warmup) / (time.perf_counter() - t0)
     kind = "reference" if drv.kind == "reference" else "port"
     return {"impl": "reference", "metric": "sweeps/sec scan-to-map", "value": round(v, 3), "unit": "sweeps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * el / args.steps, 3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / v, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": int(sweeps[0][0].shape[0]),
-                       "map_points": int(corner.shape[0] + surf.shape[0])},
-            "cpu_baseline": {"value": round(v, 3), "unit": "sweeps/s", "cores": 1, "kind": kind,
-                             "sample": f"{args.steps} sweeps, single thread (the reference nodes are single-threaded), "
-                                       f"{os.cpu_count()} host cores present"},
+                       "map_points": int(corner.shape[0] + surf.shape[0]),
+                       "mode": "three single-threaded stages (registration / odometry / mapping) pipelined over consecutive "
+                               "sweeps, as the reference's three ROS nodes run"},
+            "cpu_baseline": {"value": round(v, 3), "unit": "sweeps/s", "cores": 3, "kind": kind,
+                             "sample": f"{args.steps} sweeps through three concurrent stage threads, {os.cpu_count()} host cores "
+                                       f"present (the reference cannot use more: every node is single-threaded)",
+                             "sequential_one_core": round(v_seq, 3)},
             "e2e": {"value": round(v, 3), "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
