@@ -284,7 +284,7 @@ def run_cuda(args, rank, world, local_rank):
                        "mode": ("sharded: one stream, query slices + NCCL all-reduce of AtA/AtB per LM iteration" if sharded
                                 else "replicas: one independent sweep stream and map per GPU, no data-path collective"
                                 if world > 1 else "single"),
-                       "l2_note": ("inputs change every step (new sweep, map updated every sweep); map = %d MB points + cell table: %s the 126 MB L2"
+                       "l2_note": ("inputs change every step (new sweep, map updated every sweep); map = %d MB points + 2x that in cell table: %s the 126 MB L2"
                                    % (int(corner.shape[0] + surf.shape[0]) * 16 // 1000000,
                                       "resident in" if corner.shape[0] + surf.shape[0] <= 2_000_000 else "larger than")),
                        "odom_iters_per_sweep": round(iters_o / args.steps, 2), "map_iters_per_sweep": round(iters_m / args.steps, 2),
