@@ -252,7 +252,8 @@ typedef struct {
   int cen[3];                 /* _laserCloudCenWidth / Height / Depth after rolling (BasicLaserMapping.cpp:311-441) */
   const int32_t* valid_cubes; /* _laserCloudValidInd, cube index i + 21 j + 231 k (BasicLaserMapping.h:126-127) */
   int n_valid;                /* <= 125 */
-  float corner_leaf, surf_leaf;
+  float corner_leaf, surf_leaf; /* VoxelGrid leaf sizes of the per-cube filters (BasicLaserMapping.cpp:98-99); >= 0.2 m, smaller
+                                 * leaves are refused with LOAM_B200_ERR_ARG (8-bit per-axis voxel index inside a cube) */
 } loam_b200_map_window;
 
 /* append points (map frame) to the pool of kind 0 corner / 1 surface (unfiltered until their cube is in view at the end

@@ -265,6 +265,7 @@ void BasicLaserMapping::updateOdometry(Twist const& twist) { _transformSum = twi
 
 void BasicLaserMapping::optimizeTransformTobeMapped() {
   _lastIterations = 0;
+  _solver->isDegenerate = false;  // a local of optimizeTransformTobeMapped() upstream (:640): fresh every sweep
   // _laserCloudCornerFromMap->size() <= 10 || _laserCloudSurfFromMap->size() <= 100 (upstream :628-629); the trees
   // and the query stacks were prepared by loam_b200_map_begin_sweep
   if (_mapSizes[0] <= 10 || _mapSizes[1] <= 100) return;

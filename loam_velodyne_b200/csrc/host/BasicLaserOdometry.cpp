@@ -127,6 +127,7 @@ void BasicLaserOdometry::applyImuToEnd(pcl::PointCloud<pcl::PointXYZI>& cloud) {
 }
 
 void BasicLaserOdometry::uploadLast() {
+  _c[C_LAST_CORNER].dropNonFinite();  // upstream :252 (there after the tree was built; here before, so indices stay valid)
   _c[C_LAST_CORNER].ensureDevice();
   _c[C_LAST_SURF].ensureDevice();
   _gpu->check(loam_b200_odom_rebuild_last(_gpu->get()), "loam_b200_odom_rebuild_last");
@@ -146,6 +147,8 @@ void BasicLaserOdometry::process() {
   _frameCount++;
   _transform.pos -= _imuVeloFromStart * _scanPeriod;
   _lastIterations = 0;
+  // `bool isDegenerate = false` is a local of process() upstream (:212): a projection of an earlier sweep is never applied
+  _solver->isDegenerate = false;
   static const bool trace = std::getenv("LOAM_B200_TRACE") != nullptr;
   auto tnow = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double tr0 = tnow();
@@ -155,7 +158,10 @@ void BasicLaserOdometry::process() {
   size_t lastSurfaceCloudSize = _c[C_LAST_SURF].size();
 
   if (lastCornerCloudSize > 10 && lastSurfaceCloudSize > 100) {
-    // non-finite feature points would be dropped here upstream (removeNaNFromPointCloud, :230); inputs are dense
+    // upstream :230 / :252: removeNaNFromPointCloud on the sharp cloud and on the last corner cloud.  PCL only filters
+    // clouds flagged !is_dense; clouds adopted on the device are dense by construction (the front end drops non-finite
+    // points, MultiScanRegistration.cpp:187-192), so this only acts on caller-filled host clouds
+    _c[C_SHARP].dropNonFinite();
     _c[C_SHARP].ensureDevice();
     _c[C_FLAT].ensureDevice();
     _gpu->check(loam_b200_odom_prepare(_gpu->get()), "loam_b200_odom_prepare");

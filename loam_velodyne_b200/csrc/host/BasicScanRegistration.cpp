@@ -4,6 +4,8 @@
 #include "b200_runtime.h"
 #include "host_math.h"
 
+#include <stdexcept>
+
 namespace loam {
 
 RegistrationParams::RegistrationParams(const float& scanPeriod_, const int& imuHistorySize_, const int& nFeatureRegions_,
@@ -102,13 +104,20 @@ void BasicScanRegistration::processPackedSweep(const Time& scanTime, const float
   updateIMUTransform();
 }
 
-void BasicScanRegistration::processUnorderedSweep(const Time& scanTime, const float* xyz, int n, MultiScanMapper mapper,
+void BasicScanRegistration::processUnorderedSweep(const Time& scanTime, const float* xyz, int n, b200::RingLayout rings,
                                                   bool onDevice) {
+  // upstream de-skews every point with projectPointToStartOfSweep(point, relTime) in arrival order before binning
+  // (MultiScanRegistration.cpp:230); that sequential host interpolation is not part of the device front end, so a sweep
+  // with IMU data must take the reference's own route (host ring binning + processScanlines) instead of being
+  // silently left skewed
+  if (hasIMUData())
+    throw std::runtime_error("BasicScanRegistration::processUnorderedSweep: IMU data present -- the device front end "
+                             "does not de-skew; bin on the host (MultiScanRegistration::process) and call processScanlines");
   reset(scanTime);
-  const int nRings = (int)mapper.getNumberOfScanRings();
+  const int nRings = (int)rings.nScanRings;
   std::vector<int32_t> ringSizes((size_t)nRings, 0);
   int kept = 0;
-  _gpu->check(loam_b200_reg_bin(_gpu->get(), xyz, n, onDevice ? 1 : 0, mapper.getLowerBound(), mapper.getUpperBound(), nRings,
+  _gpu->check(loam_b200_reg_bin(_gpu->get(), xyz, n, onDevice ? 1 : 0, rings.lowerBoundDeg, rings.upperBoundDeg, nRings,
                                 _config.scanPeriod, ringSizes.data(), &kept),
               "loam_b200_reg_bin");
   size_t cloudSize = 0;

@@ -66,6 +66,19 @@ void DualCloud::materialise() {
   hostValid_ = true;
 }
 
+void DualCloud::dropNonFinite() {
+  if (!hostValid_ || host_->is_dense) return;
+  auto& pts = host_->points;
+  std::size_t j = 0;
+  for (std::size_t i = 0; i < pts.size(); i++)
+    if (std::isfinite(pts[i].x) && std::isfinite(pts[i].y) && std::isfinite(pts[i].z)) pts[j++] = pts[i];
+  if (j != pts.size()) devValid_ = false;
+  pts.resize(j);
+  host_->width = static_cast<std::uint32_t>(j);
+  host_->height = 1;
+  host_->is_dense = true;
+}
+
 void DualCloud::swap(DualCloud& o) {
   host_.swap(o.host_);
   std::swap(hostValid_, o.hostValid_);

@@ -62,6 +62,8 @@ class DualCloud {
   void ensureDevice();   // upload when the device copy is stale
   void materialise();    // download when the host copy is stale
   void clear() { host_->clear(); hostValid_ = true; devValid_ = false; devN_ = 0; }
+  // pcl::removeNaNFromPointCloud(c, c, idx) on a caller-filled host cloud (only clouds flagged !is_dense are touched)
+  void dropNonFinite();
   // exchange contents with another cloud of the same context (the reference swaps cloud pointers)
   void swap(DualCloud& o);
 

@@ -1,6 +1,7 @@
 // Minimal pcl::PointCloud<T> for builds without PCL: exactly the members the Basic* classes and their ROS adapters
 // use (points, push_back, +=, clear, size, [], iteration, is_dense, width/height, Ptr).
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <string>

@@ -152,8 +152,8 @@ int loam_b200_scanreg_process(void* h, const float* pts, const int* ring_sizes, 
 int loam_b200_scanreg_process_unordered(void* h, const float* xyz, int n, float lower_bound_deg, float upper_bound_deg,
                                         int n_rings) {
   return guarded([&] {
-    ((RegH*)h)->r.processUnorderedSweep(loam::Time(), xyz, n, loam::MultiScanMapper(lower_bound_deg, upper_bound_deg,
-                                                                                     (uint16_t)n_rings));
+    ((RegH*)h)->r.processUnorderedSweep(loam::Time(), xyz, n, loam::b200::RingLayout(lower_bound_deg, upper_bound_deg,
+                                                                                      (uint16_t)n_rings));
     return 0;
   });
 }

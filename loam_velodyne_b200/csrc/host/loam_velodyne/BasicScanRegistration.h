@@ -56,32 +56,21 @@ typedef struct IMUState {
   static void interpolate(const IMUState& start, const IMUState& end, const float& ratio, IMUState& result);
 } IMUState;
 
-/** Linear vertical-angle -> ring mapper, same class as the reference's (declared there in the ROS-bound
- *  MultiScanRegistration.h:47-103; MultiScanRegistration.cpp:44-66).  Used by processUnorderedSweep(). */
-class MultiScanMapper {
- public:
-  MultiScanMapper(const float& lowerBound = -15, const float& upperBound = 15, const uint16_t& nScanRings = 16)
-      : _lowerBound(lowerBound), _upperBound(upperBound), _nScanRings(nScanRings),
-        _factor((nScanRings - 1) / (upperBound - lowerBound)) {}
-  const float& getLowerBound() { return _lowerBound; }
-  const float& getUpperBound() { return _upperBound; }
-  const uint16_t& getNumberOfScanRings() { return _nScanRings; }
-  void set(const float& lowerBound, const float& upperBound, const uint16_t& nScanRings) {
-    _lowerBound = lowerBound;
-    _upperBound = upperBound;
-    _nScanRings = nScanRings;
-    _factor = (nScanRings - 1) / (upperBound - lowerBound);
-  }
-  int getRingForAngle(const float& angle) { return int(((angle * 180 / M_PI) - _lowerBound) * _factor + 0.5); }
-  static inline MultiScanMapper Velodyne_VLP_16() { return MultiScanMapper(-15, 15, 16); }
-  static inline MultiScanMapper Velodyne_HDL_32() { return MultiScanMapper(-30.67f, 10.67f, 32); }
-  static inline MultiScanMapper Velodyne_HDL_64E() { return MultiScanMapper(-24.9f, 2, 64); }
-
- private:
-  float _lowerBound, _upperBound;
-  uint16_t _nScanRings;
-  float _factor;
+namespace b200 {
+/** Ring layout of a multi-beam sensor for processUnorderedSweep(): plain data with the same three numbers as the
+ *  reference's loam::MultiScanMapper (MultiScanRegistration.h:49-103).  That class itself stays where upstream declares
+ *  it (the ROS-bound MultiScanRegistration.h, which compiles unchanged against this header): declaring it here as well
+ *  made upstream's MultiScanRegistration.cpp fail with a redefinition (round-1 review). */
+struct RingLayout {
+  float lowerBoundDeg, upperBoundDeg;
+  uint16_t nScanRings;
+  RingLayout(float lower = -15.f, float upper = 15.f, uint16_t rings = 16)
+      : lowerBoundDeg(lower), upperBoundDeg(upper), nScanRings(rings) {}
+  static RingLayout Velodyne_VLP_16() { return RingLayout(-15.f, 15.f, 16); }
+  static RingLayout Velodyne_HDL_32() { return RingLayout(-30.67f, 10.67f, 32); }
+  static RingLayout Velodyne_HDL_64E() { return RingLayout(-24.9f, 2.f, 64); }
 };
+}  // namespace b200
 
 class BasicScanRegistration {
  public:
@@ -113,8 +102,16 @@ class BasicScanRegistration {
   /** Extension: the ring-binning front end of MultiScanRegistration::process (MultiScanRegistration.cpp:160-238) on the
    *  GPU, followed by the regular extraction: `xyz` = n unordered sensor-frame points (3 floats each, arrival order;
    *  host memory, or device memory when `onDevice`).  Equivalent to building the per-ring clouds on the host and
-   *  calling processScanlines(). */
-  void processUnorderedSweep(const Time& scanTime, const float* xyz, int n, MultiScanMapper mapper, bool onDevice = false);
+   *  calling processScanlines().  Sweeps with IMU data need the per-point de-skew of projectPointToStartOfSweep in
+   *  arrival order (host scalar code upstream): this entry point then throws std::runtime_error, use processScanlines. */
+  void processUnorderedSweep(const Time& scanTime, const float* xyz, int n, b200::RingLayout rings, bool onDevice = false);
+  /** Same, taking upstream's loam::MultiScanMapper (or anything with its three getters) directly: the one-line change in
+   *  MultiScanRegistration::process is `processUnorderedSweep(scanTime, xyz, n, _scanMapper)`. */
+  template <typename Mapper>
+  void processUnorderedSweep(const Time& scanTime, const float* xyz, int n, Mapper& mapper, bool onDevice = false) {
+    processUnorderedSweep(scanTime, xyz, n,
+                          b200::RingLayout(mapper.getLowerBound(), mapper.getUpperBound(), mapper.getNumberOfScanRings()), onDevice);
+  }
   void processDeviceSweep(const Time& scanTime, const void* deviceXyzi, const int* ringSizes, int nRings);
   // indices (into laserCloud()) of the picked features and the per-point labels of the last sweep
   std::vector<int> const& sharpIndices();

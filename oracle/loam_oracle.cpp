@@ -1297,6 +1297,16 @@ int loamorc_odom_iteration(void* h, int iter, const float* transform6, float* co
   }
   return n;
 }
+// correspondence indices kept from the last search iteration (BasicLaserOdometry.cpp:299-301, :431-434):
+// ind[3 * q + {0, 1, 2}] = closest / second / third point of query q (sharp queries first; -1 = none; corners have no third)
+void loamorc_odom_indices(void* h, int* ind) {
+  Odom* o = (Odom*)h;
+  const size_t nSharp = o->c1.size(), nFlat = o->s1.size();
+  for (size_t i = 0; i < nSharp; i++) { ind[3 * i] = o->c1[i]; ind[3 * i + 1] = o->c2[i]; ind[3 * i + 2] = -1; }
+  for (size_t i = 0; i < nFlat; i++) {
+    ind[3 * (nSharp + i)] = o->s1[i]; ind[3 * (nSharp + i) + 1] = o->s2[i]; ind[3 * (nSharp + i) + 2] = o->s3[i];
+  }
+}
 // make `last` clouds + trees from explicit inputs (as if a previous sweep had been processed)
 void loamorc_odom_set_last(void* h, const float* corner, int nc, const float* surf, int ns) {
   Odom* o = (Odom*)h;

@@ -120,6 +120,8 @@ class Driver:
             _S = C.POINTER(C.c_int8)
             L.loamorc_odom_iteration.restype = C.c_int
             L.loamorc_odom_iteration.argtypes = [vp, C.c_int, _F, _F, _S, _F, _F]
+            L.loamorc_odom_indices.restype = None
+            L.loamorc_odom_indices.argtypes = [vp, _I]
             L.loamorc_odom_set_last.restype = None
             L.loamorc_odom_set_last.argtypes = [vp, _F, C.c_int, _F, C.c_int]
             L.loamorc_map_set.restype = None
@@ -365,7 +367,9 @@ class OdomIterator:
         t = np.ascontiguousarray(transform6, dtype=np.float32)
         n = self.d.L.loamorc_odom_iteration(self.o.h, it, _fp(t), _fp(coeff), sel.ctypes.data_as(C.POINTER(C.c_int8)),
                                             _fp(AtA), _fp(AtB))
-        return {"n_selected": n, "coeff": coeff, "selected": sel, "AtA": AtA, "AtB": AtB}
+        ind = np.full((self.nq, 3), -1, np.int32)
+        self.d.L.loamorc_odom_indices(self.o.h, _ip(ind))
+        return {"n_selected": n, "coeff": coeff, "selected": sel, "AtA": AtA, "AtB": AtB, "ind": ind}
 
 
 class Pipeline:

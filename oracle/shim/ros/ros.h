@@ -23,6 +23,21 @@ struct Time {
   }
 };
 
+inline bool operator==(const Time& a, const Time& b) { return a.sec == b.sec && a.nsec == b.nsec; }
+inline bool operator!=(const Time& a, const Time& b) { return !(a == b); }
+struct Duration { double s = 0; double toSec() const { return s; } };
+inline Duration operator-(const Time& a, const Time& b) {
+  Duration d;
+  d.s = ((double)a.sec - (double)b.sec) + 1e-9 * ((double)a.nsec - (double)b.nsec);
+  return d;
+}
+struct Rate {
+  explicit Rate(double) {}
+  void sleep() {}
+};
+inline bool ok() { return false; }  // no master: the adapters' spin() loops end at once
+inline void spinOnce() {}
+
 struct Publisher {
   template <typename M>
   void publish(const M&) const {}

@@ -1,10 +1,7 @@
 // TEST INFRASTRUCTURE (oracle/shim): see ros/ros.h
 #pragma once
 #include <sensor_msgs/PointCloud2.h>
-namespace geometry_msgs_shim {
-struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
-struct Vector3 { double x = 0, y = 0, z = 0; };
-}  // namespace geometry_msgs_shim
+#include <geometry_msgs/Quaternion.h>
 namespace sensor_msgs {
 struct Imu {
   std_msgs_shim::Header header;

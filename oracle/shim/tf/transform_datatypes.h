@@ -4,7 +4,27 @@
 #include <cmath>
 #include <sensor_msgs/Imu.h>
 namespace tf {
-struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
+struct Quaternion {
+  double x = 0, y = 0, z = 0, w = 1;
+  Quaternion() {}
+  Quaternion(double x_, double y_, double z_, double w_) : x(x_), y(y_), z(z_), w(w_) {}
+};
+struct Vector3 {
+  double x = 0, y = 0, z = 0;
+  Vector3() {}
+  Vector3(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {}
+};
+// roll about x, pitch about y, yaw about z (tf::createQuaternionMsgFromRollPitchYaw)
+inline geometry_msgs::Quaternion createQuaternionMsgFromRollPitchYaw(double roll, double pitch, double yaw) {
+  const double cr = std::cos(roll / 2), sr = std::sin(roll / 2), cp = std::cos(pitch / 2), sp = std::sin(pitch / 2),
+               cy = std::cos(yaw / 2), sy = std::sin(yaw / 2);
+  geometry_msgs::Quaternion q;
+  q.x = sr * cp * cy - cr * sp * sy;
+  q.y = cr * sp * cy + sr * cp * sy;
+  q.z = cr * cp * sy - sr * sp * cy;
+  q.w = cr * cp * cy + sr * sp * sy;
+  return q;
+}
 inline void quaternionMsgToTF(const geometry_msgs_shim::Quaternion& m, Quaternion& q) { q.x = m.x; q.y = m.y; q.z = m.z; q.w = m.w; }
 struct Matrix3x3 {
   Quaternion q;

@@ -196,7 +196,11 @@ def test_odom_iteration_per_correspondence(ctx, oracle, scene):
         both = (sel == 1) & (ref["selected"] == 1)
         np.testing.assert_allclose(coeff[both], ref["coeff"][both], rtol=0, atol=5e-5)
         assert _rel(ne["AtA"], ref["AtA"]) <= 1e-4
-        assert _rel(ne["AtB"], ref["AtB"]) <= 2e-4
+        assert _rel(ne["AtB"], ref["AtB"]) <= 1e-4
+        # O2: the correspondence indices themselves (closest / second / third point in the last clouds); they are
+        # refreshed on every 5th iteration on both sides (BasicLaserOdometry.cpp:250, :368).  A query whose two best
+        # candidates are equidistant to the last bit may legitimately pick the other one: none observed, allow 2
+        assert int((ind != ref["ind"]).any(axis=1).sum()) <= 2, np.argwhere(ind != ref["ind"])[:10]
 
 
 def test_device_resident_odometry_loop(ctx, oracle, scene):
@@ -361,6 +365,27 @@ def test_transforms(ctx, checker, scene):
     np.testing.assert_allclose(got0, ref0, rtol=0, atol=1e-6)
 
 
+def test_transform_to_end_nonzero_twist(ctx, checker, scene):
+    """O6 with a real motion estimate: the checker's BasicLaserOdometry::transformToEnd over the full-resolution cloud
+    (LaserOdometry.cpp:326) after a sweep whose _transform is non-zero, against transform_to_end_kernel with that twist.
+    Per-point sin / cos go through a double sincos rounded once on the GPU and float libm on the host: tolerance, a few
+    ulp of the 60 m ranges."""
+    from loam_velodyne_b200 import synth
+    lidar = synth.Lidar.vlp16()
+    pc = checker.pipeline()
+    for i in range(3):
+        pts, rs = synth.make_sweep(scene, lidar, i, v=(2.0, 0.0, 0.5), yaw_rate=math.radians(20.0))
+        pc.sweep(pts, rs)
+    twist = pc.odom.twist("transform")
+    assert np.abs(twist[:3]).max() > 5e-3 and np.abs(twist[3:]).max() > 0.05  # a real rotation and translation
+    ref = pc.odom.cloud("full")
+    got = ctx.transform_to_end(pts, twist)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got[:, 3], ref[:, 3])  # intensity truncated to the ring id (:70)
+    np.testing.assert_allclose(got[:, :3], ref[:, :3], rtol=0, atol=2e-5)
+    assert np.abs(got[:, :3] - pts[:, :3]).max() > 0.05  # the transform did move the points
+
+
 def test_pipeline_trajectory_vlp16(checker, scene, sweeps_vlp16, map_200k):
     """registration -> odometry -> mapping over a stream: poses within 1e-4 m / 1e-4 rad of the oracle every sweep,
     feature index sets bit-exact every sweep."""
@@ -380,6 +405,112 @@ def test_pipeline_trajectory_vlp16(checker, scene, sweeps_vlp16, map_200k):
     # the map the two arms maintain stays the same size (same voxels occupied)
     assert pg.mapping.cloud("corner_cubes").shape == pc.mapping.cloud("corner_cubes").shape
     assert abs(pg.mapping.cloud("surf_cubes").shape[0] - pc.mapping.cloud("surf_cubes").shape[0]) <= 5
+
+
+def _voxel_sets_agree(g, c, leaf, what):
+    """Two maps as point sets: the same voxels occupied and the same centroid per voxel."""
+    assert abs(g.shape[0] - c.shape[0]) <= max(3, c.shape[0] // 2000), (what, g.shape, c.shape)
+    kg = np.floor(g[:, :3] / leaf).astype(np.int64)
+    kc = np.floor(c[:, :3] / leaf).astype(np.int64)
+    dg = {tuple(k): v for k, v in zip(kg, g)}
+    dc = {tuple(k): v for k, v in zip(kc, c)}
+    common = set(dg) & set(dc)
+    # the two arms' poses differ by ~1e-5, so a point that close to a voxel face may land in the neighbouring voxel
+    assert len(set(dg) ^ set(dc)) <= max(6, len(dc) // 500), (what, len(set(dg) ^ set(dc)), len(dc))
+    errs = np.array([np.abs(dg[k][:3] - dc[k][:3]).max() for k in common])
+    return errs
+
+
+def test_map_content_matches_reference_cubes(checker, scene, sweeps_vlp16, map_200k):
+    """The map the GPU maintains (persistent cell-sorted pools, incremental "old centroid + new points" voxel update,
+    mapstore.cuh) against the cube clouds the reference maintains (insertion :536-577 + whole-cube VoxelGrid :580-593)
+    after the same sweeps, as point sets: same voxels, centroids within 1e-5 (median) -- the untouched seed points must
+    be bit-identical."""
+    from loam_velodyne_b200 import api
+    corner, surf = map_200k
+    pg, pc = api.Pipeline(), checker.pipeline()
+    pg.seed_map(corner, surf)
+    pc.seed_map(corner, surf)
+    for pts, rs in sweeps_vlp16:
+        pg.sweep(pts, rs)
+        pc.sweep(pts, rs)
+    for name, leaf in (("corner_cubes", 0.2), ("surf_cubes", 0.4)):
+        g, c = pg.mapping.cloud(name), pc.mapping.cloud(name)
+        errs = _voxel_sets_agree(g, c, leaf, name)
+        assert np.median(errs) <= 1e-5, (name, np.median(errs))
+        assert np.mean(errs > 1e-4) <= 0.002 and errs.max() <= leaf, (name, np.mean(errs > 1e-4), errs.max())
+        # points of cubes that were never in view are carried through both arms untouched
+        sg = {p.tobytes() for p in g[:, :3]}
+        sc = {p.tobytes() for p in c[:, :3]}
+        assert len(sg & sc) >= 0.2 * len(sc), (name, len(sg & sc), len(sc))
+
+
+def test_pipeline_trajectory_hdl64_1m(checker, scene):
+    """BASELINE config 3 -- the benchmarked configuration: HDL-64E 64 x 2048 sweeps against the 1 M-point map, 10 sweeps,
+    every pose within 1e-4 m / 1e-4 rad of the compiled reference, feature sets bit-exact, and the maps agree as sets."""
+    from loam_velodyne_b200 import api, synth
+    lidar = synth.Lidar.hdl64()
+    corner, surf = synth.make_map(scene, 1_000_000)
+    pg, pc = api.Pipeline(), checker.pipeline()
+    pg.seed_map(corner, surf)
+    pc.seed_map(corner, surf)
+    worst = 0.0
+    for i in range(10):
+        pts, rs = synth.make_sweep(scene, lidar, i, yaw_rate=math.radians(5.0))
+        ok_g, od_g, aft_g, _ = pg.sweep(pts, rs)
+        ok_c, od_c, aft_c, _ = pc.sweep(pts, rs)
+        assert ok_g == ok_c
+        for name in ("sharp", "less_sharp", "flat"):
+            np.testing.assert_array_equal(pg.scanreg.cloud(name), pc.scanreg.cloud(name))
+        d = max(np.abs(od_g - od_c).max(), np.abs(aft_g - aft_c).max())
+        worst = max(worst, d)
+        assert d <= POSE_TOL, (i, d, od_g, od_c, aft_g, aft_c)
+    assert pg.odom.last_iterations() >= 1 and pg.mapping.last_iterations() >= 1
+    print(f"config 3: worst pose delta over 10 sweeps {worst:.2e}")
+    errs = _voxel_sets_agree(pg.mapping.cloud("surf_cubes"), pc.mapping.cloud("surf_cubes"), 0.4, "surf_cubes")
+    assert np.median(errs) <= 1e-5
+
+
+def test_map_iteration_hdl64_1m_normal_equations(ctx, oracle, scene):
+    """AtA / AtB of one scan-to-map iteration at the benchmarked size (HDL-64 queries, 1 M-point map) <= 1e-4."""
+    from loam_velodyne_b200 import api, synth
+    from oracle import pydriver
+    corner, surf = synth.make_map(scene, 1_000_000)
+    pts, rs = synth.make_sweep(scene, synth.Lidar.hdl64(), 3, yaw_rate=math.radians(5.0))
+    f = ctx.extract_features(pts, rs)
+    cq = ctx.voxel_grid(pts[f["less_sharp"]], 0.2)
+    sq = ctx.voxel_grid(f["less_flat_ds"], 0.4)
+    pos, yaw = synth.pose_at(0.4, np.array([0.0, 0.0, 1.0]), math.radians(5.0))
+    twist = np.asarray((0.001, yaw + 0.002, -0.0015, pos[0] + 0.03, pos[1] - 0.01, pos[2] + 0.04), np.float32)
+    ref = pydriver.map_iteration(oracle, corner, surf, cq, sq, twist)
+    ctx.tree_build(api.TREE_MAP_CORNER, corner)
+    ctx.tree_build(api.TREE_MAP_SURF, surf)
+    ctx.map_set_queries(cq, sq)
+    ne, coeff, sel = ctx.map_iterate(twist, debug=True)
+    assert ref["n_selected"] > 5000
+    assert int((sel != ref["selected"]).sum()) <= 4
+    both = (sel == 1) & (ref["selected"] == 1)
+    np.testing.assert_allclose(coeff[both], ref["coeff"][both], rtol=0, atol=2e-6)
+    assert _rel(ne["AtA"], ref["AtA"]) <= 1e-4 and _rel(ne["AtB"], ref["AtB"]) <= 1e-4
+
+
+def test_pipeline_trajectory_vlp16_50_sweeps(checker, scene, map_200k):
+    """BASELINE config 2 (SURVEY 8d): VLP-16 stream of 50 sweeps (1 m/s forward, 5 deg/s yaw) against the 200 k map;
+    every pose within 1e-4 of the compiled reference."""
+    from loam_velodyne_b200 import api, synth
+    corner, surf = map_200k
+    lidar = synth.Lidar.vlp16()
+    pg, pc = api.Pipeline(), checker.pipeline()
+    pg.seed_map(corner, surf)
+    pc.seed_map(corner, surf)
+    deltas = []
+    for i in range(50):
+        pts, rs = synth.make_sweep(scene, lidar, i, yaw_rate=math.radians(5.0))
+        _, od_g, aft_g, _ = pg.sweep(pts, rs)
+        _, od_c, aft_c, _ = pc.sweep(pts, rs)
+        deltas.append(max(np.abs(od_g - od_c).max(), np.abs(aft_g - aft_c).max()))
+    print("per-sweep pose delta vs the reference:", " ".join(f"{d:.1e}" for d in deltas))
+    assert max(deltas) <= POSE_TOL, (int(np.argmax(deltas)), max(deltas))
 
 
 def test_hostcloud_chain_equals_fused_chain(scene, sweeps_vlp16, map_200k):
