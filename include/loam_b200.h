@@ -43,6 +43,9 @@ int loam_b200_version(void);
  * there is deliberately no CPU fallback. */
 int loam_b200_create(loam_b200_ctx** out, int device);
 int loam_b200_destroy(loam_b200_ctx* ctx);
+/* Bind the calling host thread to a CUDA device (cudaSetDevice): every host thread other than the one that created a
+ * context must call this once before using the context (helper threads of the library do so themselves). */
+int loam_b200_bind_thread(int device);
 int loam_b200_sync(loam_b200_ctx* ctx);
 /* cudaStream_t of the context (as void*) so callers can order their own work / time with events */
 void* loam_b200_stream(loam_b200_ctx* ctx);

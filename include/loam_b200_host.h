@@ -103,6 +103,17 @@ int loam_b200_pipeline_sweep_device(void* h, const void* d_pts, const int* ring_
  * (processScanlines(vector<PointCloud>) / cloud Ptr accessors), as separate ROS nodes would use the classes */
 int loam_b200_pipeline_sweep_hostclouds(void* h, const float* pts, const int* ring_sizes, int n_rings, float* odom_sum6,
                                         float* map_aft6, double* stage_seconds);
+/* Streaming form: registration, odometry and mapping run as three concurrent single-threaded stages over consecutive
+ * sweeps -- the way the reference's three ROS nodes run (CMakeLists.txt:40-50) -- connected by the device-to-device
+ * hand-offs; results equal the sequential chain bit for bit.  submit() queues one sweep (host `pts` or device `d_pts`,
+ * the other NULL; the buffer must stay valid until its result has been collected) and blocks only while two sweeps are
+ * already waiting; collect() returns the oldest finished sweep: 1 = result written, 0 = nothing pending (or, with
+ * wait == 0, nothing ready yet), -1 = a stage failed (loam_b200_host_last_error).  Do not mix with the _sweep calls
+ * while sweeps are in flight. */
+int loam_b200_pipeline_submit(void* h, const float* pts, const void* d_pts, const int* ring_sizes, int n_rings);
+int loam_b200_pipeline_collect(void* h, int wait, float* odom_sum6, float* map_aft6, int* ok);
+/* wait until everything the three stage objects enqueued (or posted to their helper threads) has finished on the GPU */
+int loam_b200_pipeline_sync(void* h);
 void* loam_b200_pipeline_scanreg(void* h);
 void* loam_b200_pipeline_odom(void* h);
 void* loam_b200_pipeline_map(void* h);

@@ -94,6 +94,7 @@ def lib():
         "loam_b200_create": (C.c_int, [C.POINTER(vp), C.c_int]),
         "loam_b200_destroy": (C.c_int, [vp]),
         "loam_b200_sync": (C.c_int, [vp]),
+        "loam_b200_bind_thread": (C.c_int, [C.c_int]),
         "loam_b200_stream": (vp, [vp]),
         "loam_b200_extract_features": (C.c_int, [vp, _F, C.c_int, _I, _I, C.c_int, C.POINTER(RegParams),
                                                  C.POINTER(Features)]),
@@ -188,6 +189,9 @@ def lib():
         "loam_b200_pipeline_sweep": (C.c_int, [vp, _F, _I, C.c_int, _F, _F, _D]),
         "loam_b200_pipeline_sweep_device": (C.c_int, [vp, vp, _I, C.c_int, _F, _F, _D]),
         "loam_b200_pipeline_sweep_hostclouds": (C.c_int, [vp, _F, _I, C.c_int, _F, _F, _D]),
+        "loam_b200_pipeline_submit": (C.c_int, [vp, _F, vp, _I, C.c_int]),
+        "loam_b200_pipeline_collect": (C.c_int, [vp, C.c_int, _F, _F, _I]),
+        "loam_b200_pipeline_sync": (C.c_int, [vp]),
         "loam_b200_pipeline_scanreg": (vp, [vp]),
         "loam_b200_pipeline_odom": (vp, [vp]),
         "loam_b200_pipeline_map": (vp, [vp]),
@@ -627,6 +631,56 @@ class Pipeline(_Handle):
                                                              _fp(odom), _fp(aft), st.ctypes.data_as(_D)),
                       "pipeline_sweep_device")
         return bool(ok), odom, aft, st
+
+
+    def sync(self):
+        """Everything enqueued by the three stages (helper threads included) has finished on the GPU."""
+        self._ck(self.L.loam_b200_pipeline_sync(self.h), "pipeline_sync")
+
+    # ---- streaming form: the three stages run concurrently on consecutive sweeps (include/loam_b200_host.h)
+    def submit(self, pts=None, ring_sizes=None, device_ptr=None):
+        """Queue one sweep (host array `pts` or `device_ptr`); the buffer must stay alive until collected."""
+        rs = np.ascontiguousarray(ring_sizes, dtype=np.int32)
+        if device_ptr is None:
+            pts = _pts(pts)
+            self._keep = getattr(self, "_keep", [])
+            self._keep.append(pts)
+            rc = self.L.loam_b200_pipeline_submit(self.h, _fp(pts), None, _ip(rs), rs.shape[0])
+        else:
+            rc = self.L.loam_b200_pipeline_submit(self.h, None, C.c_void_p(device_ptr), _ip(rs), rs.shape[0])
+        self._ck(rc, "pipeline_submit")
+
+    def collect(self, wait=True):
+        """Oldest finished sweep -> (ok, odom_sum6, map_aft6), or None when nothing is pending / ready."""
+        odom = np.empty(6, np.float32)
+        aft = np.empty(6, np.float32)
+        ok = C.c_int(0)
+        rc = self._ck(self.L.loam_b200_pipeline_collect(self.h, 1 if wait else 0, _fp(odom), _fp(aft), C.byref(ok)),
+                      "pipeline_collect")
+        if rc == 0:
+            return None
+        if getattr(self, "_keep", None):
+            self._keep.pop(0)
+        return bool(ok.value), odom, aft
+
+    def run_stream(self, sweeps=None, device_ptrs=None):
+        """Submit every sweep, collect every result (in order) -> list of (ok, odom_sum6, map_aft6)."""
+        res = []
+        n = len(sweeps)
+        for i in range(n):
+            if device_ptrs is not None:
+                self.submit(ring_sizes=sweeps[i][1], device_ptr=device_ptrs[i])
+            else:
+                self.submit(sweeps[i][0], sweeps[i][1])
+            r = self.collect(wait=False)
+            if r is not None:
+                res.append(r)
+        while len(res) < n:
+            r = self.collect(wait=True)
+            if r is None:
+                break
+            res.append(r)
+        return res
 
 
 def transform_maintenance(sum6, bef6, aft6):

@@ -121,6 +121,24 @@ struct Grid {            // uniform 1 m grid over a map cloud (gridnn.cuh)
   DevBuf<GridMetaHost> meta;
 };
 
+// pre-instantiated CUDA graph of a device-resident Gauss-Newton loop: gate kernel -> WHILE { iteration kernels, step }
+struct LoopGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long handle = 0;  // cudaGraphConditionalHandle of the WHILE node
+  int cap_a = 0, cap_b = 0;       // query capacities (corner-like, surface-like) the kernel grids were sized for
+  int variant = -1;               // which kernel instantiation the body holds
+  const void* baked[4] = {nullptr, nullptr, nullptr, nullptr};  // device buffers whose addresses sit in the nodes
+  long long builds = 0;
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr;
+    graph = nullptr;
+    handle = 0;
+  }
+};
+
 struct SortScratch {
   DevBuf<uint32_t> keys_a, keys_b;
   DevBuf<int> vals_a, vals_b;
@@ -201,6 +219,7 @@ struct loam_b200_ctx {
   loamb::PinBuf<int> ring_table_host;
   loamb::DevBuf<float> bin_xyz;           // raw xyz of the ring-binning front end (frontend.cuh)
   loamb::DevBuf<unsigned char> lm_state;  // OdomLmState + MapLmState (lmstep.cuh): pose of the device-resident loops
+  loamb::LoopGraph odom_loop, map_loop;   // their loop graphs (loam_b200_odom_solve / loam_b200_map_solve)
 
   // odometry
   loamb::DevBuf<float4> od_q;  // sharp then flat

@@ -101,7 +101,7 @@ void GaussNewtonSolver::solve(const loam_b200_normal_eq& ne, bool firstIteration
 bool deviceResidentLoops() {
   static const bool on = [] {
     const char* e = std::getenv("LOAM_B200_DEVICE_LOOP");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   return on;
 }

@@ -124,9 +124,9 @@ struct GaussNewtonSolver {
   void solve(const loam_b200_normal_eq& ne, bool firstIteration, float eigenThreshold, float x[6]);
 };
 
-// LOAM_B200_DEVICE_LOOP=1: run the Gauss-Newton loops through loam_b200_odom_solve / loam_b200_map_solve (pose kept on
-// the device, csrc/lmstep.cuh) instead of one kernel + host solve per iteration.  Off by default: on B200 the one-warp
-// step kernel (~15 us) costs more than the 128-byte readback + host solve it replaces.
+// The Gauss-Newton loops run through loam_b200_odom_solve / loam_b200_map_solve: pose kept on the device, the whole loop
+// one launch of a CUDA graph with a WHILE node (csrc/lmstep.cuh, loam_b200.cu), one host round trip per loop.
+// LOAM_B200_DEVICE_LOOP=0 selects the round-1 form (one kernel + host solve per iteration).
 bool deviceResidentLoops();
 
 // host-side pcl::VoxelGrid replacement: one GPU call

@@ -2,9 +2,13 @@
 #include "loam_b200_host.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <exception>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200_runtime.h"
@@ -15,6 +19,7 @@
 
 namespace {
 
+namespace b200 = loam::b200;
 typedef pcl::PointCloud<pcl::PointXYZI> Cloud;
 thread_local std::string g_err;
 
@@ -98,12 +103,177 @@ struct MapH {
     }
   }
 };
+struct StreamRunner;
 struct PipeH {
   RegH reg;
   OdomH odom;
   MapH map;
+  StreamRunner* runner = nullptr;
   PipeH(float sp, int oi, int mi) : odom(sp, oi), map(sp, mi) {}
+  ~PipeH();
 };
+
+// ---- the three stages as three concurrent single-threaded workers over consecutive sweeps ------------------------------
+// This is how the reference is deployed: multiScanRegistration, laserOdometry and laserMapping are separate single-
+// threaded ROS nodes (CMakeLists.txt:40-50), so while laserMapping works on sweep k, laserOdometry works on k + 1 and the
+// registration on k + 2.  Here each stage object has its own context / stream and one host thread; the ROS topics between
+// the nodes (ScanRegistration.cpp:187-199, LaserOdometry.cpp:286-330) are the device-to-device adopt() hand-offs, taken by
+// the consumer while the producer waits (a stage's output clouds are overwritten by its next sweep).  Results are the
+// same as the sequential chain, bit for bit: every stage still sees the sweeps in order and only through the hand-offs.
+struct SweepJob {
+  const float* pts;
+  const void* d_pts;
+  std::vector<int> rings;
+  long id;
+};
+struct SweepResult {
+  long id;
+  int ok;
+  float odom[6], aft[6];
+};
+
+struct StreamRunner {
+  PipeH* p;
+  int device;
+  std::thread th[3];
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<SweepJob> in;
+  std::deque<SweepResult> out;
+  long next_id = 0, reg_done = 0, odom_done = 0, n_submitted = 0, n_finished = 0;
+  bool reg_ready = false, odom_ready = false, stop = false;
+  std::string err;
+  static constexpr size_t MAX_QUEUED = 2;
+
+  explicit StreamRunner(PipeH* pipe) : p(pipe), device(loam::b200::defaultDevice()) {
+    th[0] = std::thread([this] { run(0); });
+    th[1] = std::thread([this] { run(1); });
+    th[2] = std::thread([this] { run(2); });
+  }
+  ~StreamRunner() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+  void fail(const char* what) {
+    std::lock_guard<std::mutex> lk(m);
+    if (err.empty()) err = what;
+    stop = true;
+    cv.notify_all();
+  }
+  void run(int stage) {
+    loam_b200_bind_thread(device);
+    try {
+      if (stage == 0) stage_reg(); else if (stage == 1) stage_odom(); else stage_map();
+    } catch (const std::exception& e) {
+      fail(e.what());
+    } catch (...) {
+      fail("unknown exception in a pipeline stage");
+    }
+  }
+  void stage_reg() {
+    for (;;) {
+      SweepJob job;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        // the previous sweep's clouds must have been taken over before they are overwritten
+        cv.wait(lk, [this] { return stop || (!in.empty() && !reg_ready); });
+        if (stop) return;
+        job = std::move(in.front());
+        in.pop_front();
+      }
+      cv.notify_all();
+      if (job.d_pts)
+        p->reg.r.processDeviceSweep(loam::Time(), job.d_pts, job.rings.data(), (int)job.rings.size());
+      else
+        p->reg.r.processPackedSweep(loam::Time(), job.pts, job.rings.data(), (int)job.rings.size());
+      {
+        std::lock_guard<std::mutex> lk(m);
+        reg_ready = true;
+      }
+      cv.notify_all();
+    }
+  }
+  void stage_odom() {
+    auto& o = p->odom.o;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        // adopt() overwrites the full-resolution cloud the mapping stage takes from this object
+        cv.wait(lk, [this] { return stop || (reg_ready && !odom_ready); });
+        if (stop) return;
+      }
+      o.adopt(p->reg.r);  // the registration thread is parked until reg_ready drops
+      {
+        std::lock_guard<std::mutex> lk(m);
+        reg_ready = false;
+      }
+      cv.notify_all();
+      o.process();
+      o.transformLaserCloudToEnd();
+      {
+        std::lock_guard<std::mutex> lk(m);
+        odom_ready = true;
+      }
+      cv.notify_all();
+    }
+  }
+  void stage_map() {
+    auto& o = p->odom.o;
+    auto& mp = p->map.m;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return stop || odom_ready; });
+        if (stop) return;
+      }
+      SweepResult r;
+      mp.adopt(o);  // the odometry thread is parked until odom_ready drops
+      twist6(o.transformSum(), r.odom);
+      {
+        std::lock_guard<std::mutex> lk(m);
+        odom_ready = false;
+      }
+      cv.notify_all();
+      r.ok = mp.process(loam::Time()) ? 1 : 0;
+      twist6(mp.transformAftMapped(), r.aft);
+      {
+        std::lock_guard<std::mutex> lk(m);
+        r.id = n_finished++;
+        out.push_back(r);
+      }
+      cv.notify_all();
+    }
+  }
+  int submit(const float* pts, const void* d_pts, const int* rings, int n_rings) {
+    SweepJob job{pts, d_pts, std::vector<int>(rings, rings + n_rings), 0};
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this] { return stop || in.size() < MAX_QUEUED; });
+    if (stop) { g_err = err.empty() ? "pipeline stopped" : err; return -1; }
+    job.id = n_submitted++;
+    in.push_back(std::move(job));
+    lk.unlock();
+    cv.notify_all();
+    return 0;
+  }
+  // 1 = a result was returned, 0 = none pending / none ready (wait == 0), -1 = a stage failed
+  int collect(int wait, SweepResult* r) {
+    std::unique_lock<std::mutex> lk(m);
+    if (wait) cv.wait(lk, [this] { return stop || !out.empty() || n_finished == n_submitted; });
+    if (!out.empty()) {
+      *r = out.front();
+      out.pop_front();
+      return 1;
+    }
+    if (!err.empty()) { g_err = err; return -1; }
+    return 0;
+  }
+};
+
+PipeH::~PipeH() { delete runner; }
 
 }  // namespace
 
@@ -338,6 +508,38 @@ int loam_b200_pipeline_sweep_hostclouds(void* hh, const float* pts, const int* r
     if (st) { st[0] = t1 - t0; st[1] = t2 - t1; st[2] = t3 - t2; st[3] = t4 - t3; st[4] = t4 - t0; }
     return ok;
   });
+}
+
+// everything enqueued or posted to helper threads by the three stage objects has finished on the GPU
+int loam_b200_pipeline_sync(void* hh) {
+  return guarded([&] {
+    PipeH* h = (PipeH*)hh;
+    b200::Context* cs[3] = {h->reg.r.deviceContext(), h->odom.o.deviceContext(), h->map.m.deviceContext()};
+    for (auto* c : cs)
+      if (c->created()) c->check(loam_b200_sync(c->get()), "loam_b200_sync");
+    return 0;
+  });
+}
+
+// ---- streaming form: the three stages work on consecutive sweeps concurrently (StreamRunner above) ----
+int loam_b200_pipeline_submit(void* hh, const float* pts, const void* d_pts, const int* ring_sizes, int n_rings) {
+  PipeH* h = (PipeH*)hh;
+  if (!h || (!pts && !d_pts) || !ring_sizes || n_rings <= 0) { g_err = "invalid argument"; return -1; }
+  if (!h->runner) h->runner = new StreamRunner(h);
+  return h->runner->submit(pts, d_pts, ring_sizes, n_rings);
+}
+
+int loam_b200_pipeline_collect(void* hh, int wait, float* odom_sum6, float* map_aft6, int* ok) {
+  PipeH* h = (PipeH*)hh;
+  if (!h || !h->runner) return 0;
+  SweepResult r;
+  const int rc = h->runner->collect(wait, &r);
+  if (rc == 1) {
+    if (odom_sum6) std::memcpy(odom_sum6, r.odom, sizeof r.odom);
+    if (map_aft6) std::memcpy(map_aft6, r.aft, sizeof r.aft);
+    if (ok) *ok = r.ok;
+  }
+  return rc;
 }
 
 }  // extern "C"

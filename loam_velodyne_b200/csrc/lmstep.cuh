@@ -103,7 +103,25 @@ struct LmHeader {
   int iter;       // index of the next iteration
   int done;       // converged or iteration cap reached
   int iters_run;  // the reference's iterCount + 1 of the last executed iteration
-  int pad[3];
+  int mb_seq;     // sequence number the finished loop posts into the host mailbox (0 = none)
+  int pad[2];
 };
+
+#if defined(__CUDACC__)
+// Loop control of the device-resident Gauss-Newton loops.  The loop itself is a CUDA-graph WHILE node whose body holds
+// the iteration kernels; `handle` is its condition (0 = the kernels were launched outside a graph: nothing to set).
+// When the loop ends the 9 header words go to the mapped host mailbox followed by the sequence word the host spins on
+// (one PCIe round trip per LOOP instead of one per iteration).
+__device__ inline void lm_loop_control(const LmHeader& h, unsigned long long handle, float* mailbox_host) {
+  if (handle) cudaGraphSetConditional((cudaGraphConditionalHandle)handle, h.done ? 0u : 1u);
+  if (h.done && mailbox_host && h.mb_seq) {
+    const int* w = reinterpret_cast<const int*>(&h);
+    volatile int* o = reinterpret_cast<volatile int*>(mailbox_host);
+    for (int i = 0; i < 9; i++) o[i] = w[i];
+    __threadfence_system();
+    o[32] = h.mb_seq;
+  }
+}
+#endif
 
 }  // namespace loamb

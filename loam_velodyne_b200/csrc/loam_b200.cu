@@ -551,6 +551,8 @@ int loam_b200_destroy(loam_b200_ctx* c) {
     st.table.release(); st.cube_stats.release(); st.valid_by_slot.release(); st.s_pts.release(); st.e_pts.release();
     st.e_state.release(); st.e_keys.release(); st.e_vals.release();
   }
+  c->odom_loop.destroy();
+  c->map_loop.destroy();
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->od_ring_off[1].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
@@ -561,9 +563,20 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   return LOAM_B200_OK;
 }
 
+int loam_b200_bind_thread(int device) {
+  if (device < 0 || cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    return LOAM_B200_ERR_NO_DEVICE;
+  }
+  return LOAM_B200_OK;
+}
+
 int loam_b200_sync(loam_b200_ctx* c) {
   CHECK_CTX(c);
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& l : c->lanes)
+    if (l.stream) LB_CUDA(c, cudaStreamSynchronize(l.stream));
+  if (c->aux) return loam_b200_sync(c->aux);  // asynchronous surround cloud
   return LOAM_B200_OK;
 }
 
@@ -953,15 +966,78 @@ int loam_b200_odom_iterate_debug(loam_b200_ctx* c, const loam_b200_odom_pose* po
 }
 
 // ------------------------------------------------------------------------------------------------ device-resident loops
-// Whole Gauss-Newton loops with the pose kept on the device (lmstep.cuh).  Iteration kernels are enqueued in chunks;
-// after a chunk the 48-byte header of the state block is read back once.  Kernels behind the converged iteration return
-// immediately.  Not available with a communicator (the all-reduce sits between kernel and solve): ERR_STATE.
+// Whole Gauss-Newton loops with the pose kept on the device (lmstep.cuh).  The loop is ONE launch of a pre-instantiated
+// CUDA graph: a gate kernel, then a WHILE conditional node whose body holds the iteration kernels and the one-warp step
+// kernel; the step kernel clears the condition when the loop has converged (cudaGraphSetConditional) and posts the final
+// pose into the mapped host mailbox, so the host pays one round trip per loop instead of one per iteration
+// (tools/probes/loop_overheads.cu: 2.3 us per WHILE iteration + 1.2 us per kernel node on B200, against ~12 us per host
+// round trip).  What a sweep changes (clouds, counts, pose) is written into the state block by the init kernel, so the
+// graph is only rebuilt when a capacity or a baked buffer address changes.  With a communicator the all-reduce sits
+// between iteration kernel and step: that mode keeps stream launches in chunks (map_solve_chunked).
 static int lm_read_header(loam_b200_ctx* c, const void* d_state, LmHeader* h) {
   LB_CUDA(c, c->result_host.reserve(NEQ));
   LB_CUDA(c, cudaMemcpyAsync(c->result_host.p, d_state, sizeof(LmHeader), cudaMemcpyDeviceToHost, c->stream));
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
   memcpy(h, c->result_host.p, sizeof(LmHeader));
   return LOAM_B200_OK;
+}
+
+// wait for the loop's final header in the mailbox (see fetch_normal_eq_mailbox)
+static int lm_wait_mailbox(loam_b200_ctx* c, LmHeader* h) {
+  volatile int* box = reinterpret_cast<volatile int*>(c->result_mailbox.p);
+  const auto t0 = std::chrono::steady_clock::now();
+  long long spins = 0;
+  while (box[32] != c->result_seq) {
+    if ((++spins & 0xfff) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) {
+      LB_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (box[32] != c->result_seq) return LOAM_B200_ERR_CUDA;
+      break;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  int* w = reinterpret_cast<int*>(h);
+  for (int i = 0; i < 9; i++) w[i] = box[i];
+  return LOAM_B200_OK;
+}
+
+static int round_cap(int n) { return ((n + n / 4 + 255) / 256) * 256; }  // 25 % head room, multiples of 256 queries
+
+// (re)build a loop graph: `launch_gate` and `launch_body` enqueue their kernels on c->stream (captured, not run)
+extern "C++" {
+template <typename GATE, typename BODY>
+static int loop_graph_build(loam_b200_ctx* c, LoopGraph& lg, GATE launch_gate, BODY launch_body) {
+  lg.destroy();
+  LB_CUDA(c, cudaGraphCreate(&lg.graph, 0));
+  cudaGraphConditionalHandle handle;
+  LB_CUDA(c, cudaGraphConditionalHandleCreate(&handle, lg.graph, 1, cudaGraphCondAssignDefault));
+  lg.handle = (unsigned long long)handle;
+  LB_CUDA(c, cudaStreamBeginCaptureToGraph(c->stream, lg.graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  launch_gate();
+  cudaGraph_t same = nullptr;
+  LB_CUDA(c, cudaStreamEndCapture(c->stream, &same));
+  cudaGraphNode_t gate_node = nullptr;
+  size_t n_nodes = 1;
+  LB_CUDA(c, cudaGraphGetNodes(lg.graph, &gate_node, &n_nodes));
+  cudaGraphNodeParams wp = {};
+  wp.type = cudaGraphNodeTypeConditional;
+  wp.conditional.handle = handle;
+  wp.conditional.type = cudaGraphCondTypeWhile;
+  wp.conditional.size = 1;
+  cudaGraphNode_t while_node = nullptr;
+  LB_CUDA(c, cudaGraphAddNode(&while_node, lg.graph, &gate_node, 1, &wp));
+  cudaGraph_t body = wp.conditional.phGraph_out[0];
+  LB_CUDA(c, cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  launch_body();
+  LB_CUDA(c, cudaStreamEndCapture(c->stream, &same));
+  LB_CUDA(c, cudaGraphInstantiate(&lg.exec, lg.graph, 0));
+  lg.builds++;
+  return LOAM_B200_OK;
+}
+}  // extern "C++"
+
+static bool loop_graphs_enabled() {
+  static const bool off = getenv("LOAM_B200_NO_LOOP_GRAPH") != nullptr;
+  return !off;
 }
 
 int loam_b200_odom_solve(loam_b200_ctx* c, const float rot[3], const float pos[3], float inv_scan_period, int max_iterations,
@@ -976,41 +1052,80 @@ int loam_b200_odom_solve(loam_b200_ctx* c, const float rot[3], const float pos[3
   if (nsh + nfl == 0 || max_iterations == 0) return LOAM_B200_OK;
   const Tree& tc = c->tree[LOAM_B200_TREE_ODOM_CORNER];
   const Tree& ts = c->tree[LOAM_B200_TREE_ODOM_SURF];
+  const bool use_graph = loop_graphs_enabled();
+  LoopGraph& lg = c->odom_loop;
+  const int cap_sh = use_graph ? std::max(lg.cap_a, nsh > lg.cap_a ? round_cap(nsh) : 0) : nsh;
+  const int cap_fl = use_graph ? std::max(lg.cap_b, nfl > lg.cap_b ? round_cap(nfl) : 0) : nfl;
   const int cb = blocks_for(nsh, LM_THREADS), sb = blocks_for(nfl, LM_THREADS);
   const int nb = cb + sb;
-  LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
+  const int nb_cap = blocks_for(cap_sh, LM_THREADS) + blocks_for(cap_fl, LM_THREADS);
+  LB_CUDA(c, c->partials.reserve((size_t)std::max(nb, nb_cap) * NEQ));
   LB_CUDA(c, c->lm_state.reserve(sizeof(OdomLmState) + sizeof(MapLmState)));
   OdomLmState* st = reinterpret_cast<OdomLmState*>(c->lm_state.p);
+  const bool use_mailbox = !c->prof_on && !getenv_no_mailbox() && c->result_mailbox.reserve(64) == cudaSuccess;
+  int seq = 0;
+  if (use_mailbox) seq = next_mailbox(c).seq;
+  OdomLoopIo io;
+  io.corner_tree = view_of(tc); io.surf_tree = view_of(ts);
+  io.last_corner = tc.points(); io.last_surf = ts.points(); io.queries = c->od_q.p; io.ind = c->od_ind.p;
+  io.ring_off_corner = c->od_ring_off[0].p; io.ring_off_surf = c->od_ring_off[1].p;
+  io.n_sharp = nsh; io.n_flat = nfl; io.sharp_blocks = cb; io.n_blocks = nb;
   odom_lm_init_kernel<<<1, 32, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], inv_scan_period,
-                                               delta_t_abort, delta_r_abort, max_iterations, tc.m, ts.m);
+                                               delta_t_abort, delta_r_abort, max_iterations, tc.m, ts.m, io, seq);
   LB_LAUNCH_CHECK(c);
   const OdomIterArgs unused{};
+  const TreeView tv0{};
   LmHeader h{};
   prof_begin(c, LOAM_B200_K_ODOM_ITER);
-  for (int it = 0; it < max_iterations;) {
-    const int chunk_end = std::min(max_iterations, it + 5);  // one correspondence search per chunk
-    for (; it < chunk_end; it++) {
-      if (it % 5 == 0) {
-        odom_search_kernel<true><<<blocks_for((long long)(nsh + nfl) * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
-            view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, unused, c->od_ind.p, st,
-            c->od_ring_off[0].p, c->od_ring_off[1].p);
+  if (use_graph) {
+    const void* baked[4] = {st, c->partials.p, c->result.p, use_mailbox ? (void*)c->result_mailbox.p : nullptr};
+    if (!lg.exec || lg.cap_a != cap_sh || lg.cap_b != cap_fl || memcmp(lg.baked, baked, sizeof baked) != 0) {
+      float* mbp = use_mailbox ? c->result_mailbox.p : nullptr;
+      unsigned long long* hp = &lg.handle;
+      const int rc = loop_graph_build(
+          c, lg, [&] { lm_gate_kernel<<<1, 32, 0, c->stream>>>(&st->h, *hp, mbp); },
+          [&] {
+            odom_search_kernel<true><<<blocks_for((long long)(cap_sh + cap_fl) * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
+                tv0, tv0, nullptr, nullptr, nullptr, 0, 0, unused, nullptr, st, nullptr, nullptr);
+            odom_iterate_kernel<true><<<nb_cap, LM_THREADS, 0, c->stream>>>(tv0, tv0, nullptr, nullptr, nullptr, 0, 0, 0, unused,
+                                                                         nullptr, c->partials.p, c->result.p, c->ticket.p,
+                                                                         nullptr, nullptr, st);
+            odom_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p, *hp, mbp);
+          });
+      if (rc) return rc;
+      lg.cap_a = cap_sh; lg.cap_b = cap_fl;
+      memcpy(lg.baked, baked, sizeof baked);
+    }
+    LB_CUDA(c, cudaGraphLaunch(lg.exec, c->stream));
+    const int rc = use_mailbox ? lm_wait_mailbox(c, &h) : lm_read_header(c, st, &h);
+    if (rc) return rc;
+    // gate + per executed iteration: search (a no-op except every 5th), iterate, step -- launched by the WHILE node
+    c->launches += 1 + 3 * h.iters_run;
+    g_total_launches.fetch_add(1 + 3 * h.iters_run, std::memory_order_relaxed);
+  } else {
+    for (int it = 0; it < max_iterations;) {
+      const int chunk_end = std::min(max_iterations, it + 5);  // one correspondence search per chunk
+      for (; it < chunk_end; it++) {
+        if (it % 5 == 0) {
+          odom_search_kernel<true><<<blocks_for((long long)(nsh + nfl) * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
+              tv0, tv0, nullptr, nullptr, nullptr, 0, 0, unused, nullptr, st, nullptr, nullptr);
+          LB_LAUNCH_CHECK(c);
+        }
+        odom_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(tv0, tv0, nullptr, nullptr, nullptr, 0, 0, 0, unused, nullptr,
+                                                                  c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, st);
+        LB_LAUNCH_CHECK(c);
+        odom_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p);
         LB_LAUNCH_CHECK(c);
       }
-      odom_iterate_kernel<true><<<nb, LM_THREADS, 0, c->stream>>>(view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p,
-                                                            nsh, nfl, cb, unused, c->od_ind.p, c->partials.p, c->result.p,
-                                                            c->ticket.p, nullptr, nullptr, st);
-      LB_LAUNCH_CHECK(c);
-      odom_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p);
-      LB_LAUNCH_CHECK(c);
+      const int rc = lm_read_header(c, st, &h);
+      if (rc) return rc;
+      if (h.done) break;
     }
-    const int rc = lm_read_header(c, st, &h);
-    if (rc) return rc;
-    if (h.done) break;
   }
   prof_end(c);
   for (int i = 0; i < 3; i++) { out->rot[i] = h.rot[i]; out->pos[i] = h.pos[i]; }
   out->iterations = h.iters_run;
-  out->converged = h.done && h.iter < max_iterations ? 1 : (h.done ? 1 : 0);
+  out->converged = h.done ? 1 : 0;
   return LOAM_B200_OK;
 }
 
@@ -1030,37 +1145,84 @@ int loam_b200_map_solve(loam_b200_ctx* c, const float rot[3], const float pos[3]
   const int lc = c1 - c0, ls = s1 - s0;
   const int cb = blocks_for(lc, MAP_Q_PER_BLOCK), sb = blocks_for(ls, MAP_Q_PER_BLOCK);
   const int nb = std::max(cb + sb, 1);
-  LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
+  const bool use_graph = loop_graphs_enabled() && !c->comm;
+  LoopGraph& lg = c->map_loop;
+  const int cap_c = use_graph ? std::max(lg.cap_a, lc > lg.cap_a ? round_cap(lc) : 0) : lc;
+  const int cap_s = use_graph ? std::max(lg.cap_b, ls > lg.cap_b ? round_cap(ls) : 0) : ls;
+  const int nb_cap = std::max(blocks_for(cap_c, MAP_Q_PER_BLOCK) + blocks_for(cap_s, MAP_Q_PER_BLOCK), 1);
+  LB_CUDA(c, c->partials.reserve((size_t)std::max(nb, nb_cap) * NEQ));
   LB_CUDA(c, c->lm_state.reserve(sizeof(OdomLmState) + sizeof(MapLmState)));
   MapLmState* st = reinterpret_cast<MapLmState*>(c->lm_state.p + sizeof(OdomLmState));
-  map_lm_init_kernel<<<1, 32, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], delta_t_abort,
-                                              delta_r_abort, max_iterations);
+  const bool use_mailbox = use_graph && !c->prof_on && !getenv_no_mailbox() && c->result_mailbox.reserve(64) == cudaSuccess;
+  int seq = 0;
+  if (use_mailbox) seq = next_mailbox(c).seq;
+  MapLoopIo io;
+  memset(&io, 0, sizeof io);
+  if (c->map_use_store) {
+    const MapCellLookup l0 = store_lookup_of(c, 0), l1 = store_lookup_of(c, 1);
+    memcpy(io.lookup[0], &l0, sizeof l0);
+    memcpy(io.lookup[1], &l1, sizeof l1);
+  } else {
+    const GridCellLookup l0{grid_view_of(c->grid[0])}, l1{grid_view_of(c->grid[1])};
+    memcpy(io.lookup[0], &l0, sizeof l0);
+    memcpy(io.lookup[1], &l1, sizeof l1);
+  }
+  io.queries = c->map_q.p; io.n_corner_total = nc; io.c0 = c0; io.n_corner = lc; io.s0 = s0; io.n_surf = ls;
+  io.corner_blocks = cb; io.n_blocks = nb;
+  map_lm_init_kernel<<<1, 128, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], delta_t_abort,
+                                               delta_r_abort, max_iterations, io, seq);
   LB_LAUNCH_CHECK(c);
   const MapIterArgs unused{};
   LmHeader h{};
   prof_begin(c, LOAM_B200_K_MAP_ITER);
-  for (int it = 0; it < max_iterations;) {
-    const int chunk_end = std::min(max_iterations, it + 3);  // 2-3 iterations is the usual case
-    for (; it < chunk_end; it++) {
-      if (c->map_use_store)
-        map_iterate_kernel<false, MapCellLookup, true><<<nb, MAP_THREADS, 0, c->stream>>>(
-            store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, unused, c->partials.p,
-            c->result.p, c->ticket.p, nullptr, nullptr, nullptr, st);
-      else
-        map_iterate_kernel<false, GridCellLookup, true><<<nb, MAP_THREADS, 0, c->stream>>>(
-            GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
-            cb, unused, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, nullptr, st);
-      LB_LAUNCH_CHECK(c);
-      {
-        const int rcc = allreduce_result(c);  // no-op without a communicator; every rank then takes the same step
-        if (rcc) return rcc;
-      }
-      map_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p);
-      LB_LAUNCH_CHECK(c);
+  auto launch_iterate = [&](int grid) {
+    if (c->map_use_store)
+      map_iterate_kernel<false, MapCellLookup, true><<<grid, MAP_THREADS, 0, c->stream>>>(
+          MapCellLookup{}, MapCellLookup{}, nullptr, 0, 0, 0, 0, 0, 0, unused, c->partials.p, c->result.p, c->ticket.p, nullptr,
+          nullptr, nullptr, st);
+    else
+      map_iterate_kernel<false, GridCellLookup, true><<<grid, MAP_THREADS, 0, c->stream>>>(
+          GridCellLookup{}, GridCellLookup{}, nullptr, 0, 0, 0, 0, 0, 0, unused, c->partials.p, c->result.p, c->ticket.p, nullptr,
+          nullptr, nullptr, st);
+  };
+  if (use_graph) {
+    const int variant = c->map_use_store ? 1 : 0;
+    const void* baked[4] = {st, c->partials.p, c->result.p, use_mailbox ? (void*)c->result_mailbox.p : nullptr};
+    if (!lg.exec || lg.cap_a != cap_c || lg.cap_b != cap_s || lg.variant != variant || memcmp(lg.baked, baked, sizeof baked) != 0) {
+      float* mbp = use_mailbox ? c->result_mailbox.p : nullptr;
+      unsigned long long* hp = &lg.handle;
+      const int rc = loop_graph_build(
+          c, lg, [&] { lm_gate_kernel<<<1, 32, 0, c->stream>>>(&st->h, *hp, mbp); },
+          [&] {
+            launch_iterate(nb_cap);
+            map_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p, *hp, mbp);
+          });
+      if (rc) return rc;
+      lg.cap_a = cap_c; lg.cap_b = cap_s; lg.variant = variant;
+      memcpy(lg.baked, baked, sizeof baked);
     }
-    const int rc = lm_read_header(c, st, &h);
+    LB_CUDA(c, cudaGraphLaunch(lg.exec, c->stream));
+    const int rc = use_mailbox ? lm_wait_mailbox(c, &h) : lm_read_header(c, st, &h);
     if (rc) return rc;
-    if (h.done) break;
+    c->launches += 1 + 2 * h.iters_run;  // gate + (iterate, step) per executed iteration
+    g_total_launches.fetch_add(1 + 2 * h.iters_run, std::memory_order_relaxed);
+  } else {
+    for (int it = 0; it < max_iterations;) {
+      const int chunk_end = std::min(max_iterations, it + 3);  // 2-3 iterations is the usual case
+      for (; it < chunk_end; it++) {
+        launch_iterate(nb);
+        LB_LAUNCH_CHECK(c);
+        {
+          const int rcc = allreduce_result(c);  // no-op without a communicator; every rank then takes the same step
+          if (rcc) return rcc;
+        }
+        map_lm_step_kernel<<<1, 32, 0, c->stream>>>(st, c->result.p);
+        LB_LAUNCH_CHECK(c);
+      }
+      const int rc = lm_read_header(c, st, &h);
+      if (rc) return rc;
+      if (h.done) break;
+    }
   }
   prof_end(c);
   for (int i = 0; i < 3; i++) { out->rot[i] = h.rot[i]; out->pos[i] = h.pos[i]; }

@@ -52,15 +52,30 @@ LOAMB_HD inline void map_args_from(const float sin_[3], const float cos_[3], con
 }
 
 // ---- device-resident Gauss-Newton loop (lmstep.cuh)
+// what the iteration kernel of the device-resident loop works on (see OdomLoopIo); the two cell lookups are stored as
+// raw bytes because their type depends on the search structure in use (MapCellLookup / GridCellLookup)
+constexpr int MAP_LOOKUP_BYTES = 128;
+struct MapLoopIo {
+  alignas(16) unsigned char lookup[2][MAP_LOOKUP_BYTES];
+  const float4* queries;
+  int n_corner_total, c0, n_corner, s0, n_surf, corner_blocks, n_blocks;
+  int min_corner_map, min_surf_map;  // sizes of the from-map clouds (the <= 10 / <= 100 gate is evaluated by the host)
+};
 struct MapLmState {
   LmHeader h;
   GnState gn;
   float delta_t_abort, delta_r_abort;
   int max_iter;
   MapIterArgs args;  // arguments of iteration h.iter
+  MapLoopIo io;
 };
 
 #if defined(__CUDACC__)
+// first node of the loop graph: the WHILE condition for iteration 0 (a loop with nothing to do posts at once)
+__global__ void lm_gate_kernel(const LmHeader* h, unsigned long long handle, float* mailbox_host) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) lm_loop_control(*h, handle, mailbox_host);
+}
+
 __device__ inline void map_lm_refresh_args(MapLmState* st) {
   float sn[3], cs[3];
   for (int i = 0; i < 3; i++) {
@@ -75,8 +90,11 @@ __device__ inline void map_lm_refresh_args(MapLmState* st) {
 }
 
 __global__ void map_lm_init_kernel(MapLmState* st, float rx, float ry, float rz, float tx, float ty, float tz,
-                                   float delta_t_abort, float delta_r_abort, int max_iter) {
+                                   float delta_t_abort, float delta_r_abort, int max_iter, MapLoopIo io, int mb_seq) {
+  if (threadIdx.x < (int)(sizeof(MapLoopIo) / 4) && blockIdx.x == 0)
+    reinterpret_cast<int*>(&st->io)[threadIdx.x] = reinterpret_cast<const int*>(&io)[threadIdx.x];
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->h.mb_seq = mb_seq;
   st->h.rot[0] = rx; st->h.rot[1] = ry; st->h.rot[2] = rz;
   st->h.pos[0] = tx; st->h.pos[1] = ty; st->h.pos[2] = tz;
   st->h.iter = 0;
@@ -273,7 +291,7 @@ __device__ __forceinline__ void mailbox_post_seq(const ResultMailbox& mb) {
 // order (double accumulation) into result[NEQ] and resets the ticket for the next launch.
 __device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __restrict__ partials,
                                                         float* __restrict__ result, unsigned int* ticket,
-                                                        ResultMailbox mb = ResultMailbox{nullptr, 0}) {
+                                                        ResultMailbox mb, unsigned n_blocks) {
   __shared__ float s_part[LM_THREADS / 32][NEQ];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -293,7 +311,7 @@ __device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __res
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == n_blocks - 1);
   __syncthreads();
   if (s_last) {
     __threadfence();
@@ -302,7 +320,7 @@ __device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __res
     __shared__ double s_fold[LM_THREADS / 32][NEQ];
     {
       double v = 0.0;
-      for (unsigned bk = warp; bk < gridDim.x; bk += LM_THREADS / 32) v += (double)__ldcg(&partials[(size_t)bk * NEQ + lane]);
+      for (unsigned bk = warp; bk < n_blocks; bk += LM_THREADS / 32) v += (double)__ldcg(&partials[(size_t)bk * NEQ + lane]);
       s_fold[warp][lane] = v;
     }
     __syncthreads();
@@ -333,7 +351,7 @@ static_assert(MAP_Q_PER_BLOCK == 32, "the fit phase maps one query to one lane o
 // registers the 8-lane kernel ran 1.06 waves: half of the kernel's time was a second wave of 63 CTAs).
 template <bool STATS, typename LOOKUP, bool DEVLOOP = false>
 __global__ void __launch_bounds__(MAP_THREADS, 4)
-map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restrict__ queries, int n_corner_total,
+map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, int n_corner_total,
                    int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a_param,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
@@ -343,10 +361,21 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
   // (staged in shared memory; the by-value `a_param` of the per-iteration API stays in the constant bank), and there
   // is nothing to do once the loop has converged
   __shared__ MapIterArgs s_args;
+  __shared__ alignas(16) unsigned char s_lookup[DEVLOOP ? MAP_LOOKUP_BYTES : 16];
+  unsigned n_blocks = gridDim.x;
   if (DEVLOOP) {
     if (lm->h.done) return;
+    const MapLoopIo& io = lm->io;  // uniform loads; the grid of the loop graph is sized for a capacity
+    n_blocks = (unsigned)io.n_blocks;
+    if (blockIdx.x >= n_blocks) return;
     if (threadIdx.x < (int)(sizeof(MapIterArgs) / 4))
       reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
+    queries = io.queries; n_corner_total = io.n_corner_total; c0 = io.c0; n_corner = io.n_corner; s0 = io.s0;
+    n_surf = io.n_surf; corner_blocks = io.corner_blocks;
+    static_assert(sizeof(LOOKUP) <= MAP_LOOKUP_BYTES, "lookup does not fit its slot in MapLoopIo");
+    const int kind = (int)blockIdx.x < corner_blocks ? 0 : 1;
+    if (threadIdx.x < (int)((sizeof(LOOKUP) + 3) / 4))
+      reinterpret_cast<unsigned*>(s_lookup)[threadIdx.x] = reinterpret_cast<const unsigned*>(io.lookup[kind])[threadIdx.x];
     __syncthreads();
   }
   const MapIterArgs& a = DEVLOOP ? s_args : a_param;
@@ -362,7 +391,8 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
   const int n_kind = is_corner ? n_corner : n_surf;
   // this rank's slice: corners [c0, c0 + n_corner), surfaces [s0, s0 + n_surf) (the whole range on one GPU)
   const int q_base = is_corner ? c0 : n_corner_total + s0;
-  LOOKUP grid = is_corner ? corner_grid : surf_grid;  // cell -> run of map points (gridnn.cuh / mapstore.cuh)
+  // cell -> run of map points (gridnn.cuh / mapstore.cuh)
+  LOOKUP grid = DEVLOOP ? *reinterpret_cast<const LOOKUP*>(s_lookup) : (is_corner ? corner_grid : surf_grid);
 
   {  // ---- search: 8 lanes per query
     const int g = threadIdx.x / MAP_GROUP;
@@ -455,7 +485,7 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
     __stcg(&partials[(size_t)blockIdx.x * NEQ + lane], mine);
     __threadfence();
     __syncwarp();
-    if (lane == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (lane == 0) s_last = (atomicAdd(ticket, 1u) == n_blocks - 1);
   }
   __syncthreads();
   if (s_last) {
@@ -464,7 +494,7 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
     __threadfence();
     __shared__ double s_fold[MAP_THREADS / 32][NEQ];
     constexpr unsigned NW = MAP_THREADS / 32;
-    const unsigned nb = gridDim.x;
+    const unsigned nb = n_blocks;
     double v = 0.0;
     unsigned bk = warp;
     for (; bk + 7 * NW < nb; bk += 8 * NW) {
@@ -489,9 +519,15 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* __restric
   }
 }
 
-__global__ void map_lm_step_kernel(MapLmState* st, const float* __restrict__ result) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || st->h.done) return;
-  map_lm_step(st, result);
+__global__ void map_lm_step_kernel(MapLmState* st, const float* __restrict__ result, unsigned long long handle = 0ull,
+                                   float* mailbox_host = nullptr) {
+  __shared__ float s_r[NEQ];  // see odom_lm_step_kernel
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < NEQ) s_r[threadIdx.x] = __ldcg(&result[threadIdx.x]);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (!st->h.done) map_lm_step(st, s_r);
+  lm_loop_control(st->h, handle, mailbox_host);
 }
 
 }  // namespace loamb

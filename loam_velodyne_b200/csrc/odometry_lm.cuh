@@ -71,12 +71,25 @@ __device__ __forceinline__ void sincos_f(float a, float& s, float& c) {
 }
 
 // ---- device-resident Gauss-Newton loop (lmstep.cuh): state block + the step the last CTA of an iteration runs
+// what the iteration kernels of the device-resident loop work on: written once per sweep by the init kernel, so the
+// kernels inside the (pre-instantiated) loop graph take nothing but the state pointer
+struct OdomLoopIo {
+  TreeView corner_tree, surf_tree;
+  const float4* last_corner;
+  const float4* last_surf;
+  const float4* queries;
+  int* ind;
+  const int* ring_off_corner;
+  const int* ring_off_surf;
+  int n_sharp, n_flat, sharp_blocks, n_blocks;
+};
 struct OdomLmState {
   LmHeader h;
   GnState gn;
   float inv_sp, delta_t_abort, delta_r_abort;
   int max_iter, n_last_corner, n_last_surf;
   OdomIterArgs args;  // arguments of iteration h.iter
+  OdomLoopIo io;
 };
 
 __device__ inline void odom_lm_refresh_args(OdomLmState* st) {
@@ -91,8 +104,10 @@ __device__ inline void odom_lm_refresh_args(OdomLmState* st) {
 
 __global__ void odom_lm_init_kernel(OdomLmState* st, float rx, float ry, float rz, float tx, float ty, float tz, float inv_sp,
                                     float delta_t_abort, float delta_r_abort, int max_iter, int n_last_corner,
-                                    int n_last_surf) {
+                                    int n_last_surf, OdomLoopIo io, int mb_seq) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->io = io;
+  st->h.mb_seq = mb_seq;
   st->h.rot[0] = rx; st->h.rot[1] = ry; st->h.rot[2] = rz;
   st->h.pos[0] = tx; st->h.pos[1] = ty; st->h.pos[2] = tz;
   st->h.iter = 0;
@@ -237,16 +252,21 @@ __device__ __forceinline__ void scan_best_warp(ScanBest& a) {
 // shared memory; the by-value argument of the per-iteration API stays in the constant bank); no work once converged
 template <bool DEVLOOP>
 __global__ void __launch_bounds__(LM_THREADS)
-odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
-                   const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
-                   OdomIterArgs a_param, int* __restrict__ ind, const OdomLmState* __restrict__ lm = nullptr,
-                   const int* __restrict__ ring_off_corner = nullptr, const int* __restrict__ ring_off_surf = nullptr) {
+odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* last_corner, const float4* last_surf,
+                   const float4* queries, int n_sharp, int n_flat, OdomIterArgs a_param, int* ind,
+                   const OdomLmState* __restrict__ lm = nullptr, const int* ring_off_corner = nullptr,
+                   const int* ring_off_surf = nullptr) {
   __shared__ OdomIterArgs s_args;
   if (DEVLOOP) {
-    if (lm->h.done) return;
+    if (lm->h.done || lm->h.iter % 5 != 0) return;  // the loop graph launches this kernel every iteration
     if (threadIdx.x < (int)(sizeof(OdomIterArgs) / 4))
       reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
     __syncthreads();
+    const OdomLoopIo& io = lm->io;  // uniform loads
+    corner_tree = io.corner_tree; surf_tree = io.surf_tree;
+    last_corner = io.last_corner; last_surf = io.last_surf; queries = io.queries;
+    n_sharp = io.n_sharp; n_flat = io.n_flat; ind = io.ind;
+    ring_off_corner = io.ring_off_corner; ring_off_surf = io.ring_off_surf;
   }
   const OdomIterArgs& a = DEVLOOP ? s_args : a_param;
   const int lane = threadIdx.x & 31;
@@ -389,18 +409,24 @@ odom_search_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __res
 
 template <bool DEVLOOP>
 __global__ void __launch_bounds__(LM_THREADS)
-odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __restrict__ last_corner,
-                    const float4* __restrict__ last_surf, const float4* __restrict__ queries, int n_sharp, int n_flat,
-                    int sharp_blocks, OdomIterArgs a_param, int* __restrict__ ind, float* __restrict__ partials,
+odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* last_corner, const float4* last_surf,
+                    const float4* queries, int n_sharp, int n_flat, int sharp_blocks, OdomIterArgs a_param, int* ind,
+                    float* __restrict__ partials,
                     float* __restrict__ result, unsigned int* ticket, float4* __restrict__ dbg_coeff,
                     int8_t* __restrict__ dbg_sel, const OdomLmState* __restrict__ lm = nullptr,
                     ResultMailbox mb = ResultMailbox{nullptr, 0}) {
   __shared__ OdomIterArgs s_args;
+  unsigned n_blocks = gridDim.x;
   if (DEVLOOP) {
     if (lm->h.done) return;
     if (threadIdx.x < (int)(sizeof(OdomIterArgs) / 4))
       reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
     __syncthreads();
+    const OdomLoopIo& io = lm->io;  // uniform loads; the grid of the loop graph is sized for a capacity
+    n_blocks = (unsigned)io.n_blocks;
+    if (blockIdx.x >= n_blocks) return;
+    last_corner = io.last_corner; last_surf = io.last_surf; queries = io.queries;
+    n_sharp = io.n_sharp; n_flat = io.n_flat; sharp_blocks = io.sharp_blocks; ind = io.ind;
   }
   const OdomIterArgs& a = DEVLOOP ? s_args : a_param;
   float acc[29];
@@ -472,12 +498,20 @@ odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* __re
       accumulate_row(acc, row, b, is_corner);
     }
   }
-  reduce_normal_equations(acc, partials, result, ticket, mb);
+  reduce_normal_equations(acc, partials, result, ticket, mb, n_blocks);
 }
 
-__global__ void odom_lm_step_kernel(OdomLmState* st, const float* __restrict__ result) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || st->h.done) return;
-  odom_lm_step(st, result);
+// one warp: the 32 sums are staged through shared memory by one coalesced load (a single thread reading them from
+// global memory one dependent load at a time is what made this kernel cost 15 us in round 1), lane 0 solves
+__global__ void odom_lm_step_kernel(OdomLmState* st, const float* __restrict__ result, unsigned long long handle = 0ull,
+                                    float* mailbox_host = nullptr) {
+  __shared__ float s_r[NEQ];
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < NEQ) s_r[threadIdx.x] = __ldcg(&result[threadIdx.x]);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (!st->h.done) odom_lm_step(st, s_r);
+  lm_loop_control(st->h, handle, mailbox_host);
 }
 
 // BasicLaserOdometry::transformToEnd without IMU terms (BasicLaserOdometry.cpp:57-87): in place on a device cloud.

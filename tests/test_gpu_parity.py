@@ -530,6 +530,33 @@ def test_hostcloud_chain_equals_fused_chain(scene, sweeps_vlp16, map_200k):
     np.testing.assert_array_equal(pa.mapping.cloud("surf_cubes"), pb.mapping.cloud("surf_cubes"))
 
 
+def test_streaming_pipeline_equals_sequential(scene, sweeps_vlp16, map_200k):
+    """The three stages as concurrent workers over consecutive sweeps (loam_b200_pipeline_submit / _collect, how the
+    reference's three ROS nodes run) produce the sequential chain's poses bit for bit, host and device input alike."""
+    import torch
+    from loam_velodyne_b200 import api
+    corner, surf = map_200k
+    pa, pb, pc = api.Pipeline(), api.Pipeline(), api.Pipeline()
+    for p in (pa, pb, pc):
+        p.seed_map(corner, surf)
+    seq = [pa.sweep(pts, rs) for pts, rs in sweeps_vlp16]
+    res = pb.run_stream(sweeps_vlp16)
+    assert len(res) == len(seq)
+    for (ok_a, od_a, aft_a, _), (ok_b, od_b, aft_b) in zip(seq, res):
+        assert ok_a == ok_b
+        np.testing.assert_array_equal(od_a, od_b)
+        np.testing.assert_array_equal(aft_a, aft_b)
+    dev = [torch.from_numpy(p).cuda() for p, _ in sweeps_vlp16]
+    torch.cuda.synchronize()
+    res = pc.run_stream(sweeps_vlp16, device_ptrs=[t.data_ptr() for t in dev])
+    for (ok_a, od_a, aft_a, _), (ok_b, od_b, aft_b) in zip(seq, res):
+        np.testing.assert_array_equal(aft_a, aft_b)
+    np.testing.assert_array_equal(pa.mapping.cloud("surf_cubes"), pb.mapping.cloud("surf_cubes"))
+    # the sequential call still works on a pipeline that has streamed
+    pts, rs = sweeps_vlp16[0]
+    assert pb.sweep(pts, rs)[0] == pa.sweep(pts, rs)[0]
+
+
 def test_device_resident_sweep_input(scene, sweeps_vlp16, map_200k):
     """Sweeps handed over as device pointers give the same result as host buffers."""
     import torch
