@@ -268,11 +268,16 @@ def run_cuda(args, rank, world, local_rank):
             pipe.sync()
 
         run(0, args.warmup, False)
+        if streaming:
+            pipe.stage_seconds(reset=True)
         barrier()
         t0 = time.perf_counter()
         run(args.warmup, n_total, True)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if streaming:
+            ss = pipe.stage_seconds()
+            acc["stage"] = np.concatenate([ss["busy"], ss["idle"], ss["handoff"]])
         el = max_over_ranks(t1 - t0)
         barrier()
         del pipe
@@ -344,6 +349,9 @@ def run_cuda(args, rank, world, local_rank):
                                   "reported": "median window; every window runs on a fresh pipeline (new data every step)",
                                   "window_ms_min_median_max": [ms(a_dev["min"]), ms(a_dev["seconds"]), ms(a_dev["max"])],
                                   "e2e_window_ms_min_median_max": [ms(a_host["min"]), ms(a_host["seconds"]), ms(a_host["max"])]},
+                       "streaming_stage_ms_per_sweep": {
+                           k: [round(1e3 * float(v) / args.steps, 4) for v in a_dev["runs"][0][2][3 * j:3 * j + 3]]
+                           for j, k in enumerate(["busy_reg_odom_map", "waiting_reg_odom_map", "handoff_reg_odom_map"])},
                        "sequential": {"value_device_input": round(streams * args.steps / s_dev["seconds"], 3),
                                       "value_host_input": round(streams * args.steps / s_host["seconds"], 3),
                                       "unit": "sweeps/s", "latency_ms_per_sweep": round(1e3 * s_dev["seconds"] / args.steps, 4),

@@ -182,6 +182,12 @@ int loam_b200_odom_solve(loam_b200_ctx* ctx, const float rot[3], const float pos
 int loam_b200_map_solve(loam_b200_ctx* ctx, const float rot[3], const float pos[3], int max_iterations,
                         float delta_t_abort, float delta_r_abort, loam_b200_lm_result* out);
 
+/* Test hook: the warp-parallel 6 x 6 Gauss-Newton step of the device-resident loops (csrc/lmstep_warp.cuh) on n systems
+ * given as 42 floats each (AtA row-major 36, AtB 6) -> x_out (6 per system), degenerate_out (0 / 1 per system).  Must equal
+ * loam_b200_host_gn_solve (include/loam_b200_host.h) bit for bit. */
+int loam_b200_debug_gn_solve(loam_b200_ctx* ctx, const float* ata_atb, int n, int first_iteration, float eigen_threshold,
+                             float* x_out, int* degenerate_out);
+
 /* BasicLaserOdometry::transformToEnd (BasicLaserOdometry.cpp:57-87) without IMU terms, in place on n host points */
 int loam_b200_transform_to_end(loam_b200_ctx* ctx, float* pts, int n, const loam_b200_odom_pose* pose);
 /* pointAssociateToMap over n host points in place (BasicLaserMapping.cpp:207-219, 235-240) */

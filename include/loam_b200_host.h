@@ -112,6 +112,9 @@ int loam_b200_pipeline_sweep_hostclouds(void* h, const float* pts, const int* ri
  * while sweeps are in flight. */
 int loam_b200_pipeline_submit(void* h, const float* pts, const void* d_pts, const int* ring_sizes, int n_rings);
 int loam_b200_pipeline_collect(void* h, int wait, float* odom_sum6, float* map_aft6, int* ok);
+/* out9 = seconds the registration / odometry / mapping stage threads spent [0..2] working, [3..5] waiting for a neighbour
+ * stage, [6..8] in the adopt() hand-offs since streaming started (or the last reset); call while no sweep is in flight */
+int loam_b200_pipeline_stage_seconds(void* h, double* out9, int reset);
 /* wait until everything the three stage objects enqueued (or posted to their helper threads) has finished on the GPU */
 int loam_b200_pipeline_sync(void* h);
 void* loam_b200_pipeline_scanreg(void* h);

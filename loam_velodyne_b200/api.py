@@ -112,6 +112,7 @@ def lib():
         "loam_b200_map_solve": (C.c_int, [vp, _F, _F, C.c_int, C.c_float, C.c_float, C.POINTER(LmResult)]),
         "loam_b200_odom_iterate": (C.c_int, [vp, C.POINTER(OdomPose), C.POINTER(NormalEq)]),
         "loam_b200_odom_iterate_debug": (C.c_int, [vp, C.POINTER(OdomPose), C.POINTER(NormalEq), _F, _B, _I]),
+        "loam_b200_debug_gn_solve": (C.c_int, [vp, _F, C.c_int, C.c_int, C.c_float, _F, _I]),
         "loam_b200_transform_to_end": (C.c_int, [vp, _F, C.c_int, C.POINTER(OdomPose)]),
         "loam_b200_transform_to_map": (C.c_int, [vp, _F, C.c_int, C.POINTER(Pose)]),
         "loam_b200_voxel_grid": (C.c_int, [vp, _F, C.c_int, C.c_float, _F, C.c_int, _I]),
@@ -192,6 +193,7 @@ def lib():
         "loam_b200_pipeline_submit": (C.c_int, [vp, _F, vp, _I, C.c_int]),
         "loam_b200_pipeline_collect": (C.c_int, [vp, C.c_int, _F, _F, _I]),
         "loam_b200_pipeline_sync": (C.c_int, [vp]),
+        "loam_b200_pipeline_stage_seconds": (C.c_int, [vp, _D, C.c_int]),
         "loam_b200_pipeline_scanreg": (vp, [vp]),
         "loam_b200_pipeline_odom": (vp, [vp]),
         "loam_b200_pipeline_map": (vp, [vp]),
@@ -371,6 +373,18 @@ class Ctx:
             return _ne(ne), coeff, sel, ind
         self._ck(self.L.loam_b200_odom_iterate(self.h, C.byref(p), C.byref(ne)), "odom_iterate")
         return _ne(ne)
+
+    def debug_gn_solve(self, AtA, AtB, first_iteration=True, eigen_threshold=10.0):
+        """The device loops' warp-parallel 6 x 6 step on n systems (AtA n x 6 x 6, AtB n x 6) -> (x n x 6, degenerate n)."""
+        A = np.ascontiguousarray(AtA, dtype=np.float32).reshape(-1, 36)
+        b = np.ascontiguousarray(AtB, dtype=np.float32).reshape(-1, 6)
+        packed = np.ascontiguousarray(np.concatenate([A, b], axis=1), dtype=np.float32)
+        n = packed.shape[0]
+        x = np.zeros((n, 6), np.float32)
+        deg = np.zeros(n, np.int32)
+        self._ck(self.L.loam_b200_debug_gn_solve(self.h, _fp(packed), n, 1 if first_iteration else 0, eigen_threshold,
+                                                 _fp(x), _ip(deg)), "debug_gn_solve")
+        return x, deg
 
     def odom_solve(self, twist6, scan_period=0.1, max_iter=25, delta_t=0.1, delta_r=0.1):
         """Whole scan-to-scan Gauss-Newton loop on the device -> (twist6, iterations)."""
@@ -636,6 +650,12 @@ class Pipeline(_Handle):
     def sync(self):
         """Everything enqueued by the three stages (helper threads included) has finished on the GPU."""
         self._ck(self.L.loam_b200_pipeline_sync(self.h), "pipeline_sync")
+
+    def stage_seconds(self, reset=False):
+        """Streaming mode: seconds per stage thread (registration, odometry, mapping) spent working / waiting / in hand-offs."""
+        out = np.zeros(9, np.float64)
+        self.L.loam_b200_pipeline_stage_seconds(self.h, out.ctypes.data_as(_D), 1 if reset else 0)
+        return {"busy": out[0:3].copy(), "idle": out[3:6].copy(), "handoff": out[6:9].copy()}
 
     # ---- streaming form: the three stages run concurrently on consecutive sweeps (include/loam_b200_host.h)
     def submit(self, pts=None, ring_sizes=None, device_ptr=None):

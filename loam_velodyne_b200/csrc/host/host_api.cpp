@@ -143,6 +143,8 @@ struct StreamRunner {
   long next_id = 0, reg_done = 0, odom_done = 0, n_submitted = 0, n_finished = 0;
   bool reg_ready = false, odom_ready = false, stop = false;
   std::string err;
+  // seconds each stage spent working / waiting for its neighbours (loam_b200_pipeline_stage_seconds)
+  double busy[3] = {0, 0, 0}, idle[3] = {0, 0, 0}, handoff[3] = {0, 0, 0};
   static constexpr size_t MAX_QUEUED = 2;
 
   explicit StreamRunner(PipeH* pipe) : p(pipe), device(loam::b200::defaultDevice()) {
@@ -177,6 +179,7 @@ struct StreamRunner {
   void stage_reg() {
     for (;;) {
       SweepJob job;
+      const double tw = now();
       {
         std::unique_lock<std::mutex> lk(m);
         // the previous sweep's clouds must have been taken over before they are overwritten
@@ -186,10 +189,13 @@ struct StreamRunner {
         in.pop_front();
       }
       cv.notify_all();
+      const double tb = now();
       if (job.d_pts)
         p->reg.r.processDeviceSweep(loam::Time(), job.d_pts, job.rings.data(), (int)job.rings.size());
       else
         p->reg.r.processPackedSweep(loam::Time(), job.pts, job.rings.data(), (int)job.rings.size());
+      idle[0] += tb - tw;
+      busy[0] += now() - tb;
       {
         std::lock_guard<std::mutex> lk(m);
         reg_ready = true;
@@ -200,20 +206,26 @@ struct StreamRunner {
   void stage_odom() {
     auto& o = p->odom.o;
     for (;;) {
+      const double tw = now();
       {
         std::unique_lock<std::mutex> lk(m);
         // adopt() overwrites the full-resolution cloud the mapping stage takes from this object
         cv.wait(lk, [this] { return stop || (reg_ready && !odom_ready); });
         if (stop) return;
       }
+      const double ta = now();
       o.adopt(p->reg.r);  // the registration thread is parked until reg_ready drops
       {
         std::lock_guard<std::mutex> lk(m);
         reg_ready = false;
       }
       cv.notify_all();
+      const double tb = now();
       o.process();
       o.transformLaserCloudToEnd();
+      idle[1] += ta - tw;
+      handoff[1] += tb - ta;
+      busy[1] += now() - tb;
       {
         std::lock_guard<std::mutex> lk(m);
         odom_ready = true;
@@ -225,11 +237,13 @@ struct StreamRunner {
     auto& o = p->odom.o;
     auto& mp = p->map.m;
     for (;;) {
+      const double tw = now();
       {
         std::unique_lock<std::mutex> lk(m);
         cv.wait(lk, [this] { return stop || odom_ready; });
         if (stop) return;
       }
+      const double ta = now();
       SweepResult r;
       mp.adopt(o);  // the odometry thread is parked until odom_ready drops
       twist6(o.transformSum(), r.odom);
@@ -238,8 +252,12 @@ struct StreamRunner {
         odom_ready = false;
       }
       cv.notify_all();
+      const double tb = now();
       r.ok = mp.process(loam::Time()) ? 1 : 0;
       twist6(mp.transformAftMapped(), r.aft);
+      idle[2] += ta - tw;
+      handoff[2] += tb - ta;
+      busy[2] += now() - tb;
       {
         std::lock_guard<std::mutex> lk(m);
         r.id = n_finished++;
@@ -527,6 +545,23 @@ int loam_b200_pipeline_submit(void* hh, const float* pts, const void* d_pts, con
   if (!h || (!pts && !d_pts) || !ring_sizes || n_rings <= 0) { g_err = "invalid argument"; return -1; }
   if (!h->runner) h->runner = new StreamRunner(h);
   return h->runner->submit(pts, d_pts, ring_sizes, n_rings);
+}
+
+// out9: seconds the registration / odometry / mapping stage threads spent working, waiting for a neighbour stage, and in
+// the adopt() hand-offs since the pipeline started streaming (call while no sweep is in flight); reset = clear afterwards
+int loam_b200_pipeline_stage_seconds(void* hh, double* out9, int reset) {
+  PipeH* h = (PipeH*)hh;
+  if (!h || !out9) return -1;
+  for (int i = 0; i < 9; i++) out9[i] = 0.0;
+  if (!h->runner) return 0;
+  std::lock_guard<std::mutex> lk(h->runner->m);
+  for (int s = 0; s < 3; s++) {
+    out9[s] = h->runner->busy[s];
+    out9[3 + s] = h->runner->idle[s];
+    out9[6 + s] = h->runner->handoff[s];
+    if (reset) h->runner->busy[s] = h->runner->idle[s] = h->runner->handoff[s] = 0.0;
+  }
+  return 0;
 }
 
 int loam_b200_pipeline_collect(void* hh, int wait, float* odom_sum6, float* map_aft6, int* ok) {

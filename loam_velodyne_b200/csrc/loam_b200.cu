@@ -1231,6 +1231,62 @@ int loam_b200_map_solve(loam_b200_ctx* c, const float rot[3], const float pos[3]
   return LOAM_B200_OK;
 }
 
+// The warp-parallel 6 x 6 step of the device-resident loops on caller-supplied normal equations (parity tests: it must
+// equal loam_b200_host_gn_solve, the serial host form of the same arithmetic, bit for bit).
+namespace loamb {
+__global__ void gn_solve_debug_kernel(const float* __restrict__ ata_atb, int n, int first, float eig_thr, GnState* g,
+                                      float* __restrict__ x_out, int* __restrict__ deg_out) {
+  __shared__ float s_r[NEQ];
+  const int lane = threadIdx.x;
+  for (int m = 0; m < n; m++) {
+    if (lane == 0) g->degenerate = 0;
+    const float* src = ata_atb + (size_t)m * 42;
+    // 21 upper-triangle entries + 6 right-hand sides, as the iteration kernels leave them
+    if (lane < 21) {
+      int k = 0, r = 0, c2 = 0;
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) {
+          if (k == lane) { r = i; c2 = j; }
+          k++;
+        }
+      s_r[lane] = src[r * 6 + c2];
+    } else if (lane < 27) {
+      s_r[lane] = src[36 + lane - 21];
+    } else {
+      s_r[lane] = 0.f;
+    }
+    __syncwarp();
+    float x[6];
+    gn_solve_warp(s_r, first != 0, eig_thr, g, x);
+    if (lane == 0) {
+      for (int i = 0; i < 6; i++) x_out[(size_t)m * 6 + i] = x[i];
+      deg_out[m] = g->degenerate;
+    }
+    __syncwarp();
+  }
+}
+}  // namespace loamb
+
+int loam_b200_debug_gn_solve(loam_b200_ctx* c, const float* ata_atb, int n, int first_iteration, float eigen_threshold,
+                             float* x_out, int* degenerate_out) {
+  CHECK_CTX(c);
+  if (!ata_atb || n <= 0 || !x_out || !degenerate_out) return LOAM_B200_ERR_ARG;
+  LB_CUDA(c, c->tmp_pts.reserve((size_t)n * 11 + 16));  // 42 floats per system
+  LB_CUDA(c, c->tmp_pts2.reserve((size_t)n * 2 + 16));   // x (6 floats) + flag per system
+  LB_CUDA(c, c->lm_state.reserve(sizeof(OdomLmState) + sizeof(MapLmState)));
+  float* d_in = reinterpret_cast<float*>(c->tmp_pts.p);
+  float* d_x = reinterpret_cast<float*>(c->tmp_pts2.p);
+  int* d_deg = reinterpret_cast<int*>(d_x + (size_t)n * 6);
+  GnState* g = &reinterpret_cast<OdomLmState*>(c->lm_state.p)->gn;
+  LB_CUDA(c, cudaMemcpyAsync(d_in, ata_atb, (size_t)n * 42 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  gn_solve_debug_kernel<<<1, 32, 0, c->stream>>>(d_in, n, first_iteration, eigen_threshold, g, d_x, d_deg);
+  LB_LAUNCH_CHECK(c);
+  LB_CUDA(c, cudaMemcpyAsync(x_out, d_x, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaMemcpyAsync(degenerate_out, d_deg, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LOAM_B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ bulk transforms
 int loam_b200_transform_to_end(loam_b200_ctx* c, float* pts, int n, const loam_b200_odom_pose* p) {
   CHECK_CTX(c);

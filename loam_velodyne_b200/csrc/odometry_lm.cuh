@@ -123,45 +123,55 @@ __global__ void odom_lm_init_kernel(OdomLmState* st, float rx, float ry, float r
   odom_lm_refresh_args(st);
 }
 
-// One thread, after the normal equations of iteration h.iter are complete in result[0..31]
-// (BasicLaserOdometry.cpp:484-488 skip, :559-622 solve / update / NaN reset / convergence)
-__device__ inline void odom_lm_step(OdomLmState* st, const float* __restrict__ result) {
-  LmHeader& h = st->h;
-  h.iters_run = h.iter + 1;
+// One warp, after the normal equations of iteration h.iter are complete in s_r[0..31] (shared memory)
+// (BasicLaserOdometry.cpp:484-488 skip, :559-622 solve / update / NaN reset / convergence); lmstep_warp.cuh
+__device__ inline void odom_lm_step_warp(OdomLmState* st, const float* s_r) {
+  const int lane = threadIdx.x & 31;
+  const int iter = st->h.iter;
+  float rot[3], pos[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { rot[i] = st->h.rot[i]; pos[i] = st->h.pos[i]; }
   bool converged = false;
-  if ((int)(result[27] + 0.5f) >= 10) {
-    float AtA[36], AtB[6], x[6];
-    int k = 0;
-    for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) {
-        AtA[i * 6 + j] = result[k];
-        AtA[j * 6 + i] = result[k];
-        k++;
-      }
-    for (int i = 0; i < 6; i++) AtB[i] = result[21 + i];
-    gn_solve(AtA, AtB, h.iter == 0, 10.f, st->gn, x);
+  if ((int)(s_r[27] + 0.5f) >= 10) {
+    float x[6];
+    gn_solve_warp(s_r, iter == 0, 10.f, &st->gn, x);
+#pragma unroll
     for (int i = 0; i < 3; i++) {
-      h.rot[i] = h.rot[i] + x[i];
-      h.pos[i] += x[3 + i];
+      rot[i] = rot[i] + x[i];
+      pos[i] += x[3 + i];
     }
+#pragma unroll
     for (int i = 0; i < 3; i++) {
-      if (!isfinite(h.rot[i])) h.rot[i] = 0.f;
-      if (!isfinite(h.pos[i])) h.pos[i] = 0.f;
+      if (!isfinite(rot[i])) rot[i] = 0.f;
+      if (!isfinite(pos[i])) pos[i] = 0.f;
     }
-    double r2 = 0.0, t2 = 0.0;
-    for (int i = 0; i < 3; i++) {
-      const double rd = (double)(float)((double)x[i] * 180.0 / 3.14159265358979323846);  // rad2deg returns float
-      r2 += rd * rd;
-      const double td = (double)(x[3 + i] * 100.f);
-      t2 += td * td;
-    }
-    const float deltaR = (float)sqrt(r2), deltaT = (float)sqrt(t2);
+    float deltaR, deltaT;
+    gn_deltas(x, deltaR, deltaT);
     converged = deltaR < st->delta_r_abort && deltaT < st->delta_t_abort;
   }
-  h.iter++;
-  if (converged || h.iter >= st->max_iter) h.done = 1;
-  odom_lm_refresh_args(st);
-  __threadfence();
+  // arguments of the next iteration: sin / cos of the three angles on lanes 0..2, the rest on lane 0
+  float sn, cs;
+  sincos_f(lane == 1 ? rot[1] : (lane == 2 ? rot[2] : rot[0]), sn, cs);
+  float s3[3], c3[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    s3[i] = __shfl_sync(0xffffffffu, sn, i);
+    c3[i] = __shfl_sync(0xffffffffu, cs, i);
+  }
+  if (lane == 0) {
+    OdomIterArgs a;
+    odom_args_from(rot, s3, c3, pos, st->inv_sp, iter + 1, a);
+    a.n_last_corner = st->n_last_corner;
+    a.n_last_surf = st->n_last_surf;
+    st->args = a;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { st->h.rot[i] = rot[i]; st->h.pos[i] = pos[i]; }
+    st->h.iters_run = iter + 1;
+    st->h.iter = iter + 1;
+    if (converged || iter + 1 >= st->max_iter) st->h.done = 1;
+    __threadfence();
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void rot_zxy(float& x, float& y, float& z, float sz, float cz, float sx, float cx,
@@ -501,17 +511,15 @@ odom_iterate_kernel(TreeView corner_tree, TreeView surf_tree, const float4* last
   reduce_normal_equations(acc, partials, result, ticket, mb, n_blocks);
 }
 
-// one warp: the 32 sums are staged through shared memory by one coalesced load (a single thread reading them from
-// global memory one dependent load at a time is what made this kernel cost 15 us in round 1), lane 0 solves
+// one warp: the 32 sums are staged through shared memory by one coalesced load, the warp solves (lmstep_warp.cuh)
 __global__ void odom_lm_step_kernel(OdomLmState* st, const float* __restrict__ result, unsigned long long handle = 0ull,
                                     float* mailbox_host = nullptr) {
   __shared__ float s_r[NEQ];
-  if (blockIdx.x != 0) return;
-  if (threadIdx.x < NEQ) s_r[threadIdx.x] = __ldcg(&result[threadIdx.x]);
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  if (!st->h.done) odom_lm_step(st, s_r);
-  lm_loop_control(st->h, handle, mailbox_host);
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  s_r[threadIdx.x] = __ldcg(&result[threadIdx.x]);
+  __syncwarp();
+  if (!st->h.done) odom_lm_step_warp(st, s_r);  // uniform over the warp
+  if (threadIdx.x == 0) lm_loop_control(st->h, handle, mailbox_host);
 }
 
 // BasicLaserOdometry::transformToEnd without IMU terms (BasicLaserOdometry.cpp:57-87): in place on a device cloud.

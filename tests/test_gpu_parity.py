@@ -203,6 +203,38 @@ def test_odom_iteration_per_correspondence(ctx, oracle, scene):
         assert int((ind != ref["ind"]).any(axis=1).sum()) <= 2, np.argwhere(ind != ref["ind"])[:10]
 
 
+def test_warp_solver_equals_host_solver(ctx):
+    """The warp-parallel 6 x 6 Gauss-Newton step of the device loops (csrc/lmstep_warp.cuh) against the host's serial form
+    of the same arithmetic (gn_solve, itself checked against the reference's Eigen calls in test_abi.py): bit for bit,
+    including matrices with a weak direction (degeneracy projection) and thresholds that force the eigen path."""
+    from loam_velodyne_b200 import api
+    rng = np.random.RandomState(11)
+    n = 300
+    AtA = np.zeros((n, 6, 6), np.float32)
+    AtB = np.zeros((n, 6), np.float32)
+    for m in range(n):
+        rows = rng.randint(200, 3000)
+        J = np.concatenate([rng.uniform(-10, 10, (rows, 3)), rng.uniform(-1, 1, (rows, 3))], axis=1)
+        if m % 4 == 0:
+            J[:, 4] *= 0.02  # nearly unobservable translation
+        if m % 50 == 7:
+            J[:, 5] = 0.0    # exactly rank deficient
+        r = rng.uniform(-0.05, 0.05, rows)
+        AtA[m] = (J.T @ J).astype(np.float32)
+        AtB[m] = (J.T @ r).astype(np.float32)
+    for thr in (10.0, 100.0, 1e5):
+        for first in (True, False):
+            xg, dg = ctx.debug_gn_solve(AtA, AtB, first, thr)
+            n_deg = 0
+            for m in range(n):
+                xh, dh = api.gn_solve(AtA[m], AtB[m], first, thr)
+                assert bool(dg[m]) == dh, (thr, first, m)
+                np.testing.assert_array_equal(xg[m], xh, err_msg=f"thr {thr} first {first} system {m}")
+                n_deg += int(dh)
+            if first and thr >= 100.0:
+                assert n_deg >= n // 4  # the projection path was exercised
+
+
 def test_device_resident_odometry_loop(ctx, oracle, scene):
     """loam_b200_odom_solve (whole Gauss-Newton loop on the device) against the loop driven from the host through the
     per-iteration entry point + the oracle's own 6x6 solve: same iteration count, pose within 2e-6; deterministic."""
