@@ -43,6 +43,29 @@ int loam_b200_version(void);
  * there is deliberately no CPU fallback. */
 int loam_b200_create(loam_b200_ctx** out, int device);
 int loam_b200_destroy(loam_b200_ctx* ctx);
+/* Scheduling priority of the context's streams relative to other contexts on the same GPU: level 0 = default, 1 = high
+ * (the latency-critical Gauss-Newton loops of the odometry stage), -1 = low.  Call right after loam_b200_create, before
+ * any work has been enqueued (the streams are re-created). */
+int loam_b200_set_priority(loam_b200_ctx* ctx, int level);
+/* ---- multi-GPU with the map sharded by cube slabs (csrc/shard.cuh, csrc/peer.inc) --------------------
+ * One process per GPU.  Rank r owns the slabs of `slab_cells` 1 m cells along x with (slab index mod world) == r and stores a
+ * 2-cell halo around them; it evaluates the scan-to-map queries whose transformed position falls into a cell it owns, and the
+ * 32 partial sums of every Gauss-Newton iteration are all-reduced INSIDE the iteration kernel: the folding CTA stores them
+ * into every peer's inbox over NVLink (CUDA IPC mapped memory), flags them, and adds the world contributions in rank order,
+ * so every rank holds bit-identical normal equations without a host round trip or a separate collective.
+ *   loam_b200_peer_export   -> this rank's inbox as a 64-byte CUDA IPC handle (distribute with any all-gather)
+ *   loam_b200_peer_connect  <- world x 64 bytes of handles in rank order
+ *   loam_b200_peer_connect_local: the same wiring for contexts of ONE process (tests, single-process multi-GPU)
+ * After connecting: loam_b200_map_pool_append / seedMap must only be given the points this rank stores
+ * (loam_b200_shard_stores), inserted points are filtered by the library; loam_b200_map_iterate returns the all-reduced sums.
+ * Every rank must run the same sequence of sweeps and iterations (they do: same sums, same solve). */
+int loam_b200_peer_export(loam_b200_ctx* ctx, unsigned char handle_out[64]);
+int loam_b200_peer_connect(loam_b200_ctx* ctx, int rank, int world, const unsigned char* handles, int slab_cells);
+int loam_b200_peer_connect_local(loam_b200_ctx** ctxs, int world, int slab_cells);
+int loam_b200_peer_disconnect(loam_b200_ctx* ctx);
+/* host logic of the slab partition: owner of the cell with x index cell_x; does `rank` store the point with coordinate x */
+int loam_b200_shard_owner(int cell_x, int slab_cells, int world);
+int loam_b200_shard_stores(float x, int rank, int world, int slab_cells);
 /* Bind the calling host thread to a CUDA device (cudaSetDevice): every host thread other than the one that created a
  * context must call this once before using the context (helper threads of the library do so themselves). */
 int loam_b200_bind_thread(int device);

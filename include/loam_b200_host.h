@@ -89,6 +89,14 @@ int loam_b200_map_retain_from_map(void* h, int on);
 int loam_b200_host_nccl_unique_id(unsigned char* out128);
 int loam_b200_map_enable_sharding(void* h, int rank, int world, const unsigned char* nccl_id128);
 
+/* multi-GPU with the MAP sharded by cube slabs along x (include/loam_b200.h "peer"): every rank exports its 64-byte inbox
+ * handle, the caller all-gathers them, every rank enables sharding with all handles in rank order.  A rank then stores
+ * only its slabs (+ 2 m halo; loam_b200_map_seed keeps the points that belong to it) and the per-iteration normal equations
+ * are all-reduced inside the iteration kernel over NVLink peer memory.  _local: objects of one process, hs[r] = rank r. */
+int loam_b200_map_peer_export(void* h, unsigned char* out64);
+int loam_b200_map_enable_cube_sharding(void* h, int rank, int world, const unsigned char* handles, int slab_metres);
+int loam_b200_map_enable_cube_sharding_local(void** hs, int world, int slab_metres);
+
 /* ---- the three chained in-process: registration -> odometry -> mapping on one sweep ---- */
 void* loam_b200_pipeline_create(float scanPeriod, int odomMaxIter, int mapMaxIter);
 void loam_b200_pipeline_destroy(void* h);

@@ -95,6 +95,7 @@ def lib():
         "loam_b200_destroy": (C.c_int, [vp]),
         "loam_b200_sync": (C.c_int, [vp]),
         "loam_b200_bind_thread": (C.c_int, [C.c_int]),
+        "loam_b200_set_priority": (C.c_int, [vp, C.c_int]),
         "loam_b200_stream": (vp, [vp]),
         "loam_b200_extract_features": (C.c_int, [vp, _F, C.c_int, _I, _I, C.c_int, C.POINTER(RegParams),
                                                  C.POINTER(Features)]),
@@ -184,6 +185,15 @@ def lib():
         "loam_b200_map_retain_from_map": (C.c_int, [vp, C.c_int]),
         "loam_b200_host_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
+        "loam_b200_map_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
+        "loam_b200_map_enable_cube_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
+        "loam_b200_map_enable_cube_sharding_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+        "loam_b200_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
+        "loam_b200_peer_connect": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
+        "loam_b200_peer_connect_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+        "loam_b200_peer_disconnect": (C.c_int, [vp]),
+        "loam_b200_shard_owner": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+        "loam_b200_shard_stores": (C.c_int, [C.c_float, C.c_int, C.c_int, C.c_int]),
         "loam_b200_pipeline_create": (vp, [C.c_float, C.c_int, C.c_int]),
         "loam_b200_pipeline_destroy": (None, [vp]),
         "loam_b200_pipeline_seed_map": (C.c_int, [vp, _F, C.c_int, _F, C.c_int]),
@@ -601,6 +611,34 @@ class LaserMapping(_Handle):
         else:
             buf = (C.c_ubyte * 128).from_buffer_copy(nccl_id)
             self._ck(self.L.loam_b200_map_enable_sharding(self.h, rank, world, buf), "enableSharding")
+
+
+    # ---- multi-GPU with the map sharded by cube slabs (include/loam_b200_host.h)
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.L.loam_b200_map_peer_export(self.h, buf), "exportPeerHandle")
+        return bytes(buf)
+
+    def enable_cube_sharding(self, rank, world, handles: bytes, slab_metres=10):
+        """handles: world x 64 bytes (peer_export of every rank, in rank order)."""
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(handles)
+        self._ck(self.L.loam_b200_map_enable_cube_sharding(self.h, rank, world, buf, slab_metres), "enableCubeSharding")
+
+
+def enable_cube_sharding_local(mappings, slab_metres=10):
+    """Several LaserMapping objects of this process become the ranks 0..n-1 of one cube-sharded map."""
+    L = lib()
+    arr = (C.c_void_p * len(mappings))(*[m.h for m in mappings])
+    if L.loam_b200_map_enable_cube_sharding_local(arr, len(mappings), slab_metres) < 0:
+        raise LoamB200Error(f"enableCubeShardingLocal: {L.loam_b200_host_last_error().decode()}")
+
+
+def shard_stores(x, rank, world, slab_metres=10):
+    return lib().loam_b200_shard_stores(float(x), rank, world, slab_metres) == 1
+
+
+def shard_owner(cell_x, world, slab_metres=10):
+    return lib().loam_b200_shard_owner(int(cell_x), slab_metres, world)
 
 
 class Pipeline(_Handle):

@@ -182,6 +182,12 @@ struct loam_b200_ctx {
   // multi-GPU: query slice of this rank and the NCCL communicator (comm.inc)
   void* comm = nullptr;
   int shard_rank = 0, shard_world = 1;
+  // multi-GPU, cube-sharded map (peer.inc): slab width in cells (0 = off), this rank's inbox (slots + flags + the
+  // reduction counter, one allocation) and the peers' inboxes mapped through CUDA IPC
+  int shard_slab = 0;
+  unsigned* peer_inbox = nullptr;
+  void* peer_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peer_ready = false;
 
   // scan registration
   loamb::DevBuf<float4> reg_pts;

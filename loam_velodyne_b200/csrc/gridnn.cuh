@@ -17,6 +17,7 @@
 #pragma once
 
 #include "lbvh.cuh"
+#include "shard.cuh"
 
 namespace loamb {
 

@@ -60,6 +60,30 @@ void BasicLaserMapping::enableSharding(int rank, int world, const unsigned char*
     _gpu->check(loam_b200_map_set_shard(_gpu->get(), rank, world), "loam_b200_map_set_shard");
 }
 
+void BasicLaserMapping::exportPeerHandle(unsigned char out64[64]) {
+  _gpu->check(loam_b200_peer_export(_gpu->get(), out64), "loam_b200_peer_export");
+}
+
+void BasicLaserMapping::enableCubeSharding(int rank, int world, const unsigned char* handles, int slabMetres) {
+  _gpu->check(loam_b200_peer_connect(_gpu->get(), rank, world, handles, slabMetres), "loam_b200_peer_connect");
+  _sharded = world > 1;  // per-iteration form: the all-reduce is fused into the iteration kernel
+  _shardRank = rank;
+  _shardWorld = world;
+  _shardSlab = slabMetres;
+}
+
+void BasicLaserMapping::enableCubeShardingLocal(BasicLaserMapping** objs, int world, int slabMetres) {
+  std::vector<loam_b200_ctx*> ctxs((size_t)world);
+  for (int r = 0; r < world; r++) ctxs[r] = objs[r]->_gpu->get();
+  objs[0]->_gpu->check(loam_b200_peer_connect_local(ctxs.data(), world, slabMetres), "loam_b200_peer_connect_local");
+  for (int r = 0; r < world; r++) {
+    objs[r]->_sharded = world > 1;
+    objs[r]->_shardRank = r;
+    objs[r]->_shardWorld = world;
+    objs[r]->_shardSlab = slabMetres;
+  }
+}
+
 void BasicLaserMapping::retainFromMapClouds(bool on) {
   _retainFromMap = on;
   _gpu->check(loam_b200_map_debug_from_map(_gpu->get(), on ? 1 : 0), "loam_b200_map_debug_from_map");
@@ -317,10 +341,21 @@ void BasicLaserMapping::optimizeTransformTobeMapped() {
 void BasicLaserMapping::seedMap(Cloud const& cornerPoints, Cloud const& surfPoints) {
   // points outside the 21 x 11 x 21 grid are dropped by the first end-of-sweep pass, like upstream's insertion
   // (:548-554) would never have stored them
-  b200::pack(cornerPoints, _bufA);
-  _gpu->check(loam_b200_map_pool_append(_gpu->get(), 0, _bufA.data(), (int)cornerPoints.size()), "loam_b200_map_pool_append");
-  b200::pack(surfPoints, _bufA);
-  _gpu->check(loam_b200_map_pool_append(_gpu->get(), 1, _bufA.data(), (int)surfPoints.size()), "loam_b200_map_pool_append");
+  const Cloud* in[2] = {&cornerPoints, &surfPoints};
+  for (int kind = 0; kind < 2; kind++) {
+    if (_shardSlab > 0 && _shardWorld > 1) {
+      // cube-sharded map: this rank only holds the points of the slabs it owns and their halo (start-up, not hot path)
+      _bufA.clear();
+      _bufA.reserve(in[kind]->points.size() * 4 / _shardWorld + 64);
+      for (auto const& p : in[kind]->points)
+        if (loam_b200_shard_stores(p.x, _shardRank, _shardWorld, _shardSlab) == 1) {
+          _bufA.push_back(p.x); _bufA.push_back(p.y); _bufA.push_back(p.z); _bufA.push_back(p.intensity);
+        }
+    } else {
+      b200::pack(*in[kind], _bufA);
+    }
+    _gpu->check(loam_b200_map_pool_append(_gpu->get(), kind, _bufA.data(), (int)(_bufA.size() / 4)), "loam_b200_map_pool_append");
+  }
 }
 
 void BasicLaserMapping::collectMap(Cloud& corner, Cloud& surf) const {

@@ -38,6 +38,9 @@ BasicLaserOdometry::BasicLaserOdometry(float scanPeriod, size_t maxIterations)
                                    LOAM_B200_C_ODOM_LESS_FLAT, LOAM_B200_C_ODOM_FULL, LOAM_B200_C_ODOM_LAST_CORNER,
                                    LOAM_B200_C_ODOM_LAST_SURF};
   for (int i = 0; i < C_NUM; i++) _c[i].bind(_gpu, slots[i]);
+  // the scan-to-scan loop is a chain of small latency-bound kernels: when the three stages share a GPU (in-process
+  // pipeline) its stream goes ahead of the registration's and the map update's bulk kernels
+  _gpu->setPriority(1);
 }
 
 BasicLaserOdometry::~BasicLaserOdometry() {

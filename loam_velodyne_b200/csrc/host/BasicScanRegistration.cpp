@@ -35,6 +35,7 @@ BasicScanRegistration::BasicScanRegistration() : _clouds(new b200::DualCloud[5])
   static const int slots[5] = {LOAM_B200_C_REG_FULL, LOAM_B200_C_REG_SHARP, LOAM_B200_C_REG_LESS_SHARP,
                                LOAM_B200_C_REG_FLAT, LOAM_B200_C_REG_LESS_FLAT};
   for (int i = 0; i < 5; i++) _clouds[i].bind(_gpu, slots[i]);
+  _gpu->setPriority(-1);  // never the bottleneck of the three stages
 }
 BasicScanRegistration::~BasicScanRegistration() {
   delete[] _clouds;

@@ -26,6 +26,8 @@ loam_b200_ctx* Context::get() {
       ctx_ = nullptr;
       throw std::runtime_error(std::string("loam_b200_create: ") + loam_b200_strerror(rc));
     }
+    static const bool no_prio = std::getenv("LOAM_B200_NO_PRIORITY") != nullptr;
+    if (priority_ != 0 && !no_prio) check(loam_b200_set_priority(ctx_, priority_), "loam_b200_set_priority");
   }
   return ctx_;
 }
@@ -101,7 +103,7 @@ void GaussNewtonSolver::solve(const loam_b200_normal_eq& ne, bool firstIteration
 bool deviceResidentLoops() {
   static const bool on = [] {
     const char* e = std::getenv("LOAM_B200_DEVICE_LOOP");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }

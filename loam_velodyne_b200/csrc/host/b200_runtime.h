@@ -23,7 +23,8 @@ void setDefaultDevice(int device);
 
 class Context {
  public:
-  Context() : ctx_(nullptr) {}
+  Context() : ctx_(nullptr), priority_(0) {}
+  void setPriority(int level) { priority_ = level; }  // before first use (loam_b200_set_priority)
   ~Context() { if (ctx_) loam_b200_destroy(ctx_); }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
@@ -33,6 +34,7 @@ class Context {
 
  private:
   loam_b200_ctx* ctx_;
+  int priority_;
 };
 
 typedef pcl::PointCloud<pcl::PointXYZI> Cloud;

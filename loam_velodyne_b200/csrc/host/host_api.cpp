@@ -160,6 +160,25 @@ struct StreamRunner {
     cv.notify_all();
     for (auto& t : th) t.join();
   }
+  // Stage hand-offs are latency critical (the cycle of the pipeline is odometry + both hand-offs): poll the condition for
+  // a short while before falling back to the condition variable (a futex wake-up costs 10-50 us on a busy box).
+  template <typename PRED>
+  void wait_for(std::unique_lock<std::mutex>& lk, PRED pred) {
+    if (pred()) return;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+      lk.unlock();
+      for (int i = 0; i < 64; i++) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      lk.lock();
+      if (pred()) return;
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 300e-6) break;
+    }
+    cv.wait(lk, pred);
+  }
   void fail(const char* what) {
     std::lock_guard<std::mutex> lk(m);
     if (err.empty()) err = what;
@@ -183,7 +202,7 @@ struct StreamRunner {
       {
         std::unique_lock<std::mutex> lk(m);
         // the previous sweep's clouds must have been taken over before they are overwritten
-        cv.wait(lk, [this] { return stop || (!in.empty() && !reg_ready); });
+        wait_for(lk, [this] { return stop || (!in.empty() && !reg_ready); });
         if (stop) return;
         job = std::move(in.front());
         in.pop_front();
@@ -210,7 +229,7 @@ struct StreamRunner {
       {
         std::unique_lock<std::mutex> lk(m);
         // adopt() overwrites the full-resolution cloud the mapping stage takes from this object
-        cv.wait(lk, [this] { return stop || (reg_ready && !odom_ready); });
+        wait_for(lk, [this] { return stop || (reg_ready && !odom_ready); });
         if (stop) return;
       }
       const double ta = now();
@@ -240,7 +259,7 @@ struct StreamRunner {
       const double tw = now();
       {
         std::unique_lock<std::mutex> lk(m);
-        cv.wait(lk, [this] { return stop || odom_ready; });
+        wait_for(lk, [this] { return stop || odom_ready; });
         if (stop) return;
       }
       const double ta = now();
@@ -444,6 +463,20 @@ int loam_b200_host_nccl_unique_id(unsigned char* out128) {
 }
 int loam_b200_map_enable_sharding(void* h, int rank, int world, const unsigned char* nccl_id128) {
   return guarded([&] { ((MapH*)h)->m.enableSharding(rank, world, nccl_id128); return 0; });
+}
+int loam_b200_map_peer_export(void* h, unsigned char* out64) {
+  return guarded([&] { ((MapH*)h)->m.exportPeerHandle(out64); return 0; });
+}
+int loam_b200_map_enable_cube_sharding(void* h, int rank, int world, const unsigned char* handles, int slab_metres) {
+  return guarded([&] { ((MapH*)h)->m.enableCubeSharding(rank, world, handles, slab_metres); return 0; });
+}
+int loam_b200_map_enable_cube_sharding_local(void** hs, int world, int slab_metres) {
+  return guarded([&] {
+    std::vector<loam::BasicLaserMapping*> objs((size_t)world);
+    for (int r = 0; r < world; r++) objs[r] = &((MapH*)hs[r])->m;
+    loam::BasicLaserMapping::enableCubeShardingLocal(objs.data(), world, slab_metres);
+    return 0;
+  });
 }
 void* loam_b200_pipeline_scanreg(void* h) { return &((PipeH*)h)->reg; }
 void* loam_b200_pipeline_odom(void* h) { return &((PipeH*)h)->odom; }

@@ -91,6 +91,15 @@ class BasicLaserMapping {
   // all-reduces the 6x6 normal equations over NCCL every iteration (ncclId: 128 bytes from
   // loam_b200_comm_unique_id on rank 0; nullptr = slice only, the caller reduces)
   void enableSharding(int rank, int world, const unsigned char* ncclId);
+  // multi-GPU with the MAP sharded by cube slabs (one process per GPU; csrc/shard.cuh, include/loam_b200.h "peer"):
+  // exportPeerHandle() gives this rank's 64-byte inbox handle, enableCubeSharding() takes all of them in rank order.
+  // Afterwards this object stores only the slabs it owns (+ 2 m halo): seedMap() keeps the points that belong here,
+  // process() evaluates the queries that fall into its slabs and the per-iteration normal equations are all-reduced
+  // inside the iteration kernel over NVLink peer memory.  slabMetres: slab width (whole metres, default 10).
+  void exportPeerHandle(unsigned char out64[64]);
+  void enableCubeSharding(int rank, int world, const unsigned char* handles, int slabMetres = 10);
+  // the same for several objects of ONE process (tests / single-process multi-GPU): objs[r] becomes rank r
+  static void enableCubeShardingLocal(BasicLaserMapping** objs, int world, int slabMetres = 10);
   /** Test hook (not in the reference): keep a copy of the points of the cubes in view (upstream's internal
    *  _laserCloudCornerFromMap / _laserCloudSurfFromMap) after every process(); off by default, the persistent GPU map
    *  only needs their sizes. */
@@ -129,6 +138,7 @@ class BasicLaserMapping {
   bool _downsizedMapCreated = false;
   bool _retainFromMap = false;
   bool _sharded = false;
+  int _shardRank = 0, _shardWorld = 1, _shardSlab = 0;  // cube-sharded map (0 = off)
 
   b200::Context* _gpu;
   b200::GaussNewtonSolver* _solver;

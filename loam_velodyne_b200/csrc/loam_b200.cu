@@ -359,6 +359,7 @@ int fetch_ints(loam_b200_ctx* c, const int* d_src, int n, int* h_dst) {
 }  // namespace
 
 #include "comm.inc"
+#include "peer.inc"
 
 static thread_local bool tl_in_worker = false;
 
@@ -501,7 +502,8 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
                                        (int)sizeof(ClusterSortSmem)) == cudaSuccess;
   cudaGetLastError();
   if (c->partials.reserve(4096 * NEQ) != cudaSuccess || c->result.reserve(NEQ) != cudaSuccess ||
-      c->ticket.reserve(4) != cudaSuccess || c->result_host.reserve(NEQ) != cudaSuccess) {
+      c->ticket.reserve(4) != cudaSuccess || c->result_host.reserve(NEQ) != cudaSuccess ||
+      c->result_mailbox.reserve(64) != cudaSuccess || c->int_mailbox.reserve(512) != cudaSuccess) {
     cudaGetLastError();
     delete c;
     return LOAM_B200_ERR_CUDA;
@@ -553,6 +555,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   }
   c->odom_loop.destroy();
   c->map_loop.destroy();
+  if (c->peer_inbox) cudaFree(c->peer_inbox);
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->od_ring_off[1].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
@@ -560,6 +563,28 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+  return LOAM_B200_OK;
+}
+
+int loam_b200_set_priority(loam_b200_ctx* c, int level) {
+  CHECK_CTX(c);
+  int least = 0, greatest = 0;  // numerically: greatest priority <= least priority
+  LB_CUDA(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  const int mid = (least + greatest) / 2;
+  const int prio = level > 0 ? greatest : (level < 0 ? least : mid);
+  LB_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaStream_t s = nullptr;
+  LB_CUDA(c, cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
+  cudaStreamDestroy(c->stream);
+  c->stream = s;
+  c->main_stream = s;
+  // side lanes carry work nobody waits for immediately (tree rebuilds, the corner half of the map update): lowest
+  for (auto& l : c->lanes) {
+    cudaStream_t ls = nullptr;
+    LB_CUDA(c, cudaStreamCreateWithPriority(&ls, cudaStreamNonBlocking, least));
+    if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+    l.stream = ls;
+  }
   return LOAM_B200_OK;
 }
 
@@ -795,8 +820,9 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   if (nc + ns == 0) return LOAM_B200_OK;
   MapIterArgs a;
   fill_map_args(pose, a);
-  // this rank's contiguous slice of each query kind (everything when not sharded)
-  const int W = c->shard_world, R = c->shard_rank;
+  // this rank's contiguous slice of each query kind (everything when not sharded, and with the cube-sharded map, where
+  // every rank looks at every query and evaluates those whose transformed position falls into a cell it owns)
+  const int W = c->shard_slab > 0 ? 1 : c->shard_world, R = c->shard_slab > 0 ? 0 : c->shard_rank;
   const int c0 = (int)((long long)nc * R / W), c1 = (int)((long long)nc * (R + 1) / W);
   const int s0 = (int)((long long)ns * R / W), s1 = (int)((long long)ns * (R + 1) / W);
   const int lc = c1 - c0, ls = s1 - s0;
@@ -804,12 +830,15 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   const int nb = std::max(cb + sb, 1);
   LB_CUDA(c, c->partials.reserve((size_t)nb * NEQ));
   const bool dbg = coeff != nullptr;
-  const bool use_mailbox = !c->comm && c->shard_world == 1 && !c->prof_on && !walk_totals_host && !getenv_no_mailbox();
+  const ShardSpec sh = shard_spec_of(c);
+  const PeerReduce pr = peer_view_of(c);
+  const bool use_mailbox = !c->comm && (c->shard_world == 1 || c->peer_ready) && !c->prof_on && !walk_totals_host &&
+                           !getenv_no_mailbox();
   ResultMailbox mb{nullptr, 0};
   if (dbg) {
     LB_CUDA(c, c->dbg_coeff.reserve(nc + ns));
     LB_CUDA(c, c->dbg_sel.reserve(nc + ns));
-    if (W > 1) {
+    if (c->shard_world > 1) {
       LB_CUDA(c, cudaMemsetAsync(c->dbg_coeff.p, 0, (size_t)(nc + ns) * 16, c->stream));
       LB_CUDA(c, cudaMemsetAsync(c->dbg_sel.p, 0, (size_t)(nc + ns), c->stream));
     }
@@ -836,12 +865,12 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     if (c->map_use_store)
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
           store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
-          c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, nullptr, mb);
+          c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, nullptr, mb, sh, pr);
     else
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
           GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
           cb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
-          nullptr, nullptr, mb);
+          nullptr, nullptr, mb, sh, pr);
     LB_LAUNCH_CHECK(c);
     prof_end(c);
   }
@@ -1133,7 +1162,9 @@ int loam_b200_map_solve(loam_b200_ctx* c, const float rot[3], const float pos[3]
                         float delta_r_abort, loam_b200_lm_result* out) {
   CHECK_CTX(c);
   if (!rot || !pos || !out || max_iterations < 0) return LOAM_B200_ERR_ARG;
-  if (c->shard_world > 1 && !c->comm) return LOAM_B200_ERR_STATE;  // a shard without a communicator only yields partials
+  // a query slice without a communicator only yields partials; the cube-sharded map runs the per-iteration form (its
+  // all-reduce is fused into the iteration kernel)
+  if (c->shard_world > 1 && !c->comm) return LOAM_B200_ERR_STATE;
   const int nc = c->map_nc, ns = c->map_ns;
   memset(out, 0, sizeof *out);
   for (int i = 0; i < 3; i++) { out->rot[i] = rot[i]; out->pos[i] = pos[i]; }

@@ -297,6 +297,75 @@ __device__ __forceinline__ void mailbox_post_seq(const ResultMailbox& mb) {
   }
 }
 
+// ---- fused all-reduce of the normal equations over NVLink peer memory (multi-GPU, cube-sharded map) -------------------
+// Every rank owns an INBOX in its HBM that all peers have mapped (CUDA IPC): world x 2 slots of 32 words + world x 2
+// flags.  The CTA that folds a rank's partials stores its 32 sums straight into slot [rank][parity] of EVERY rank's inbox
+// (plain stores over NVLink), fences, raises flag [rank][parity] = seq in every inbox, waits until its own inbox holds
+// seq from every rank and adds the world contributions in rank order (double) -- so every rank ends up with the same
+// bits, with no host involvement and no separate collective launch.  seq comes from a device-side counter the ranks
+// advance in lock step (they execute the same sequence of reductions); two slots per rank (parity = seq & 1) suffice
+// because a rank can run at most one reduction ahead of the slowest peer.  A bounded spin turns a lost peer into a NaN
+// result instead of a hung GPU.
+constexpr int PEER_MAX = 8;
+struct PeerReduce {
+  float* slots[PEER_MAX];      // inbox of rank p: [world][2][32] words
+  unsigned* flags[PEER_MAX];   // inbox flags of rank p: [world][2]
+  unsigned* seq_counter;       // this rank's reduction counter (device memory)
+  int rank, world;
+};
+constexpr int PEER_INBOX_WORDS = PEER_MAX * 2 * 32;
+
+// Called by the 32 first threads of ONE CTA with their folded sum `v` (lane k = sum k); returns the all-reduced sum.
+// kind 0: float sums (double accumulation in rank order); kind 1: the words are ints (exact integer sum).
+template <int KIND>
+__device__ __forceinline__ float peer_allreduce32(const PeerReduce& pr, float v) {
+  const int lane = threadIdx.x & 31;
+  const unsigned seq = *pr.seq_counter + 1u;
+  const int par = (int)(seq & 1u);
+  for (int p = 0; p < pr.world; p++) pr.slots[p][(pr.rank * 2 + par) * 32 + lane] = v;
+  __threadfence_system();
+  __syncwarp();
+  if (lane < pr.world) {
+    *reinterpret_cast<volatile unsigned*>(&pr.flags[lane][pr.rank * 2 + par]) = seq;
+    // wait for the contribution of rank `lane` in my own inbox
+    const volatile unsigned* f = reinterpret_cast<volatile unsigned*>(&pr.flags[pr.rank][lane * 2 + par]);
+    const long long t0 = clock64();
+    while (*f != seq) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000ll) break;  // ~2 s: give up (result becomes NaN below)
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  bool ok = true;
+  for (int q = 0; q < pr.world; q++)
+    ok = ok && (*reinterpret_cast<volatile unsigned*>(&pr.flags[pr.rank][q * 2 + par]) == seq);
+  float out;
+  if (KIND == 0) {
+    double acc = 0.0;
+    for (int q = 0; q < pr.world; q++)
+      acc += (double)*reinterpret_cast<volatile float*>(&pr.slots[pr.rank][(q * 2 + par) * 32 + lane]);
+    out = ok ? (float)acc : __int_as_float(0x7fc00000);
+  } else {
+    int acc = 0;
+    for (int q = 0; q < pr.world; q++)
+      acc += *reinterpret_cast<volatile int*>(&pr.slots[pr.rank][(q * 2 + par) * 32 + lane]);
+    out = __int_as_float(ok ? acc : -1);
+  }
+  __syncwarp();
+  if (lane == 0) *pr.seq_counter = seq;
+  return out;
+}
+
+// stand-alone form: all-reduce n <= 32 ints in place (per-sweep counts of the sharded map)
+__global__ void peer_allreduce_ints_kernel(PeerReduce pr, int* data, int n) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const float v = __int_as_float(lane < n ? data[lane] : 0);
+  const float r = peer_allreduce32<1>(pr, v);
+  if (lane < n) data[lane] = __float_as_int(r);
+}
+
 // block reduction of NEQ accumulators -> partials[block]; the last block to finish folds all partials in block
 // order (double accumulation) into result[NEQ] and resets the ticket for the next launch.
 __device__ __forceinline__ bool reduce_normal_equations(float* acc, float* __restrict__ partials,
@@ -366,7 +435,8 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
                    unsigned long long* __restrict__ walk_totals, const MapLmState* __restrict__ lm = nullptr,
-                   ResultMailbox mb = ResultMailbox{nullptr, 0}) {
+                   ResultMailbox mb = ResultMailbox{nullptr, 0}, ShardSpec sh = ShardSpec{0, 1, 0},
+                   PeerReduce pr = PeerReduce{}) {
   // DEVLOOP (device-resident loop, lmstep.cuh): the arguments of the current iteration come from the state block
   // (staged in shared memory; the by-value `a_param` of the per-iteration API stays in the constant bank), and there
   // is nothing to do once the loop has converged
@@ -412,11 +482,16 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
       float sx, sy, sz;
       associate_to_map(a, po, sx, sy, sz);
       Cand5 best;
-      unsigned ws[2] = {0u, 0u};
-      grid_knn5_group8<STATS>(grid, sx, sy, sz, sub, gmask, s_pre[g], s_first[g], best, ws);
-      if (STATS) {
-        atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
-        atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
+#pragma unroll
+      for (int i = 0; i < 5; i++) { best.d[i] = 1.0f; best.id[i] = -1; }
+      // cube-sharded map: the rank owning the cell of the transformed point evaluates it, everybody else skips it
+      if (shard_owns(sh, store_cell(sx))) {
+        unsigned ws[2] = {0u, 0u};
+        grid_knn5_group8<STATS>(grid, sx, sy, sz, sub, gmask, s_pre[g], s_first[g], best, ws);
+        if (STATS) {
+          atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
+          atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
+        }
       }
       if (sub < 5) {  // lanes 0..4 fetch one neighbour each
         const int id = sub == 0 ? best.id[0] : sub == 1 ? best.id[1] : sub == 2 ? best.id[2] : sub == 3 ? best.id[3]
@@ -520,8 +595,10 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
     if (threadIdx.x < NEQ) {
       double r = 0.0;
       for (unsigned wv = 0; wv < NW; wv++) r += s_fold[wv][threadIdx.x];
-      result[threadIdx.x] = (float)r;
-      mailbox_post_value(mb, threadIdx.x, (float)r);
+      float rf = (float)r;
+      if (pr.world > 1) rf = peer_allreduce32<0>(pr, rf);  // fused all-reduce over NVLink peer memory (warp 0)
+      result[threadIdx.x] = rf;
+      mailbox_post_value(mb, threadIdx.x, rf);
     }
     if (threadIdx.x == 0) *ticket = 0u;
     __syncthreads();

@@ -56,14 +56,6 @@ __device__ __forceinline__ unsigned torus_key(const CellAxis& x, const CellAxis&
   const unsigned slot = (unsigned)(x.pm + CUBE_W * (y.pm + CUBE_H * z.pm));
   return (slot << 17) | (unsigned)((z.r * 50 + y.r) * 50 + x.r);
 }
-// Cell of a stored point.  The reference's cube index truncates (x + 25) / 50 toward zero and then decrements when
-// x + 25 < 0 (:540-553), which puts a coordinate that is EXACTLY a negative multiple of 50 below -25 one cube lower
-// than floor() would; such a point is filed under the cell below so that "cube = f(cell)" holds for every point.
-__device__ __forceinline__ int store_cell(float x) {
-  int c = (int)floorf(x);
-  if ((float)c == x && c + 25 < 0 && (c + 25) % 50 == 0) c--;
-  return c;
-}
 __device__ __forceinline__ unsigned torus_key_of(const float4& p) {
   return torus_key(cell_axis(store_cell(p.x), CUBE_W), cell_axis(store_cell(p.y), CUBE_H), cell_axis(store_cell(p.z), CUBE_D));
 }
@@ -200,7 +192,8 @@ __device__ __forceinline__ unsigned filter_key_of(const float4& q, int i, const 
 // S[0..n_ins) = pointAssociateToMap(stackDS) with the optimised pose (:536-577) + its filter key
 __global__ void store_insert_kernel(const float4* __restrict__ stack_ds, int n, MapIterArgs a, CubeGrid g,
                                     const unsigned char* __restrict__ rank_of_cube, float inv_leaf,
-                                    float4* __restrict__ s_pts, unsigned* __restrict__ keys, int* __restrict__ vals) {
+                                    float4* __restrict__ s_pts, unsigned* __restrict__ keys, int* __restrict__ vals,
+                                    ShardSpec sh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 q = stack_ds[i];
@@ -208,7 +201,9 @@ __global__ void store_insert_kernel(const float4* __restrict__ stack_ds, int n, 
   associate_to_map(a, q, x, y, z);
   const float4 p = make_float4(x, y, z, q.w);
   s_pts[i] = p;
-  keys[i] = filter_key_of(p, i, g, rank_of_cube, inv_leaf);
+  // a sharded map only takes the points of the cells this rank stores (the others go to the rank that does)
+  keys[i] = shard_stores(sh, store_cell(p.x)) ? filter_key_of(p, i, g, rank_of_cube, inv_leaf)
+                                              : (((unsigned)CLS_DROP << 24) | ((unsigned)i & 0xffffffu));
   vals[i] = i;
 }
 

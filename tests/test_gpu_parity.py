@@ -666,6 +666,49 @@ def test_sharded_iteration_partials_sum_to_total(ctx, scene, map_200k):
         assert _rel(AtA, total["AtA"]) <= 1e-5 and _rel(AtB, total["AtB"]) <= 1e-5
 
 
+def test_cube_sharded_map_two_ranks_one_gpu(scene, sweeps_vlp16, map_200k):
+    """The cube-sharded map with its fused peer all-reduce, two ranks as two pipelines of this process on ONE GPU (the
+    inboxes are plain device pointers here; across processes they are CUDA IPC mappings): each rank holds about half of
+    the map (+ halo), evaluates the queries of its slabs, the iteration kernels exchange their partial sums through each
+    other's inbox, and both ranks follow the unsharded trajectory within 1e-4 with bit-identical poses."""
+    import threading
+    from loam_velodyne_b200 import api
+    corner, surf = map_200k
+    single = api.Pipeline()
+    single.seed_map(corner, surf)
+    ranks = [api.Pipeline(), api.Pipeline()]
+    api.enable_cube_sharding_local([p.mapping for p in ranks], slab_metres=10)
+    for p in ranks:
+        p.seed_map(corner, surf)
+    out = [[], []]
+    errs = []
+
+    def drive(r):
+        try:
+            for pts, rs in sweeps_vlp16[:6]:
+                out[r].append(ranks[r].sweep(pts, rs))
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=drive, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    ref = [single.sweep(pts, rs) for pts, rs in sweeps_vlp16[:6]]
+    for t in th:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert len(out[0]) == 6 and len(out[1]) == 6
+    for i in range(6):
+        (_, od0, aft0, _), (_, od1, aft1, _), (_, od_s, aft_s, _) = out[0][i], out[1][i], ref[i]
+        np.testing.assert_array_equal(aft0, aft1)  # same sums in the same order on both ranks
+        np.testing.assert_array_equal(od0, od_s)   # odometry is replicated
+        assert np.isfinite(aft0).all()
+        assert np.abs(aft0 - aft_s).max() <= POSE_TOL, (i, aft0, aft_s)
+    n_single = single.mapping.cloud("surf_cubes").shape[0]
+    n0, n1 = ranks[0].mapping.cloud("surf_cubes").shape[0], ranks[1].mapping.cloud("surf_cubes").shape[0]
+    assert max(n0, n1) < 0.9 * n_single and n0 + n1 >= n_single  # each rank holds a part, together (with halos) all of it
+
+
 def test_nccl_sharded_pipeline_two_gpus(tmp_path):
     """Two ranks, two GPUs, NCCL: the sharded stream (all-reduce per LM iteration) follows the single-GPU stream."""
     import subprocess
@@ -676,7 +719,22 @@ def test_nccl_sharded_pipeline_two_gpus(tmp_path):
     root = os.path.dirname(HERE)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "run_sharded.py"),
-                        "--sweeps", "6", "--check"], capture_output=True, text=True, timeout=900)
+                        "--sweeps", "6", "--check", "--mode", "nccl"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARDED_OK" in r.stdout
+
+
+def test_cube_sharded_pipeline_two_gpus(tmp_path):
+    """Two ranks, two GPUs, one process each: cube-sharded map, fused all-reduce over NVLink peer memory (CUDA IPC)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(root, "tools", "run_sharded.py"),
+                        "--sweeps", "6", "--check", "--mode", "peer"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_OK" in r.stdout
 

@@ -116,3 +116,37 @@ def test_bench_core_partition():
     assert bench.partition_cores(0, 8, gpus, {0, 1, 2, 3, 4, 5, 6, 7}, first) is None
     # CPUs outside the GPU's node only: fall back to what is allowed
     assert bench.partition_cores(0, 1, gpus, set(range(32, 48)), first) == list(range(32, 48))
+
+
+def test_slab_partition_covers_every_cell_once_and_halo_is_two_cells(build_libs):
+    """Host logic of the cube-sharded map (csrc/shard.cuh): every 1 m cell has exactly one owner, owners cycle slab by slab,
+    and a rank stores exactly its cells plus two halo cells on both sides of every slab."""
+    from loam_velodyne_b200 import api
+    for world in (1, 2, 3, 8):
+        for slab in (1, 5, 10, 25):
+            owners = [api.shard_owner(c, world, slab) for c in range(-130, 131)]
+            assert set(owners) == set(range(world)) or 261 < slab * world
+            for c, o in zip(range(-130, 131), owners):
+                assert 0 <= o < world
+                assert o == ((c // slab) % world)  # python floor division: slabs tile the negative axis too
+            for rank in range(world):
+                for c in range(-60, 61):
+                    near = any(api.shard_owner(c + d, world, slab) == rank for d in (-2, -1, 0, 1, 2))
+                    assert api.shard_stores(c + 0.5, rank, world, slab) == (near or world == 1)
+    # a coordinate that is exactly a negative multiple of 50 below -25 is filed one cell lower (the reference's truncating
+    # cube index, BasicLaserMapping.cpp:540-553): the partition follows the stored cell
+    assert api.shard_stores(-75.0, api.shard_owner(-76, 8, 10), 8, 10)
+
+
+def test_seed_points_partition_is_a_cover(build_libs):
+    """Every seed point is stored by at least one rank and owned by exactly one (no map point is lost by sharding)."""
+    from loam_velodyne_b200 import api
+    rng = np.random.RandomState(4)
+    xs = rng.uniform(-125, 125, 2000).astype(np.float32)
+    for world, slab in ((2, 10), (8, 10), (8, 7)):
+        stored = np.array([[api.shard_stores(x, r, world, slab) for r in range(world)] for x in xs])
+        assert stored.any(axis=1).all()
+        owners = np.array([api.shard_owner(int(np.floor(x)), world, slab) for x in xs])
+        assert all(stored[i, owners[i]] for i in range(len(xs)))
+        # storage overhead of the halo: (slab + 4) / slab on average
+        assert abs(stored.sum() / len(xs) - min(world, (slab + 4) / slab)) < 0.15
