@@ -34,7 +34,8 @@ WORKLOADS = {
     # name: (lidar factory name, map points, description)
     "vlp16_200k": ("vlp16", 200_000, "VLP-16 16x1800 sweeps, 200k-pt map (BASELINE config 2)"),
     "hdl64_1m": ("hdl64", 1_000_000, "HDL-64E 64x2048 sweeps, 1M-pt surrounding map (BASELINE config 3)"),
-    "hdl64_10m": ("hdl64", 10_000_000, "HDL-64E 64x2048 sweeps, 10M-pt map (BASELINE config 4, single-GPU variant)"),
+    "hdl64_10m": ("hdl64", 10_000_000, "HDL-64E 64x2048 sweeps, 10M-pt map (BASELINE config 4)"),
+    "dense128_20m": ("dense128", 20_000_000, "128-ring x 4096 dense sweeps, 20M-pt map (BASELINE config 5)"),
 }
 
 
@@ -223,11 +224,21 @@ def run_cuda(args, rank, world, local_rank):
     sweeps = [(pinned[i].numpy(), sweeps[i][1]) for i in range(len(sweeps))]
     torch.cuda.synchronize()
 
+    def all_gather_bytes(b):
+        mine = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        return b"".join(bytes(t.cpu().tolist()) for t in every)
+
+    # what the timed windows run on: (corner map, surface map, host sweeps, device sweeps, cube-sharded?)
+    work = {"corner": corner, "surf": surf, "sweeps": sweeps, "d_sweeps": d_sweeps, "cube_sharded": sharded}
+
     def fresh_pipeline():
         p = api.Pipeline()
-        p.seed_map(corner, surf)
-        if sharded:
-            p.mapping.enable_sharding(rank, world, fresh_nccl_id())
+        if work["cube_sharded"]:
+            # the MAP sharded by cube slabs over the ranks, all-reduce fused into the iteration kernel (NVLink peer memory)
+            p.mapping.enable_cube_sharding(rank, world, all_gather_bytes(p.mapping.peer_export()), args.slab)
+        p.seed_map(work["corner"], work["surf"])
         return p
 
     def window(streaming, device_input):
@@ -236,6 +247,7 @@ def run_cuda(args, rank, world, local_rank):
         helper thread joined inside the timed region.  Returns (max-over-ranks seconds, poses of all W + K sweeps, stage
         seconds, iteration counts)."""
         pipe = fresh_pipeline()
+        sweeps, d_sweeps = work["sweeps"], work["d_sweeps"]
         poses = []
         acc = {"stage": np.zeros(5), "it_o": 0, "it_m": 0}
 
@@ -317,6 +329,12 @@ def run_cuda(args, rank, world, local_rank):
                 if not (np.array_equal(od0, od1) and np.array_equal(aft0, aft1)):
                     raise SystemExit(f"arm '{nm}' disagrees with the streaming device-input arm: {aft0} vs {aft1}")
 
+    # ---- N > 1: ONE stream against a map that is sharded over the GPUs (BASELINE configs 4 / 5): cube slabs + 2 m halo,
+    # fused all-reduce of the normal equations over NVLink peer memory; reported next to the replica figure
+    shard_report = None
+    if world > 1 and not sharded and not args.no_sharded:
+        shard_report = sharded_section(args, api, torch, dev, rank, world, work, arm, ref_sweeps=None)
+
     # ---- kernel-level pass (rank 0, N = 1 semantics): north-star kernel roofline through the kernel ABI
     out = None
     if rank == 0:
@@ -338,7 +356,8 @@ def run_cuda(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][2], "sweep_points": n_pts, "cpu_binding": pinned_cores,
                        "map_points": int(corner.shape[0] + surf.shape[0]),
-                       "mode": ("sharded: one stream, query slices + all-reduce of AtA/AtB per LM iteration" if sharded
+                       "mode": ("sharded: one stream, map sharded by cube slabs (+2 m halo) over the GPUs, all-reduce of AtA/AtB fused "
+                                "into the iteration kernel over NVLink peer memory" if sharded
                                 else "replicas: one independent sweep stream and map per GPU, no data-path collective"
                                 if world > 1 else "single"),
                        "execution": "registration / odometry / mapping as three concurrent single-threaded stages over "
@@ -365,12 +384,48 @@ def run_cuda(args, rank, world, local_rank):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
+        if shard_report is not None:
+            out["sharded"] = shard_report
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, corner, surf, sweeps, ref_poses)
             out["pose_delta_vs_reference"] = out["cpu_baseline"].pop("pose_delta_vs_reference")
     if world > 1:
         dist.destroy_process_group()
     return out
+
+
+def sharded_section(args, api, torch, dev, rank, world, work, arm, ref_sweeps):
+    """One sweep stream on `world` GPUs with the map sharded by cube slabs (DESIGN.md "Multi-GPU"): every rank feeds the
+    same sweeps (registration and odometry are replicated), holds its slabs of the map, evaluates the queries
+    that fall into them; the per-iteration all-reduce is fused into the iteration kernel.  Timed like the main arms."""
+    lidar_name, m, desc = WORKLOADS[args.sharded_workload]
+    n_total = args.warmup + args.steps
+    _, corner, surf, sweeps = make_workload(args.sharded_workload, n_total, 0)  # the same stream on every rank
+    d_sweeps = [torch.from_numpy(p).to(dev) for p, _ in sweeps]
+    pinned = [torch.from_numpy(p).pin_memory() for p, _ in sweeps]
+    sweeps = [(pinned[i].numpy(), sweeps[i][1]) for i in range(len(sweeps))]
+    saved = dict(work)
+    work.update({"corner": corner, "surf": surf, "sweeps": sweeps, "d_sweeps": d_sweeps, "cube_sharded": True})
+    try:
+        a_stream = arm(True, True, min(args.min_seconds, 0.2), 12)
+        a_seq = arm(False, True, 0.0, 3)
+    finally:
+        work.clear()
+        work.update(saved)
+    if rank != 0:
+        return None
+    ms = lambda x: round(1e3 * x, 3)
+    last = a_seq["runs"][0]
+    return {"workload": desc, "map_points": int(corner.shape[0] + surf.shape[0]), "n_gpus": world,
+            "what": "ONE sweep stream, map sharded by %d m cube slabs (+ 2 m halo) over the GPUs, queries evaluated by the owner "
+                    "of their cell, all-reduce of the 32 normal-equation sums fused into the iteration kernel (peer stores over "
+                    "NVLink, CUDA IPC inboxes); registration and odometry replicated" % args.slab,
+            "value": round(args.steps / a_stream["seconds"], 3), "unit": "sweeps/s", "scaling": "strong",
+            "window_ms_min_median_max": [ms(a_stream["min"]), ms(a_stream["seconds"]), ms(a_stream["max"])],
+            "windows": a_stream["windows"],
+            "sequential_value": round(args.steps / a_seq["seconds"], 3),
+            "sequential_mapping_ms_per_sweep": round(1e3 * float(last[2][3]) / args.steps, 4),
+            "map_iters_per_sweep": round(last[4] / args.steps, 2)}
 
 
 def kernel_roofline(args, api, corner, surf, sweep, pipe):
@@ -573,6 +628,10 @@ def main():
     ap.add_argument("--workload", default="hdl64_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sweeps", type=int, default=12, help="sweeps timed for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slab", type=int, default=10, help="slab width in metres of the cube-sharded map (N > 1)")
+    ap.add_argument("--sharded-workload", default="hdl64_10m", choices=sorted(WORKLOADS),
+                    help="N > 1: workload of the additional single-stream run on the cube-sharded map")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the cube-sharded single-stream section")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="repeat the K-step timed window (fresh pipeline each) until the windows add up to this")
     ap.add_argument("--max-windows", type=int, default=100)

@@ -666,47 +666,23 @@ def test_sharded_iteration_partials_sum_to_total(ctx, scene, map_200k):
         assert _rel(AtA, total["AtA"]) <= 1e-5 and _rel(AtB, total["AtB"]) <= 1e-5
 
 
-def test_cube_sharded_map_two_ranks_one_gpu(scene, sweeps_vlp16, map_200k):
-    """The cube-sharded map with its fused peer all-reduce, two ranks as two pipelines of this process on ONE GPU (the
-    inboxes are plain device pointers here; across processes they are CUDA IPC mappings): each rank holds about half of
-    the map (+ halo), evaluates the queries of its slabs, the iteration kernels exchange their partial sums through each
-    other's inbox, and both ranks follow the unsharded trajectory within 1e-4 with bit-identical poses."""
-    import threading
+def test_cube_sharded_single_rank_equals_unsharded(scene, sweeps_vlp16, map_200k):
+    """World 1 of the cube-sharded mode (peer wiring on, one rank owning every slab) is the unsharded computation, bit for
+    bit: the ownership test, the store filter and the fused epilogue are all in the code path.  (Two ranks need two GPUs --
+    a rank's kernel spins for its peers, and on one GPU the peer can be blocked in an allocation behind that very kernel --
+    see test_cube_sharded_pipeline_two_gpus.)"""
     from loam_velodyne_b200 import api
     corner, surf = map_200k
-    single = api.Pipeline()
+    single, sharded = api.Pipeline(), api.Pipeline()
+    api.enable_cube_sharding_local([sharded.mapping], slab_metres=10)
     single.seed_map(corner, surf)
-    ranks = [api.Pipeline(), api.Pipeline()]
-    api.enable_cube_sharding_local([p.mapping for p in ranks], slab_metres=10)
-    for p in ranks:
-        p.seed_map(corner, surf)
-    out = [[], []]
-    errs = []
-
-    def drive(r):
-        try:
-            for pts, rs in sweeps_vlp16[:6]:
-                out[r].append(ranks[r].sweep(pts, rs))
-        except Exception as e:  # pragma: no cover
-            errs.append(e)
-
-    th = [threading.Thread(target=drive, args=(r,)) for r in range(2)]
-    for t in th:
-        t.start()
-    ref = [single.sweep(pts, rs) for pts, rs in sweeps_vlp16[:6]]
-    for t in th:
-        t.join(timeout=120)
-    assert not errs, errs
-    assert len(out[0]) == 6 and len(out[1]) == 6
-    for i in range(6):
-        (_, od0, aft0, _), (_, od1, aft1, _), (_, od_s, aft_s, _) = out[0][i], out[1][i], ref[i]
-        np.testing.assert_array_equal(aft0, aft1)  # same sums in the same order on both ranks
-        np.testing.assert_array_equal(od0, od_s)   # odometry is replicated
-        assert np.isfinite(aft0).all()
-        assert np.abs(aft0 - aft_s).max() <= POSE_TOL, (i, aft0, aft_s)
-    n_single = single.mapping.cloud("surf_cubes").shape[0]
-    n0, n1 = ranks[0].mapping.cloud("surf_cubes").shape[0], ranks[1].mapping.cloud("surf_cubes").shape[0]
-    assert max(n0, n1) < 0.9 * n_single and n0 + n1 >= n_single  # each rank holds a part, together (with halos) all of it
+    sharded.seed_map(corner, surf)
+    for pts, rs in sweeps_vlp16[:4]:
+        _, od_a, aft_a, _ = single.sweep(pts, rs)
+        _, od_b, aft_b, _ = sharded.sweep(pts, rs)
+        np.testing.assert_array_equal(od_a, od_b)
+        np.testing.assert_array_equal(aft_a, aft_b)
+    np.testing.assert_array_equal(single.mapping.cloud("surf_cubes"), sharded.mapping.cloud("surf_cubes"))
 
 
 def test_nccl_sharded_pipeline_two_gpus(tmp_path):
