@@ -30,6 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ENTRY_BYTES = 16          # bytes of one cell-table entry (csrc/gridnn.cuh)
+TRAFFIC_FILE = "r1_map_iterate_traffic.json"       # committed ncu DRAM bytes per launch, config 3
+TRAFFIC_FILE_HBM = "r2_map_iterate_hbm_traffic.json"  # ... config 5
+
 WORKLOADS = {
     # name: (lidar factory name, map points, description)
     "vlp16_200k": ("vlp16", 200_000, "VLP-16 16x1800 sweeps, 200k-pt map (BASELINE config 2)"),
@@ -386,6 +390,8 @@ def run_cuda(args, rank, world, local_rank):
         }
         if shard_report is not None:
             out["sharded"] = shard_report
+        if world == 1 and not args.no_hbm_roofline:
+            out["roofline_hbm"] = hbm_roofline(args, api)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, corner, surf, sweeps, ref_poses)
             out["pose_delta_vs_reference"] = out["cpu_baseline"].pop("pose_delta_vs_reference")
@@ -429,67 +435,72 @@ def sharded_section(args, api, torch, dev, rank, world, work, arm, ref_sweeps):
 
 
 def kernel_roofline(args, api, corner, surf, sweep, pipe):
-    """North-star kernel (fused 5-NN + fit + Jacobian + reduction = map_iterate_kernel) timed with CUDA events on its
-    own stream through the kernel ABI, on the same queries / map the pipeline uses."""
-    ctx = api.Ctx(int(os.environ.get("LOCAL_RANK", "0")))
-    # the persistent map does not materialise the from-map clouds: a private, unsharded pipeline runs two sweeps with
-    # the test hook that retains them (never part of a timed region)
+    """North-star kernel (fused 5-NN + fit + Jacobian + reduction = map_iterate_kernel) exactly as the pipeline launches it
+    (map_iterate_kernel<false, MapCellLookup, false> on the mapping stage's own context and persistent map), timed with
+    CUDA events on that context's stream over 50 launches (loam_b200_map_kernel_profile)."""
     pipe = api.Pipeline()
     pipe.seed_map(corner, surf)
-    pipe.mapping.retain_from_map(True)
-    for _ in range(2):
+    for _ in range(3):
         pipe.sweep(*sweep)
-    cq = pipe.mapping.cloud("corner_stack_ds")
-    sq = pipe.mapping.cloud("surf_stack_ds")
-    cm = pipe.mapping.cloud("corner_from_map")
-    sm = pipe.mapping.cloud("surf_from_map")
-    twist = pipe.mapping.twist("aft")
-    ctx.tree_build(api.TREE_MAP_CORNER, cm)
-    ctx.tree_build(api.TREE_MAP_SURF, sm)
-    ctx.map_set_queries(cq, sq)
-    _, probes, cands = ctx.map_iterate_stats(twist)
-    nq = cq.shape[0] + sq.shape[0]
-    for _ in range(5):
-        ctx.map_iterate(twist)
-    ctx.profile(True)
-    reps = 50
-    for _ in range(reps):
-        ctx.map_iterate(twist)
-    ms, n = ctx.profile_get()["map_iter"]
-    ctx.profile(False)
-    # algorithmic bytes per launch (DESIGN.md "Roofline"): every query reads itself (16 B), its 27 cell-table entries
-    # (16 B each, counted as probed) and every candidate point of the occupied cells (16 B each); the 36-float result
-    alg_bytes = nq * 16 + probes * 16 + cands * 16 + 36 * 4
-    dur_s = ms / n * 1e-3
+    prof = pipe.mapping.kernel_profile(50)
+    nq, probes, cands = prof["queries"], prof["probes_per_query"] * prof["queries"], prof["candidates_per_query"] * prof["queries"]
+    # algorithmic bytes per launch (DESIGN.md "Roofline"): every query reads itself (16 B), the cell-table entries it
+    # probes and every candidate point of the occupied cells (16 B each); the 36-float result
+    alg_bytes = nq * 16 + probes * ENTRY_BYTES + cands * 16 + 36 * 4
+    dur_s = prof["avg_us"] * 1e-6
     peak, how = measure_peaks()
     achieved = alg_bytes / dur_s / 1e9
-    # launches per sweep of the whole pipeline: count through a separate profiled pipeline pass is not possible from
-    # here (three private contexts); the kernel ABI context exposes its own launch counter instead
-    launches_per_sweep = estimate_launches(api, pipe)
-    ctx.close()
+    del pipe
     # DRAM bytes per launch from the committed ncu --set full capture of this kernel on this workload (a number printed
     # under a profiler is never measured here); only quoted for the workload it was captured on
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_map_iterate_traffic.json")
+    tp = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
     if args.workload == "hdl64_1m" and os.path.exists(tp):
         with open(tp) as fh:
             tj = json.load(fh)
         traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj["source"]
-    return ({"bound": "hbm", "kernel": "map_iterate_kernel (fused fixed-radius 5-NN + line/plane fit + Jacobian + 6x6 reduction)",
+    return ({"bound": "hbm", "kernel": "map_iterate_kernel<MapCellLookup> (fused fixed-radius 5-NN + line/plane fit + Jacobian + "
+                                       "6x6 reduction), the instantiation the pipeline launches, on the mapping stage's own context",
              "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
              "traffic": traffic, "traffic_source": traffic_src, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes),
              "avg_launch_us": round(dur_s * 1e6, 2), "queries": int(nq), "table_probes_per_query": round(probes / max(nq, 1), 2),
              "candidate_points_per_query": round(cands / max(nq, 1), 2),
-             "note": "1M-pt map + nodes fit in the 126 MB L2, so DRAM traffic is structurally far below the algorithmic bytes"},
-            launches_per_sweep)
+             "note": "1M-pt map + cell table fit in the 126 MB L2, so DRAM traffic is structurally far below the algorithmic "
+                     "bytes and the fraction of the HBM roofline small; the HBM-bound regime of the same kernel is 'roofline_hbm'"},
+            None)
 
 
-def estimate_launches(api, pipe):
-    """Kernels launched per sweep: 2 (features) + trees (4 builds x ~19) + iterations + transforms + voxel calls."""
-    it_o = max(pipe.odom.last_iterations(), 1)
-    it_m = max(pipe.mapping.last_iterations(), 1)
-    per_tree = 3 + 4 * 3 + 4
-    return 2 + 4 * per_tree + it_o + it_m + 4
+def hbm_roofline(args, api):
+    """The same kernel where it IS bound by HBM: BASELINE config 5 -- a 128-ring x 4096 sweep against a 20 M-point map held
+    by the pipeline's persistent store (320 MB of points + cell table: far beyond the 126 MB L2); the queries of one sweep
+    touch more candidate data than L2 holds.  CUDA-event time of the pipeline's own instantiation, as above."""
+    from loam_velodyne_b200 import synth
+    scene = synth.make_scene()
+    corner, surf = synth.make_map(scene, 20_000_000)
+    lidar = synth.Lidar.dense128()
+    sweeps = [synth.make_sweep(scene, lidar, i, yaw_rate=math.radians(5.0)) for i in range(2)]
+    pipe = api.Pipeline()
+    pipe.seed_map(corner, surf)
+    for s in sweeps:
+        pipe.sweep(*s)
+    prof = pipe.mapping.kernel_profile(20)
+    nq, probes, cands = prof["queries"], prof["probes_per_query"] * prof["queries"], prof["candidates_per_query"] * prof["queries"]
+    alg_bytes = nq * 16 + probes * ENTRY_BYTES + cands * 16 + 36 * 4
+    dur_s = prof["avg_us"] * 1e-6
+    peak, how = measure_peaks()
+    del pipe
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", TRAFFIC_FILE_HBM)
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            tj = json.load(fh)
+        traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj["source"]
+    return {"bound": "hbm", "workload": "128-ring x 4096 sweep vs 20M-pt map (BASELINE config 5), pipeline store", "kernel": "map_iterate_kernel<MapCellLookup>",
+            "achieved": round(alg_bytes / dur_s / 1e9, 2), "peak": peak, "unit": "GB/s", "frac": round(alg_bytes / dur_s / 1e9 / peak, 5),
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
+            "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_us": round(dur_s * 1e6, 2), "queries": int(nq),
+            "table_probes_per_query": round(prof["probes_per_query"], 2), "candidate_points_per_query": round(prof["candidates_per_query"], 2),
+            "queries_per_second": round(nq / dur_s, 0), "map_points": int(corner.shape[0] + surf.shape[0])}
 
 
 def cpu_baseline(args, corner, surf, sweeps, gpu_poses=None):
@@ -631,6 +642,7 @@ def main():
     ap.add_argument("--slab", type=int, default=10, help="slab width in metres of the cube-sharded map (N > 1)")
     ap.add_argument("--sharded-workload", default="hdl64_10m", choices=sorted(WORKLOADS),
                     help="N > 1: workload of the additional single-stream run on the cube-sharded map")
+    ap.add_argument("--no-hbm-roofline", action="store_true", help="skip the config-5 (20 M-point map) kernel measurement")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the cube-sharded single-stream section")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="repeat the K-step timed window (fresh pipeline each) until the windows add up to this")

@@ -82,6 +82,10 @@ int loam_b200_map_cloud_copy(void* h, int which, float* out);
 int loam_b200_map_last_iterations(void* h);
 /* host wall seconds of the last process(): begin_sweep, LM loop, end_sweep, surround map */
 int loam_b200_map_last_phase_seconds(void* h, double* out4);
+/* measurement hook: the scan-to-map iteration kernel exactly as this object launches it (own context, persistent map, the
+ * queries of the last process()), CUDA-event time over `reps` launches at the current pose.  out5 = average launch
+ * microseconds, queries, table probes / query, candidate points / query, selected correspondences */
+int loam_b200_map_kernel_profile(void* h, int reps, double* out5);
 /* test hook: keep a copy of laserCloudCornerFromMap / laserCloudSurfFromMap (cloud ids 2, 3) at every process() */
 int loam_b200_map_retain_from_map(void* h, int on);
 /* multi-GPU, one process per GPU: rank 0 calls loam_b200_host_nccl_unique_id and distributes the 128 bytes; every rank

@@ -185,6 +185,7 @@ def lib():
         "loam_b200_map_retain_from_map": (C.c_int, [vp, C.c_int]),
         "loam_b200_host_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
+        "loam_b200_map_kernel_profile": (C.c_int, [vp, C.c_int, _D]),
         "loam_b200_map_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_cube_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
         "loam_b200_map_enable_cube_sharding_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
@@ -612,6 +613,13 @@ class LaserMapping(_Handle):
             buf = (C.c_ubyte * 128).from_buffer_copy(nccl_id)
             self._ck(self.L.loam_b200_map_enable_sharding(self.h, rank, world, buf), "enableSharding")
 
+
+    def kernel_profile(self, reps=50):
+        """The scan-to-map iteration kernel as this object launches it, timed with CUDA events (see the header)."""
+        out = np.zeros(5, np.float64)
+        self._ck(self.L.loam_b200_map_kernel_profile(self.h, reps, out.ctypes.data_as(_D)), "map_kernel_profile")
+        return {"avg_us": float(out[0]), "queries": int(out[1]), "probes_per_query": float(out[2]),
+                "candidates_per_query": float(out[3]), "n_selected": int(out[4])}
 
     # ---- multi-GPU with the map sharded by cube slabs (include/loam_b200_host.h)
     def peer_export(self) -> bytes:

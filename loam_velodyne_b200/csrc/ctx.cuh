@@ -226,6 +226,10 @@ struct loam_b200_ctx {
   loamb::DevBuf<float> bin_xyz;           // raw xyz of the ring-binning front end (frontend.cuh)
   loamb::DevBuf<unsigned char> lm_state;  // OdomLmState + MapLmState (lmstep.cuh): pose of the device-resident loops
   loamb::LoopGraph odom_loop, map_loop;   // their loop graphs (loam_b200_odom_solve / loam_b200_map_solve)
+  // map_iterate_v2_kernel (persistent, warp-specialised, bulk-staged candidates): persistent grid per instantiation
+  // [store / bounding-box lookup][stage API / device loop] for the candidate capacity in use, 0 = not yet queried
+  int map_v2_grid[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  bool map_v2_off = false;
 
   // odometry
   loamb::DevBuf<float4> od_q;  // sharp then flat

@@ -145,6 +145,7 @@ struct StreamRunner {
   std::string err;
   // seconds each stage spent working / waiting for its neighbours (loam_b200_pipeline_stage_seconds)
   double busy[3] = {0, 0, 0}, idle[3] = {0, 0, 0}, handoff[3] = {0, 0, 0};
+  double t_reset = 0.0;  // waiting that began before the last reset of the counters is not counted
   static constexpr size_t MAX_QUEUED = 2;
 
   explicit StreamRunner(PipeH* pipe) : p(pipe), device(loam::b200::defaultDevice()) {
@@ -213,7 +214,7 @@ struct StreamRunner {
         p->reg.r.processDeviceSweep(loam::Time(), job.d_pts, job.rings.data(), (int)job.rings.size());
       else
         p->reg.r.processPackedSweep(loam::Time(), job.pts, job.rings.data(), (int)job.rings.size());
-      idle[0] += tb - tw;
+      idle[0] += tb - std::max(tw, t_reset);
       busy[0] += now() - tb;
       {
         std::lock_guard<std::mutex> lk(m);
@@ -242,7 +243,7 @@ struct StreamRunner {
       const double tb = now();
       o.process();
       o.transformLaserCloudToEnd();
-      idle[1] += ta - tw;
+      idle[1] += ta - std::max(tw, t_reset);
       handoff[1] += tb - ta;
       busy[1] += now() - tb;
       {
@@ -274,7 +275,7 @@ struct StreamRunner {
       const double tb = now();
       r.ok = mp.process(loam::Time()) ? 1 : 0;
       twist6(mp.transformAftMapped(), r.aft);
-      idle[2] += ta - tw;
+      idle[2] += ta - std::max(tw, t_reset);
       handoff[2] += tb - ta;
       busy[2] += now() - tb;
       {
@@ -464,6 +465,37 @@ int loam_b200_host_nccl_unique_id(unsigned char* out128) {
 int loam_b200_map_enable_sharding(void* h, int rank, int world, const unsigned char* nccl_id128) {
   return guarded([&] { ((MapH*)h)->m.enableSharding(rank, world, nccl_id128); return 0; });
 }
+// The scan-to-map iteration kernel exactly as this object launches it (its own context, persistent map store, the queries
+// of the last process() call), timed with CUDA events over `reps` launches at the current mapped pose.
+// out5: average launch microseconds, queries, table probes per query, candidate points per query, selected correspondences
+int loam_b200_map_kernel_profile(void* h, int reps, double* out5) {
+  return guarded([&] {
+    auto& m = ((MapH*)h)->m;
+    loam_b200_ctx* c = m.deviceContext()->get();
+    auto ck = [&](int rc, const char* what) { m.deviceContext()->check(rc, what); };
+    loam_b200_pose pose;
+    b200::fillPose(m.transformAftMapped(), pose);
+    loam_b200_normal_eq ne;
+    unsigned long long probes = 0, cands = 0;
+    ck(loam_b200_map_iterate_stats(c, &pose, &ne, &probes, &cands), "loam_b200_map_iterate_stats");
+    for (int i = 0; i < 5; i++) ck(loam_b200_map_iterate(c, &pose, &ne), "loam_b200_map_iterate");
+    ck(loam_b200_profile_reset(c), "loam_b200_profile_reset");
+    ck(loam_b200_profile_enable(c, 1), "loam_b200_profile_enable");
+    for (int i = 0; i < reps; i++) ck(loam_b200_map_iterate(c, &pose, &ne), "loam_b200_map_iterate");
+    double ms = 0.0;
+    long long launches = 0;
+    ck(loam_b200_profile_get(c, LOAM_B200_K_MAP_ITER, &ms, &launches), "loam_b200_profile_get");
+    ck(loam_b200_profile_enable(c, 0), "loam_b200_profile_enable");
+    const double nq = (double)(m.cornerStackSize() + m.surfStackSize());
+    out5[0] = launches > 0 ? 1e3 * ms / (double)launches : 0.0;
+    out5[1] = nq;
+    out5[2] = nq > 0 ? (double)probes / nq : 0.0;
+    out5[3] = nq > 0 ? (double)cands / nq : 0.0;
+    out5[4] = (double)ne.n_selected;
+    return 0;
+  });
+}
+
 int loam_b200_map_peer_export(void* h, unsigned char* out64) {
   return guarded([&] { ((MapH*)h)->m.exportPeerHandle(out64); return 0; });
 }
@@ -594,6 +626,7 @@ int loam_b200_pipeline_stage_seconds(void* hh, double* out9, int reset) {
     out9[6 + s] = h->runner->handoff[s];
     if (reset) h->runner->busy[s] = h->runner->idle[s] = h->runner->handoff[s] = 0.0;
   }
+  if (reset) h->runner->t_reset = now();
   return 0;
 }
 

@@ -75,6 +75,9 @@ class BasicLaserMapping {
   // cube-index arithmetic as the insertion step (upstream BasicLaserMapping.cpp:540-553); introspection for tests.
   void seedMap(pcl::PointCloud<pcl::PointXYZI> const& cornerPoints, pcl::PointCloud<pcl::PointXYZI> const& surfPoints);
   size_t lastIterationCount() const { return _lastIterations; }
+  // sizes of the down-sized feature stacks of the last process() (the queries of its optimisation loop)
+  size_t cornerStackSize() const { return (size_t)_mapSizes[2]; }
+  size_t surfStackSize() const { return (size_t)_mapSizes[3]; }
   // host wall seconds of the last process(): begin_sweep, LM loop, end_sweep, surround map
   const double* lastPhaseSeconds() const { return _phase; }
   auto const& transformTobeMapped() const { return _transformTobeMapped; }

@@ -811,6 +811,34 @@ int loam_b200_map_set_queries(loam_b200_ctx* c, const float* corner, int n_corne
   return LOAM_B200_OK;
 }
 
+// map_iterate_v2_kernel: candidate capacity per query (points staged in shared memory) and the persistent grid.
+// Sparse maps (the 0.2 / 0.4 m voxel lattice of a LOAM map holds ~63 candidates per query at 1 M points) take the small
+// capacity = 4 CTAs per SM; maps beyond a few million points (~200 candidates per query) the large one.
+static int map_v2_cap_index(const loam_b200_ctx* c) {
+  const long long pts = (long long)c->cloud_n[LOAM_B200_C_MAP_CORNER_POOL] + c->cloud_n[LOAM_B200_C_MAP_SURF_POOL] +
+                        (c->map_use_store ? 0 : (long long)c->grid[0].m + c->grid[1].m);
+  return pts > 4000000 ? 1 : 0;
+}
+static const int MAP_V2_CAP[2] = {96, 224};
+extern "C++" {
+template <typename K>
+static int map_v2_grid_of(loam_b200_ctx* c, K kernel, int& cached, int cap) {
+  if (cached > 0) return cached;
+  const size_t smem = (size_t)MAP_Q_PER_BLOCK * cap * sizeof(float4);
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MAPV2_THREADS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  cached = per_sm * c->sm_count;
+  return cached;
+}
+}  // extern "C++"
+
 static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b200_normal_eq* out, float* coeff,
                             int8_t* selected, unsigned long long* walk_totals_host = nullptr) {
   CHECK_CTX(c);
@@ -861,8 +889,28 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     // single GPU: the folding CTA posts the sums straight into mapped host memory (no memcpy + synchronise); with a
     // shard / communicator the all-reduce has to run first, so the result is fetched the classic way
     if (use_mailbox) mb = next_mailbox(c);
+    static const bool v1_only = getenv("LOAM_B200_MAP_V1") != nullptr;
+    const int ci = map_v2_cap_index(c), cap = MAP_V2_CAP[ci];
+    int grid_v2 = 0;
+    if (!v1_only && !c->map_v2_off)
+      grid_v2 = c->map_use_store ? map_v2_grid_of(c, map_iterate_v2_kernel<MapCellLookup, false>, c->map_v2_grid[1][0][ci], cap)
+                                 : map_v2_grid_of(c, map_iterate_v2_kernel<GridCellLookup, false>, c->map_v2_grid[0][0][ci], cap);
     prof_begin(c, LOAM_B200_K_MAP_ITER);
-    if (c->map_use_store)
+    if (grid_v2 > 0) {
+      const size_t smem = (size_t)MAP_Q_PER_BLOCK * cap * sizeof(float4);
+      // balanced persistent grid: every CTA gets the same number of 32-query blocks (+-1)
+      const int per_cta = (nb + grid_v2 - 1) / grid_v2;
+      const int grid = (nb + per_cta - 1) / per_cta;
+      if (c->map_use_store)
+        map_iterate_v2_kernel<MapCellLookup, false><<<grid, MAPV2_THREADS, smem, c->stream>>>(
+            store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, nb, a, c->partials.p, c->result.p,
+            c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, mb, sh, pr, cap);
+      else
+        map_iterate_v2_kernel<GridCellLookup, false><<<grid, MAPV2_THREADS, smem, c->stream>>>(
+            GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls, cb,
+            nb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr,
+            mb, sh, pr, cap);
+    } else if (c->map_use_store)
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
           store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
           c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, nullptr, mb, sh, pr);
