@@ -270,9 +270,15 @@ int loam_b200_reg_labels(loam_b200_ctx* ctx, int8_t* out, int n);
  * BasicLaserOdometry.cpp:203-204,662-663), built asynchronously on side streams;
  * loam_b200_odom_iterate (above) then works on them. */
 int loam_b200_odom_prepare(loam_b200_ctx* ctx);
+/* The registration -> odometry hand-off in one launch: the five clouds of `src_ctx` (src5 = its sharp, less sharp, flat,
+ * less flat, full-resolution slots) go to the ODOM_SHARP .. ODOM_FULL slots of `ctx` like loam_b200_cloud_copy_many, and
+ * this sweep's query array is filled at the same time (the next loam_b200_odom_prepare then copies nothing). */
+int loam_b200_odom_adopt(loam_b200_ctx* ctx, loam_b200_ctx* src_ctx, const int* src5);
 int loam_b200_odom_rebuild_last(loam_b200_ctx* ctx);
 /* transformToEnd / pointAssociateToMap in place on a device cloud */
 int loam_b200_cloud_transform_to_end(loam_b200_ctx* ctx, int slot, const loam_b200_odom_pose* pose);
+/* the same on two clouds with one launch (slot_b < 0: only slot_a) */
+int loam_b200_cloud_transform_to_end2(loam_b200_ctx* ctx, int slot_a, int slot_b, const loam_b200_odom_pose* pose);
 int loam_b200_cloud_transform_to_map(loam_b200_ctx* ctx, int slot, const loam_b200_pose* pose);
 
 /* Mapping stage.  The surrounding map is one point pool per kind (MAP_CORNER_POOL / MAP_SURF_POOL), kept sorted by 1 m

@@ -86,6 +86,9 @@ int loam_b200_map_last_phase_seconds(void* h, double* out4);
  * queries of the last process()), CUDA-event time over `reps` launches at the current pose.  out5 = average launch
  * microseconds, queries, table probes / query, candidate points / query, selected correspondences */
 int loam_b200_map_kernel_profile(void* h, int reps, double* out5);
+/* ... on n caller-supplied surface queries (packed float4, map frame, identity pose) against this object's persistent map:
+ * the k-NN bandwidth stress (queries spread over a map far larger than L2).  Replaces the queries of the last process(). */
+int loam_b200_map_kernel_profile_queries(void* h, const float* queries, int n, int reps, double* out5);
 /* test hook: keep a copy of laserCloudCornerFromMap / laserCloudSurfFromMap (cloud ids 2, 3) at every process() */
 int loam_b200_map_retain_from_map(void* h, int on);
 /* multi-GPU, one process per GPU: rank 0 calls loam_b200_host_nccl_unique_id and distributes the 128 bytes; every rank

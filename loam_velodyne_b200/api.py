@@ -129,6 +129,8 @@ def lib():
         "loam_b200_reg_indices": (C.c_int, [vp, C.c_int, _I, C.c_int, _I]),
         "loam_b200_reg_labels": (C.c_int, [vp, _B, C.c_int]),
         "loam_b200_odom_prepare": (C.c_int, [vp]),
+        "loam_b200_odom_adopt": (C.c_int, [vp, vp, _I]),
+        "loam_b200_cloud_transform_to_end2": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(OdomPose)]),
         "loam_b200_odom_rebuild_last": (C.c_int, [vp]),
         "loam_b200_cloud_transform_to_end": (C.c_int, [vp, C.c_int, C.POINTER(OdomPose)]),
         "loam_b200_cloud_transform_to_map": (C.c_int, [vp, C.c_int, C.POINTER(Pose)]),
@@ -186,6 +188,7 @@ def lib():
         "loam_b200_host_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
         "loam_b200_map_kernel_profile": (C.c_int, [vp, C.c_int, _D]),
+        "loam_b200_map_kernel_profile_queries": (C.c_int, [vp, _F, C.c_int, C.c_int, _D]),
         "loam_b200_map_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_cube_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
         "loam_b200_map_enable_cube_sharding_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
@@ -618,6 +621,15 @@ class LaserMapping(_Handle):
         """The scan-to-map iteration kernel as this object launches it, timed with CUDA events (see the header)."""
         out = np.zeros(5, np.float64)
         self._ck(self.L.loam_b200_map_kernel_profile(self.h, reps, out.ctypes.data_as(_D)), "map_kernel_profile")
+        return {"avg_us": float(out[0]), "queries": int(out[1]), "probes_per_query": float(out[2]),
+                "candidates_per_query": float(out[3]), "n_selected": int(out[4])}
+
+    def kernel_profile_queries(self, queries, reps=10):
+        """... on caller-supplied surface queries in the map frame (k-NN bandwidth stress)."""
+        q = _pts(queries)
+        out = np.zeros(5, np.float64)
+        self._ck(self.L.loam_b200_map_kernel_profile_queries(self.h, _fp(q), q.shape[0], reps, out.ctypes.data_as(_D)),
+                 "map_kernel_profile_queries")
         return {"avg_us": float(out[0]), "queries": int(out[1]), "probes_per_query": float(out[2]),
                 "candidates_per_query": float(out[3]), "n_selected": int(out[4])}
 

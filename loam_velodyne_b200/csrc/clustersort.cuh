@@ -302,10 +302,32 @@ cluster_sort_pairs_kernel(const unsigned* keys_in, const int* vals_in, int n, co
 }
 
 // LBVH build of lbvh.cuh in one launch: bbox -> Morton keys -> cluster sort -> gather -> leaves -> Karras -> refit
+// One launch builds up to TWO trees (one cluster each: the last corner / last surface cloud of the odometry stage are
+// rebuilt together every sweep); a1.n == 0 with a grid of one cluster builds one.
+struct BvhBuildArgs {
+  const float4* pts;
+  int n, n_leaf;
+  float4* sorted;
+  unsigned* leaf_key;
+  BvhNode* nodes;
+  int* parent;
+  float4* box_lo;
+  float4* box_hi;
+  int* flags;
+};
 __global__ void __cluster_dims__(CS_CL, 1, 1) __launch_bounds__(CS_THREADS)
-bvh_build_cluster_kernel(const float4* __restrict__ pts, int n, int n_leaf, float4* __restrict__ sorted,
-                         unsigned* __restrict__ leaf_key, BvhNode* __restrict__ nodes, int* __restrict__ parent,
-                         float4* __restrict__ box_lo, float4* __restrict__ box_hi, int* __restrict__ flags) {
+bvh_build_cluster_kernel(BvhBuildArgs a0, BvhBuildArgs a1) {
+  const BvhBuildArgs& A = blockIdx.x < CS_CL ? a0 : a1;
+  const float4* __restrict__ pts = A.pts;
+  const int n = A.n, n_leaf = A.n_leaf;
+  if (n <= 0) return;  // the whole cluster leaves together
+  float4* __restrict__ sorted = A.sorted;
+  unsigned* __restrict__ leaf_key = A.leaf_key;
+  BvhNode* __restrict__ nodes = A.nodes;
+  int* __restrict__ parent = A.parent;
+  float4* __restrict__ box_lo = A.box_lo;
+  float4* __restrict__ box_hi = A.box_hi;
+  int* __restrict__ flags = A.flags;
   extern __shared__ __align__(16) unsigned char cs_raw[];
   ClusterSortSmem& sm = *reinterpret_cast<ClusterSortSmem*>(cs_raw);
   cg::cluster_group cluster = cg::this_cluster();

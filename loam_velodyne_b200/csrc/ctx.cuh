@@ -209,7 +209,9 @@ struct loam_b200_ctx {
   loamb::DevBuf<float> knn_d2;
 
   // mapping
-  loamb::DevBuf<float4> map_q;  // corner queries then surf queries
+  loamb::DevBuf<float4> map_q;  // corner queries then surf queries (kernel-level API: loam_b200_map_set_queries)
+  const float4* map_q_corner = nullptr;  // where the kernels read the queries: map_q, or the two down-sized stack clouds
+  const float4* map_q_surf = nullptr;    // of the stage API (no copy)
   int map_nc = 0, map_ns = 0;
   loamb::DevBuf<float> partials;   // per-block partial normal equations
   loamb::DevBuf<float> result;     // 36 floats
@@ -237,6 +239,8 @@ struct loam_b200_ctx {
   loamb::DevBuf<int> od_ind;   // (n_sharp + n_flat) x 3 persisted correspondence indices
   bool od_last_set = false;
   bool od_rebuild_pending = false;
+  int od_rebuild_lanes = 2;    // side lanes the pending rebuild runs on
+  bool od_prepared = false;    // od_q already holds this sweep's queries (loam_b200_odom_adopt)
   loamb::DevBuf<int> od_ring_off[2];  // ring offset tables of the last corner / surface clouds (odometry_lm.cuh)
 
   // device-resident clouds of the stage API

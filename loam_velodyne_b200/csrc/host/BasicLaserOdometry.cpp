@@ -71,8 +71,9 @@ void BasicLaserOdometry::adopt(BasicScanRegistration& reg) {
     dstSlots[i] = _c[to[i]].slot();
     srcSlots[i] = src.slot();
   }
-  _gpu->check(loam_b200_cloud_copy_many(_gpu->get(), dstSlots, reg.deviceContext()->get(), srcSlots, 5),
-              "loam_b200_cloud_copy_many");
+  (void)dstSlots;
+  // one launch: the five clouds and this sweep's query array (sharp + flat points)
+  _gpu->check(loam_b200_odom_adopt(_gpu->get(), reg.deviceContext()->get(), srcSlots), "loam_b200_odom_adopt");
   for (int i = 0; i < 5; i++) _c[to[i]].deviceWritten((int)reg.deviceCloud(from[i]).size());
   updateIMU(reg.imuTransform());
 }
@@ -238,10 +239,12 @@ void BasicLaserOdometry::process() {
   // transformToEnd(less sharp / less flat) in HBM, then they become the "last" clouds (:651-655)
   loam_b200_odom_pose endPose;
   fillOdomPoseOf(_transform, _scanPeriod, 0, endPose);
+  _c[C_LESS_SHARP].ensureDevice();
+  _c[C_LESS_FLAT].ensureDevice();
+  _gpu->check(loam_b200_cloud_transform_to_end2(_gpu->get(), _c[C_LESS_SHARP].slot(), _c[C_LESS_FLAT].slot(), &endPose),
+              "loam_b200_cloud_transform_to_end2");
   for (int which : {C_LESS_SHARP, C_LESS_FLAT}) {
     if (_c[which].size() == 0) continue;
-    _c[which].ensureDevice();
-    _gpu->check(loam_b200_cloud_transform_to_end(_gpu->get(), _c[which].slot(), &endPose), "loam_b200_cloud_transform_to_end");
     _c[which].deviceWritten((int)_c[which].size());
     if (hasIMU()) applyImuToEnd(_c[which].hostMutable());
   }

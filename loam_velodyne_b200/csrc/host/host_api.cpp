@@ -496,6 +496,37 @@ int loam_b200_map_kernel_profile(void* h, int reps, double* out5) {
   });
 }
 
+// The same kernel on caller-supplied queries (map frame, identity pose) against this object's persistent map: the
+// bandwidth stress of BASELINE config 5 -- queries spread over a map far larger than L2.  out5 as above.
+int loam_b200_map_kernel_profile_queries(void* h, const float* queries, int n, int reps, double* out5) {
+  return guarded([&] {
+    auto& m = ((MapH*)h)->m;
+    loam_b200_ctx* c = m.deviceContext()->get();
+    auto ck = [&](int rc, const char* what) { m.deviceContext()->check(rc, what); };
+    ck(loam_b200_map_set_queries(c, nullptr, 0, queries, n), "loam_b200_map_set_queries");
+    loam::Twist identity;
+    loam_b200_pose pose;
+    b200::fillPose(identity, pose);
+    loam_b200_normal_eq ne;
+    unsigned long long probes = 0, cands = 0;
+    ck(loam_b200_map_iterate_stats(c, &pose, &ne, &probes, &cands), "loam_b200_map_iterate_stats");
+    for (int i = 0; i < 3; i++) ck(loam_b200_map_iterate(c, &pose, &ne), "loam_b200_map_iterate");
+    ck(loam_b200_profile_reset(c), "loam_b200_profile_reset");
+    ck(loam_b200_profile_enable(c, 1), "loam_b200_profile_enable");
+    for (int i = 0; i < reps; i++) ck(loam_b200_map_iterate(c, &pose, &ne), "loam_b200_map_iterate");
+    double ms = 0.0;
+    long long launches = 0;
+    ck(loam_b200_profile_get(c, LOAM_B200_K_MAP_ITER, &ms, &launches), "loam_b200_profile_get");
+    ck(loam_b200_profile_enable(c, 0), "loam_b200_profile_enable");
+    out5[0] = launches > 0 ? 1e3 * ms / (double)launches : 0.0;
+    out5[1] = (double)n;
+    out5[2] = n > 0 ? (double)probes / n : 0.0;
+    out5[3] = n > 0 ? (double)cands / n : 0.0;
+    out5[4] = (double)ne.n_selected;
+    return 0;
+  });
+}
+
 int loam_b200_map_peer_export(void* h, unsigned char* out64) {
   return guarded([&] { ((MapH*)h)->m.exportPeerHandle(out64); return 0; });
 }

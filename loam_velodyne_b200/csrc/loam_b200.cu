@@ -173,31 +173,37 @@ int grid_build_device(loam_b200_ctx* c, Grid& g, const float4* d_pts, int m, con
   return LOAM_B200_OK;
 }
 
-// ring offset table of an odometry last-sweep cloud (odometry_lm.cuh: ring_offsets_kernel)
+// ring offset tables of the odometry's last-sweep clouds (odometry_lm.cuh: ring_offsets_kernel); both live in one buffer
+int* ring_off_ptr(loam_b200_ctx* c, int kind) { return c->od_ring_off[0].p ? c->od_ring_off[0].p + kind * RING_OFF_WORDS : nullptr; }
 int odom_ring_offsets(loam_b200_ctx* c, int kind, const float4* d_pts, int m) {
-  LB_CUDA(c, c->od_ring_off[kind].reserve(RING_OFF_WORDS));
-  LB_CUDA(c, cudaMemsetAsync(c->od_ring_off[kind].p, 0, RING_OFF_WORDS * sizeof(int), c->stream));
+  LB_CUDA(c, c->od_ring_off[0].reserve(2 * RING_OFF_WORDS));
+  LB_CUDA(c, cudaMemsetAsync(ring_off_ptr(c, kind), 0, RING_OFF_WORDS * sizeof(int), c->stream));
   if (m > 0) {
-    ring_offsets_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, m, c->od_ring_off[kind].p);
+    ring_offsets_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(d_pts, m, ring_off_ptr(c, kind));
+    LB_LAUNCH_CHECK(c);
+  }
+  return LOAM_B200_OK;
+}
+// ... of both clouds: one memset + one launch
+int odom_ring_offsets_pair(loam_b200_ctx* c, const float4* p0, int m0, const float4* p1, int m1) {
+  LB_CUDA(c, c->od_ring_off[0].reserve(2 * RING_OFF_WORDS));
+  LB_CUDA(c, cudaMemsetAsync(c->od_ring_off[0].p, 0, 2 * RING_OFF_WORDS * sizeof(int), c->stream));
+  const int m = std::max(m0, m1);
+  if (m > 0) {
+    ring_offsets_kernel<<<dim3(blocks_for(m, 256), 2), 256, 0, c->stream>>>(p0, m0, ring_off_ptr(c, 0), p1, m1, ring_off_ptr(c, 1));
     LB_LAUNCH_CHECK(c);
   }
   return LOAM_B200_OK;
 }
 
-// build the BVH of tree t from t.pts (device, m points)
-int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
+// buffers of a tree over m points (no scratch of the multi-launch build)
+int tree_reserve(loam_b200_ctx* c, Tree& t, int m) {
   t.m = m;
   t.n_leaf = 0;
   t.root = 0;
   if (m <= 0) return LOAM_B200_OK;
   const int n_leaf = (m + LEAF_SIZE - 1) / LEAF_SIZE;
   t.n_leaf = n_leaf;
-  SortScratch& s = c->sort;
-  LB_CUDA(c, s.keys_a.reserve(m));
-  LB_CUDA(c, s.keys_b.reserve(m));
-  LB_CUDA(c, s.vals_a.reserve(m));
-  LB_CUDA(c, s.vals_b.reserve(m));
-  LB_CUDA(c, c->bbox.reserve(8));
   LB_CUDA(c, t.sorted.reserve(m));
   LB_CUDA(c, t.nodes.reserve(n_leaf > 1 ? n_leaf - 1 : 1));
   LB_CUDA(c, t.leaf_key.reserve(n_leaf));
@@ -205,13 +211,46 @@ int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
   LB_CUDA(c, t.flags.reserve(n_leaf));
   LB_CUDA(c, t.box_lo.reserve(2 * (size_t)n_leaf));
   LB_CUDA(c, t.box_hi.reserve(2 * (size_t)n_leaf));
+  return LOAM_B200_OK;
+}
+BvhBuildArgs bvh_args_of(const Tree& t) {
+  return BvhBuildArgs{t.points(), t.m, t.n_leaf, t.sorted.p, t.leaf_key.p, t.nodes.p, t.parent.p, t.box_lo.p, t.box_hi.p, t.flags.p};
+}
+
+// both trees of the odometry stage in ONE launch (two clusters); false when a cloud needs the multi-launch path
+int tree_build_pair_cluster(loam_b200_ctx* c, Tree& t0, int m0, Tree& t1, int m1, bool* done) {
+  *done = false;
+  if (!cluster_path_ok(c, m0) || !cluster_path_ok(c, m1)) return LOAM_B200_OK;
+  int rc = tree_reserve(c, t0, m0);
+  if (rc == LOAM_B200_OK) rc = tree_reserve(c, t1, m1);
+  if (rc) return rc;
+  bvh_build_cluster_kernel<<<2 * CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(bvh_args_of(t0), bvh_args_of(t1));
+  LB_LAUNCH_CHECK(c);
+  t0.root = t0.n_leaf == 1 ? ~0 : 0;
+  t1.root = t1.n_leaf == 1 ? ~0 : 0;
+  *done = true;
+  return LOAM_B200_OK;
+}
+
+// build the BVH of tree t from t.pts (device, m points)
+int tree_build_device(loam_b200_ctx* c, Tree& t, int m) {
+  int rc0 = tree_reserve(c, t, m);
+  if (rc0) return rc0;
+  if (m <= 0) return LOAM_B200_OK;
+  const int n_leaf = t.n_leaf;
   if (cluster_path_ok(c, m)) {
-    bvh_build_cluster_kernel<<<CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(
-        t.points(), m, n_leaf, t.sorted.p, t.leaf_key.p, t.nodes.p, t.parent.p, t.box_lo.p, t.box_hi.p, t.flags.p);
+    BvhBuildArgs none{};
+    bvh_build_cluster_kernel<<<CS_CL, CS_THREADS, sizeof(ClusterSortSmem), c->stream>>>(bvh_args_of(t), none);
     LB_LAUNCH_CHECK(c);
     t.root = n_leaf == 1 ? ~0 : 0;
     return LOAM_B200_OK;
   }
+  SortScratch& s = c->sort;
+  LB_CUDA(c, s.keys_a.reserve(m));
+  LB_CUDA(c, s.keys_b.reserve(m));
+  LB_CUDA(c, s.vals_a.reserve(m));
+  LB_CUDA(c, s.vals_b.reserve(m));
+  LB_CUDA(c, c->bbox.reserve(8));
   unsigned* bb = reinterpret_cast<unsigned*>(c->bbox.p);
   bbox_init_kernel<<<1, 32, 0, c->stream>>>(bb);
   LB_LAUNCH_CHECK(c);
@@ -253,11 +292,12 @@ void fill_odom_args(const loam_b200_odom_pose* p, OdomIterArgs& a) {
   odom_args_from(p->rot, p->sin_, p->cos_, p->pos, p->inv_scan_period, p->iter, a);
 }
 
-// BVHs of the last clouds are rebuilt asynchronously on lanes 1 / 2 (loam_b200_odom_rebuild_last)
+// BVHs of the last clouds are rebuilt asynchronously on lane 1 (+ lane 2 on the multi-launch path)
 cudaError_t odom_join_rebuild(loam_b200_ctx* c) {
   if (!c->od_rebuild_pending) return cudaSuccess;
+  const int lanes = c->od_rebuild_lanes;
   c->od_rebuild_pending = false;
-  return lanes_join(c, 2);
+  return lanes_join(c, lanes);
 }
 
 static void unpack_normal_eq(const float* r, loam_b200_normal_eq* out) {
@@ -557,7 +597,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   c->map_loop.destroy();
   if (c->peer_inbox) cudaFree(c->peer_inbox);
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
-  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->od_ring_off[1].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
+  c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
   c->tmp_pts2.release(); c->vox_key.release(); c->vox_val.release(); c->vox_scalars.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -808,6 +848,8 @@ int loam_b200_map_set_queries(loam_b200_ctx* c, const float* corner, int n_corne
   LB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->map_nc = n_corner;
   c->map_ns = n_surf;
+  c->map_q_corner = c->map_q.p;
+  c->map_q_surf = c->map_q.p + n_corner;
   return LOAM_B200_OK;
 }
 
@@ -876,11 +918,11 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     LB_CUDA(c, cudaMemsetAsync(c->walk_totals.p, 0, 2 * sizeof(unsigned long long), c->stream));
     if (c->map_use_store)
       map_iterate_kernel<true><<<nb, MAP_THREADS, 0, c->stream>>>(
-          store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
+          store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
           c->ticket.p, nullptr, nullptr, c->walk_totals.p);
     else
       map_iterate_kernel<true><<<nb, MAP_THREADS, 0, c->stream>>>(
-          GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
+          GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls,
           cb, a, c->partials.p, c->result.p, c->ticket.p, nullptr, nullptr, c->walk_totals.p);
     LB_LAUNCH_CHECK(c);
     LB_CUDA(c, cudaMemcpyAsync(walk_totals_host, c->walk_totals.p, 2 * sizeof(unsigned long long),
@@ -889,10 +931,13 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
     // single GPU: the folding CTA posts the sums straight into mapped host memory (no memcpy + synchronise); with a
     // shard / communicator the all-reduce has to run first, so the result is fetched the classic way
     if (use_mailbox) mb = next_mailbox(c);
-    static const bool v1_only = getenv("LOAM_B200_MAP_V1") != nullptr;
+    // v2 (persistent, warp-specialised, cp.async.bulk staging) is kept as a measured alternative: on B200 it runs 42.9 us
+    // against 29.7 us for the phase-split kernel at config 3 (profiles/r2_map_iterate_v2.md) -- 27 bulk copies of ~100 B per
+    // query cost more than the loads they replace.  LOAM_B200_MAP_V2=1 selects it.
+    static const bool use_v2 = getenv("LOAM_B200_MAP_V2") != nullptr;
     const int ci = map_v2_cap_index(c), cap = MAP_V2_CAP[ci];
     int grid_v2 = 0;
-    if (!v1_only && !c->map_v2_off)
+    if (use_v2 && !c->map_v2_off)
       grid_v2 = c->map_use_store ? map_v2_grid_of(c, map_iterate_v2_kernel<MapCellLookup, false>, c->map_v2_grid[1][0][ci], cap)
                                  : map_v2_grid_of(c, map_iterate_v2_kernel<GridCellLookup, false>, c->map_v2_grid[0][0][ci], cap);
     prof_begin(c, LOAM_B200_K_MAP_ITER);
@@ -903,20 +948,20 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
       const int grid = (nb + per_cta - 1) / per_cta;
       if (c->map_use_store)
         map_iterate_v2_kernel<MapCellLookup, false><<<grid, MAPV2_THREADS, smem, c->stream>>>(
-            store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, nb, a, c->partials.p, c->result.p,
+            store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls, cb, nb, a, c->partials.p, c->result.p,
             c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, mb, sh, pr, cap);
       else
         map_iterate_v2_kernel<GridCellLookup, false><<<grid, MAPV2_THREADS, smem, c->stream>>>(
-            GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls, cb,
+            GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls, cb,
             nb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr,
             mb, sh, pr, cap);
     } else if (c->map_use_store)
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
-          store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q.p, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
+          store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
           c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, nullptr, mb, sh, pr);
     else
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
-          GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q.p, nc, c0, lc, s0, ls,
+          GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls,
           cb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr,
           nullptr, nullptr, mb, sh, pr);
     LB_LAUNCH_CHECK(c);
@@ -1009,7 +1054,7 @@ static int odom_iterate_impl(loam_b200_ctx* c, const loam_b200_odom_pose* pose, 
     const int warps = nsh + nfl;
     odom_search_kernel<false><<<blocks_for((long long)warps * 32, LM_THREADS), LM_THREADS, 0, c->stream>>>(
         view_of(tc), view_of(ts), tc.points(), ts.points(), c->od_q.p, nsh, nfl, a, c->od_ind.p, nullptr,
-        c->od_ring_off[0].p, c->od_ring_off[1].p);
+        ring_off_ptr(c, 0), ring_off_ptr(c, 1));
     LB_LAUNCH_CHECK(c);
   }
   ResultMailbox mb{nullptr, 0};
@@ -1145,7 +1190,7 @@ int loam_b200_odom_solve(loam_b200_ctx* c, const float rot[3], const float pos[3
   OdomLoopIo io;
   io.corner_tree = view_of(tc); io.surf_tree = view_of(ts);
   io.last_corner = tc.points(); io.last_surf = ts.points(); io.queries = c->od_q.p; io.ind = c->od_ind.p;
-  io.ring_off_corner = c->od_ring_off[0].p; io.ring_off_surf = c->od_ring_off[1].p;
+  io.ring_off_corner = ring_off_ptr(c, 0); io.ring_off_surf = ring_off_ptr(c, 1);
   io.n_sharp = nsh; io.n_flat = nfl; io.sharp_blocks = cb; io.n_blocks = nb;
   odom_lm_init_kernel<<<1, 32, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], inv_scan_period,
                                                delta_t_abort, delta_r_abort, max_iterations, tc.m, ts.m, io, seq);
@@ -1246,7 +1291,7 @@ int loam_b200_map_solve(loam_b200_ctx* c, const float rot[3], const float pos[3]
     memcpy(io.lookup[0], &l0, sizeof l0);
     memcpy(io.lookup[1], &l1, sizeof l1);
   }
-  io.queries = c->map_q.p; io.n_corner_total = nc; io.c0 = c0; io.n_corner = lc; io.s0 = s0; io.n_surf = ls;
+  io.queries = c->map_q_corner; io.queries_surf = c->map_q_surf; io.n_corner_total = nc; io.c0 = c0; io.n_corner = lc; io.s0 = s0; io.n_surf = ls;
   io.corner_blocks = cb; io.n_blocks = nb;
   map_lm_init_kernel<<<1, 128, 0, c->stream>>>(st, rot[0], rot[1], rot[2], pos[0], pos[1], pos[2], delta_t_abort,
                                                delta_r_abort, max_iterations, io, seq);
@@ -1257,11 +1302,11 @@ int loam_b200_map_solve(loam_b200_ctx* c, const float rot[3], const float pos[3]
   auto launch_iterate = [&](int grid) {
     if (c->map_use_store)
       map_iterate_kernel<false, MapCellLookup, true><<<grid, MAP_THREADS, 0, c->stream>>>(
-          MapCellLookup{}, MapCellLookup{}, nullptr, 0, 0, 0, 0, 0, 0, unused, c->partials.p, c->result.p, c->ticket.p, nullptr,
+          MapCellLookup{}, MapCellLookup{}, nullptr, nullptr, 0, 0, 0, 0, 0, 0, unused, c->partials.p, c->result.p, c->ticket.p, nullptr,
           nullptr, nullptr, st);
     else
       map_iterate_kernel<false, GridCellLookup, true><<<grid, MAP_THREADS, 0, c->stream>>>(
-          GridCellLookup{}, GridCellLookup{}, nullptr, 0, 0, 0, 0, 0, 0, unused, c->partials.p, c->result.p, c->ticket.p, nullptr,
+          GridCellLookup{}, GridCellLookup{}, nullptr, nullptr, 0, 0, 0, 0, 0, 0, unused, c->partials.p, c->result.p, c->ticket.p, nullptr,
           nullptr, nullptr, st);
   };
   if (use_graph) {

@@ -58,7 +58,8 @@ LOAMB_HD inline void map_args_from(const float sin_[3], const float cos_[3], con
 constexpr int MAP_LOOKUP_BYTES = 128;
 struct MapLoopIo {
   alignas(16) unsigned char lookup[2][MAP_LOOKUP_BYTES];
-  const float4* queries;
+  const float4* queries;       // corner queries
+  const float4* queries_surf;  // surface queries (the two down-sized stacks are separate clouds)
   int n_corner_total, c0, n_corner, s0, n_surf, corner_blocks, n_blocks;
   int min_corner_map, min_surf_map;  // sizes of the from-map clouds (the <= 10 / <= 100 gate is evaluated by the host)
 };
@@ -430,8 +431,8 @@ static_assert(MAP_Q_PER_BLOCK == 32, "the fit phase maps one query to one lane o
 // registers the 8-lane kernel ran 1.06 waves: half of the kernel's time was a second wave of 63 CTAs).
 template <bool STATS, typename LOOKUP, bool DEVLOOP = false>
 __global__ void __launch_bounds__(MAP_THREADS, 4)
-map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, int n_corner_total,
-                   int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a_param,
+map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, const float4* queries_surf,
+                   int n_corner_total, int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a_param,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                    float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel,
                    unsigned long long* __restrict__ walk_totals, const MapLmState* __restrict__ lm = nullptr,
@@ -450,8 +451,8 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
     if (blockIdx.x >= n_blocks) return;
     if (threadIdx.x < (int)(sizeof(MapIterArgs) / 4))
       reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
-    queries = io.queries; n_corner_total = io.n_corner_total; c0 = io.c0; n_corner = io.n_corner; s0 = io.s0;
-    n_surf = io.n_surf; corner_blocks = io.corner_blocks;
+    queries = io.queries; queries_surf = io.queries_surf; n_corner_total = io.n_corner_total; c0 = io.c0;
+    n_corner = io.n_corner; s0 = io.s0; n_surf = io.n_surf; corner_blocks = io.corner_blocks;
     static_assert(sizeof(LOOKUP) <= MAP_LOOKUP_BYTES, "lookup does not fit its slot in MapLoopIo");
     const int kind = (int)blockIdx.x < corner_blocks ? 0 : 1;
     if (threadIdx.x < (int)((sizeof(LOOKUP) + 3) / 4))
@@ -470,7 +471,8 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
   const int block_first = (is_corner ? blockIdx.x : blockIdx.x - corner_blocks) * MAP_Q_PER_BLOCK;
   const int n_kind = is_corner ? n_corner : n_surf;
   // this rank's slice: corners [c0, c0 + n_corner), surfaces [s0, s0 + n_surf) (the whole range on one GPU)
-  const int q_base = is_corner ? c0 : n_corner_total + s0;
+  const int q_base = is_corner ? c0 : n_corner_total + s0;   // index in the concatenated numbering (debug outputs)
+  const float4* __restrict__ qsrc = is_corner ? queries + c0 : queries_surf + s0;
   // cell -> run of map points (gridnn.cuh / mapstore.cuh)
   LOOKUP grid = DEVLOOP ? *reinterpret_cast<const LOOKUP*>(s_lookup) : (is_corner ? corner_grid : surf_grid);
 
@@ -478,7 +480,7 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
     const int g = threadIdx.x / MAP_GROUP;
     const int local = block_first + g;
     if (local < n_kind) {  // uniform within a group of 8 lanes
-      const float4 po = queries[q_base + local];
+      const float4 po = qsrc[local];
       float sx, sy, sz;
       associate_to_map(a, po, sx, sy, sz);
       Cand5 best;
@@ -511,7 +513,7 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
     bool sel = false;
     if (local < n_kind) {
       const int qi = q_base + local;
-      const float4 po = queries[qi];
+      const float4 po = qsrc[local];
       float sx, sy, sz;
       associate_to_map(a, po, sx, sy, sz);
       Top5 nn;
@@ -623,8 +625,9 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 
 template <typename LOOKUP, bool DEVLOOP>
 __global__ void __launch_bounds__(MAPV2_THREADS, 3)
-map_iterate_v2_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, int n_corner_total, int c0, int n_corner,
-                      int s0, int n_surf, int corner_blocks, int n_blocks_arg, MapIterArgs a_param,
+map_iterate_v2_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, const float4* queries_surf,
+                      int n_corner_total, int c0, int n_corner, int s0, int n_surf, int corner_blocks, int n_blocks_arg,
+                      MapIterArgs a_param,
                       float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
                       float4* __restrict__ dbg_coeff, int8_t* __restrict__ dbg_sel, const MapLmState* __restrict__ lm,
                       ResultMailbox mb, ShardSpec sh, PeerReduce pr, int cand_cap) {
@@ -644,8 +647,8 @@ map_iterate_v2_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* querie
     n_blocks = io.n_blocks;
     if (threadIdx.x < (int)(sizeof(MapIterArgs) / 4))
       reinterpret_cast<float*>(&s_args)[threadIdx.x] = reinterpret_cast<const float*>(&lm->args)[threadIdx.x];
-    queries = io.queries; n_corner_total = io.n_corner_total; c0 = io.c0; n_corner = io.n_corner; s0 = io.s0;
-    n_surf = io.n_surf; corner_blocks = io.corner_blocks;
+    queries = io.queries; queries_surf = io.queries_surf; n_corner_total = io.n_corner_total; c0 = io.c0;
+    n_corner = io.n_corner; s0 = io.s0; n_surf = io.n_surf; corner_blocks = io.corner_blocks;
     static_assert(sizeof(LOOKUP) <= MAP_LOOKUP_BYTES, "lookup does not fit its slot in MapLoopIo");
     for (int w = threadIdx.x; w < 2 * (int)((sizeof(LOOKUP) + 3) / 4); w += blockDim.x) {
       const int kind = w / (int)((sizeof(LOOKUP) + 3) / 4), k = w % (int)((sizeof(LOOKUP) + 3) / 4);
@@ -671,13 +674,14 @@ map_iterate_v2_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* querie
     const int block_first = (is_corner ? b : b - corner_blocks) * MAP_Q_PER_BLOCK;
     const int n_kind = is_corner ? n_corner : n_surf;
     const int q_base = is_corner ? c0 : n_corner_total + s0;
+    const float4* __restrict__ qsrc = is_corner ? queries + c0 : queries_surf + s0;
     if (!fit_warp) {  // ---- search warps: 8 lanes per query
       if (it >= 2) named_bar_sync(BAR_EMPTY + half, MAPV2_THREADS);  // warp 8 is done with this half
       LOOKUP grid = DEVLOOP ? *reinterpret_cast<const LOOKUP*>(s_lookup[is_corner ? 0 : 1]) : (is_corner ? corner_grid : surf_grid);
       const int g = threadIdx.x / MAP_GROUP;
       const int local = block_first + g;
       if (local < n_kind) {  // uniform within a group of 8 lanes
-        const float4 po = queries[q_base + local];
+        const float4 po = qsrc[local];
         float sx, sy, sz;
         associate_to_map(a, po, sx, sy, sz);
         Cand5 best;
@@ -703,7 +707,7 @@ map_iterate_v2_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* querie
       bool sel = false;
       if (local < n_kind) {
         const int qi = q_base + local;
-        const float4 po = queries[qi];
+        const float4 po = qsrc[local];
         float sx, sy, sz;
         associate_to_map(a, po, sx, sy, sz);
         Top5 nn;

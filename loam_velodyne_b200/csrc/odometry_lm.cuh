@@ -218,7 +218,12 @@ __device__ __forceinline__ float sqdiff3(const float4& a, float bx, float by, fl
 // reference's scan loops with their ring `break` (:262-276, :281-296) visit exactly an index range given by two of
 // these offsets, which removes the only dependency between the steps of the scan.
 constexpr int RING_OFF_WORDS = 258;
-__global__ void ring_offsets_kernel(const float4* __restrict__ last, int n, int* __restrict__ off) {
+// blockIdx.y selects the cloud: one launch covers the last corner and the last surface cloud (off1 = nullptr: one cloud)
+__global__ void ring_offsets_kernel(const float4* __restrict__ last0, int n0, int* __restrict__ off0,
+                                    const float4* __restrict__ last1 = nullptr, int n1 = 0, int* __restrict__ off1 = nullptr) {
+  const float4* __restrict__ last = blockIdx.y == 0 ? last0 : last1;
+  const int n = blockIdx.y == 0 ? n0 : n1;
+  int* __restrict__ off = blockIdx.y == 0 ? off0 : off1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int r = (int)last[i].w;
@@ -528,9 +533,15 @@ struct ToEndArgs {
   float rx, ry, rz, tx, ty, tz, inv_sp;
   float srx, crx, sry, cry, srz, crz;
 };
-__global__ void transform_to_end_kernel(float4* __restrict__ p, int n, ToEndArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// (p1, n1): an optional second cloud handled by the same launch (less sharp + less flat at the end of an odometry sweep)
+__global__ void transform_to_end_kernel(float4* __restrict__ p0, int n0, ToEndArgs a, float4* __restrict__ p1 = nullptr, int n1 = 0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4* __restrict__ p = p0;
+  if (i >= n0) {
+    i -= n0;
+    p = p1;
+    if (i >= n1) return;
+  }
   float4 q = p[i];
   const float s = a.inv_sp * (q.w - (float)(int)q.w);
   float x = q.x - s * a.tx, y = q.y - s * a.ty, z = q.z - s * a.tz;
@@ -546,6 +557,26 @@ __global__ void transform_to_end_kernel(float4* __restrict__ p, int n, ToEndArgs
   q.y = y + a.ty;
   q.z = z + a.tz;
   p[i] = q;
+}
+
+// Several device-to-device cloud copies in ONE launch (the hand-offs between the stage objects move 3-7 clouds per sweep;
+// as separate cudaMemcpyAsync calls they cost more host time than the copies take on the GPU).
+constexpr int GATHER_MAX_SEG = 8;
+struct GatherSegs {
+  const float4* src[GATHER_MAX_SEG];
+  float4* dst[GATHER_MAX_SEG];
+  int end[GATHER_MAX_SEG];  // exclusive prefix end of segment k in the flattened index space
+  int n_seg;
+};
+__global__ void gather_segments_kernel(GatherSegs g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.end[g.n_seg - 1]) return;
+  int k = 0;
+#pragma unroll
+  for (int s = 0; s < GATHER_MAX_SEG - 1; s++)
+    if (s < g.n_seg - 1 && i >= g.end[s]) k = s + 1;
+  const int local = i - (k > 0 ? g.end[k - 1] : 0);
+  g.dst[k][local] = g.src[k][local];
 }
 
 __global__ void transform_to_map_kernel(float4* __restrict__ p, int n, MapIterArgs a) {
