@@ -517,6 +517,9 @@ def hbm_roofline(args, api):
     nq = 2_000_000
     q = surf[rng.randint(0, surf.shape[0], nq)].copy()
     q[:, :3] += rng.normal(0, 0.05, (nq, 3)).astype(np.float32)
+    if os.environ.get("LOAM_B200_STRESS_SORTED"):  # development: queries in cell order (z, y, x)
+        cell = np.floor(q[:, :3]).astype(np.int64)
+        q = np.ascontiguousarray(q[np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))])
     prof = pipe.mapping.kernel_profile_queries(q, 10)
     probes, cands = prof["probes_per_query"] * nq, prof["candidates_per_query"] * nq
     alg_bytes = nq * 16 + probes * ENTRY_BYTES + cands * 16 + 36 * 4
@@ -677,6 +680,7 @@ def main():
     ap.add_argument("--slab", type=int, default=10, help="slab width in metres of the cube-sharded map (N > 1)")
     ap.add_argument("--sharded-workload", default="hdl64_10m", choices=sorted(WORKLOADS),
                     help="N > 1: workload of the additional single-stream run on the cube-sharded map")
+    ap.add_argument("--only-hbm", action="store_true", help="development: print only the roofline_hbm object")
     ap.add_argument("--no-hbm-roofline", action="store_true", help="skip the config-5 (20 M-point map) kernel measurement")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the cube-sharded single-stream section")
     ap.add_argument("--min-seconds", type=float, default=0.5,
@@ -690,6 +694,12 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     rank, world, local_rank = rank_world()
+    if args.only_hbm:  # development aid: just the config-5 kernel measurement
+        import __graft_entry__ as ge
+        ge.build()
+        from loam_velodyne_b200 import api
+        print(json.dumps(hbm_roofline(args, api)))
+        return
     if args.impl == "reference":
         if args.steps > 40:
             args.steps = 40  # bounded sample: ~0.3 s per sweep on one core

@@ -216,7 +216,7 @@ struct GridCellLookup {
 // (d2 < 1.0) in `out` (ascending; id = -1 for missing ones).  gmask = the group's 8 lanes within the warp;
 // pre[GRID_SLOTS + 1] / first[GRID_SLOTS] = this group's rows of shared memory.  LOOKUP maps a neighbour cell to its
 // run of points (GridCellLookup above, MapCellLookup in mapstore.cuh).
-template <bool STATS, typename LOOKUP>
+template <bool STATS, typename LOOKUP, int MLP = 2>
 __device__ __forceinline__ void grid_knn5_group8(LOOKUP& lk, float qx, float qy, float qz, int sub,
                                                  unsigned gmask, unsigned* pre, unsigned* first, Cand5& out,
                                                  unsigned* stats) {
@@ -267,33 +267,32 @@ __device__ __forceinline__ void grid_knn5_group8(LOOKUP& lk, float qx, float qy,
       while (j_begin >= hi) { f++; hi = pre[f + 1]; }  // skip empty slots with the same prefix
       int idx = (int)(first[f] + (j_begin - pre[f]));
       unsigned j = j_begin;
+      // MLP loads in flight per lane: the cursor is advanced MLP times first (ALU + shared memory only), then the loads are
+      // issued together, then evaluated in order -- the same candidates in the same order for every MLP
       while (j < j_end) {
-        const int i0 = idx;
-        const float4 p0 = __ldg(sorted + i0);
-        j++; idx++;
-        if (j < j_end && j >= hi) {
-          do { f++; hi = pre[f + 1]; } while (j >= hi);
-          idx = (int)first[f];
-        }
-        int i1 = -1;
-        float4 p1 = p0;
-        if (j < j_end) {
-          i1 = idx;
-          p1 = __ldg(sorted + i1);
-          j++; idx++;
-          if (j < j_end && j >= hi) {
-            do { f++; hi = pre[f + 1]; } while (j >= hi);
-            idx = (int)first[f];
+        int ids[MLP];
+#pragma unroll
+        for (int u = 0; u < MLP; u++) {
+          ids[u] = -1;
+          if (j < j_end) {
+            ids[u] = idx;
+            j++; idx++;
+            if (j < j_end && j >= hi) {
+              do { f++; hi = pre[f + 1]; } while (j >= hi);
+              idx = (int)first[f];
+            }
           }
         }
-        {
-          const float dx = qx - p0.x, dy = qy - p0.y, dz = qz - p0.z;
-          cand5_offer(mine, dx * dx + dy * dy + dz * dz, i0);
-        }
-        if (i1 >= 0) {
-          const float dx = qx - p1.x, dy = qy - p1.y, dz = qz - p1.z;
-          cand5_offer(mine, dx * dx + dy * dy + dz * dz, i1);
-        }
+        float4 pp[MLP];
+#pragma unroll
+        for (int u = 0; u < MLP; u++)
+          if (ids[u] >= 0) pp[u] = __ldg(sorted + ids[u]);
+#pragma unroll
+        for (int u = 0; u < MLP; u++)
+          if (ids[u] >= 0) {
+            const float dx = qx - pp[u].x, dy = qy - pp[u].y, dz = qz - pp[u].z;
+            cand5_offer(mine, dx * dx + dy * dy + dz * dz, ids[u]);
+          }
       }
     }
   }

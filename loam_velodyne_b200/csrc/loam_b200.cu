@@ -396,6 +396,49 @@ int fetch_ints(loam_b200_ctx* c, const int* d_src, int n, int* h_dst) {
   return LOAM_B200_OK;
 }
 
+// Run `body` (enqueues on c->stream and its lanes only: no host synchronisation, no waits on events of other contexts)
+// through capture + update + one launch (ctx.cuh: CapturedSeq).  LOAM_B200_NO_CAPTURE=1 or profiling: direct enqueues.
+template <typename F>
+int run_captured(loam_b200_ctx* c, CapturedSeq& cs, F body) {
+  static const bool off = getenv("LOAM_B200_NO_CAPTURE") != nullptr;
+  if (off || c->prof_on) return body();
+  cudaStream_t origin = c->stream;
+  LB_CUDA(c, cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed));
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(origin, &g);
+  if (rc != LOAM_B200_OK || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    if (rc != LOAM_B200_OK) return rc;
+    return fail_cuda(c, e == cudaSuccess ? cudaErrorUnknown : e, "cudaStreamEndCapture", __LINE__);
+  }
+  bool updated = false;
+  if (cs.exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(cs.exec, g, &info) == cudaSuccess) {
+      updated = true;
+    } else {  // the sequence took a different branch: instantiate anew
+      cudaGetLastError();
+      cs.destroy();
+    }
+  }
+  if (!updated) {
+    const cudaError_t ei = cudaGraphInstantiate(&cs.exec, g, 0);
+    if (ei != cudaSuccess) {
+      cudaGraphDestroy(g);
+      cs.exec = nullptr;
+      return fail_cuda(c, ei, "cudaGraphInstantiate", __LINE__);
+    }
+    cs.rebuilds++;
+  }
+  const cudaError_t el = cudaGraphLaunch(cs.exec, origin);
+  cudaGraphDestroy(g);
+  if (el != cudaSuccess) return fail_cuda(c, el, "cudaGraphLaunch", __LINE__);
+  cs.launches++;
+  return LOAM_B200_OK;
+}
+
 }  // namespace
 
 #include "comm.inc"
@@ -595,6 +638,7 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   }
   c->odom_loop.destroy();
   c->map_loop.destroy();
+  c->seq_features.destroy(); c->seq_begin_sweep.destroy(); c->seq_end_sweep.destroy(); c->seq_rebuild.destroy();
   if (c->peer_inbox) cudaFree(c->peer_inbox);
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
@@ -707,22 +751,27 @@ static int run_features(loam_b200_ctx* c, const float4* d_pts, int n, const int3
   LB_CUDA(c, c->ring_table_host.reserve(2 * (size_t)n_rings));
   memcpy(c->ring_table_host.p, ring_start, (size_t)n_rings * 4);
   memcpy(c->ring_table_host.p + n_rings, ring_end, (size_t)n_rings * 4);
-  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_start.p, c->ring_table_host.p, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
-  LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_end.p, c->ring_table_host.p + n_rings, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
-
-  prof_begin(c, LOAM_B200_K_FEATURES);
-  feature_ring_kernel<<<n_rings, FEAT_THREADS, smem, c->stream>>>(d_pts, c->reg_ring_start.p, c->reg_ring_end.p, fp,
-                                                                  ncap, n2cap, c->reg_picks.p, c->reg_counts.p,
-                                                                  c->reg_label.p, c->reg_lessflat.p);
-  LB_LAUNCH_CHECK(c);
   int* dense = c->reg_picks.p + (size_t)n_rings * slots;
   int* totals = c->reg_counts.p + (size_t)n_rings * 4;
-  feature_pack_kernel<<<n_rings, 256, 0, c->stream>>>(
-      c->reg_counts.p, c->reg_picks.p, c->reg_ring_start.p, d_pts, c->reg_lessflat.p, n_rings, fp, dense,
-      dense + (size_t)n_rings * fp.cap_sharp, dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less),
-      c->cloud[LOAM_B200_C_REG_SHARP].p, c->cloud[LOAM_B200_C_REG_LESS_SHARP].p, c->cloud[LOAM_B200_C_REG_FLAT].p,
-      c->cloud[LOAM_B200_C_REG_LESS_FLAT].p, totals);
-  LB_LAUNCH_CHECK(c);
+  prof_begin(c, LOAM_B200_K_FEATURES);
+  {
+    const int rcs = run_captured(c, c->seq_features, [&]() -> int {
+      LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_start.p, c->ring_table_host.p, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
+      LB_CUDA(c, cudaMemcpyAsync(c->reg_ring_end.p, c->ring_table_host.p + n_rings, n_rings * 4, cudaMemcpyHostToDevice, c->stream));
+      feature_ring_kernel<<<n_rings, FEAT_THREADS, smem, c->stream>>>(d_pts, c->reg_ring_start.p, c->reg_ring_end.p, fp,
+                                                                      ncap, n2cap, c->reg_picks.p, c->reg_counts.p,
+                                                                      c->reg_label.p, c->reg_lessflat.p);
+      LB_LAUNCH_CHECK(c);
+      feature_pack_kernel<<<n_rings, 256, 0, c->stream>>>(
+          c->reg_counts.p, c->reg_picks.p, c->reg_ring_start.p, d_pts, c->reg_lessflat.p, n_rings, fp, dense,
+          dense + (size_t)n_rings * fp.cap_sharp, dense + (size_t)n_rings * (fp.cap_sharp + fp.cap_less),
+          c->cloud[LOAM_B200_C_REG_SHARP].p, c->cloud[LOAM_B200_C_REG_LESS_SHARP].p, c->cloud[LOAM_B200_C_REG_FLAT].p,
+          c->cloud[LOAM_B200_C_REG_LESS_FLAT].p, totals);
+      LB_LAUNCH_CHECK(c);
+      return LOAM_B200_OK;
+    });
+    if (rcs) return rcs;
+  }
   prof_end(c);
   {
     const int rcf = fetch_ints(c, totals, 4, c->reg_totals);
@@ -955,7 +1004,8 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
             GridCellLookup{grid_view_of(c->grid[0])}, GridCellLookup{grid_view_of(c->grid[1])}, c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls, cb,
             nb, a, c->partials.p, c->result.p, c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr,
             mb, sh, pr, cap);
-    } else if (c->map_use_store)
+    }
+    else if (c->map_use_store)
       map_iterate_kernel<false><<<nb, MAP_THREADS, 0, c->stream>>>(
           store_lookup_of(c, 0), store_lookup_of(c, 1), c->map_q_corner, c->map_q_surf, nc, c0, lc, s0, ls, cb, a, c->partials.p, c->result.p,
           c->ticket.p, dbg ? c->dbg_coeff.p : nullptr, dbg ? c->dbg_sel.p : nullptr, nullptr, nullptr, mb, sh, pr);

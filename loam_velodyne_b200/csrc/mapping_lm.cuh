@@ -429,8 +429,11 @@ static_assert(MAP_Q_PER_BLOCK == 32, "the fit phase maps one query to one lane o
 //            partial written straight from registers; the last CTA folds all partials in fixed order.
 // 64 registers / thread -> 4 CTAs per SM, so the ~550 CTAs of an HDL-64 sweep are a single wave on 148 SMs (at 72
 // registers the 8-lane kernel ran 1.06 waves: half of the kernel's time was a second wave of 63 CTAs).
-template <bool STATS, typename LOOKUP, bool DEVLOOP = false>
-__global__ void __launch_bounds__(MAP_THREADS, 4)
+// MLP = candidate loads in flight per lane.  Measured on the 20 M-point stress (HBM-bound, profiles/r2_map_iterate_hbm.md):
+// MLP 2 (64 registers, 4 CTAs / SM) 3.31 ms, MLP 4 (80 registers, 3 CTAs) 3.63 ms, MLP 8 (96 registers, 2 CTAs) 4.69 ms --
+// occupancy is worth more than deeper per-lane pipelining, so 2 is used everywhere.
+template <bool STATS, typename LOOKUP, bool DEVLOOP = false, int MLP = 2>
+__global__ void __launch_bounds__(MAP_THREADS, MLP > 4 ? 2 : (MLP > 2 ? 3 : 4))
 map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, const float4* queries_surf,
                    int n_corner_total, int c0, int n_corner, int s0, int n_surf, int corner_blocks, MapIterArgs a_param,
                    float* __restrict__ partials, float* __restrict__ result, unsigned int* ticket,
@@ -489,7 +492,7 @@ map_iterate_kernel(LOOKUP corner_grid, LOOKUP surf_grid, const float4* queries, 
       // cube-sharded map: the rank owning the cell of the transformed point evaluates it, everybody else skips it
       if (shard_owns(sh, store_cell(sx))) {
         unsigned ws[2] = {0u, 0u};
-        grid_knn5_group8<STATS>(grid, sx, sy, sz, sub, gmask, s_pre[g], s_first[g], best, ws);
+        grid_knn5_group8<STATS, LOOKUP, MLP>(grid, sx, sy, sz, sub, gmask, s_pre[g], s_first[g], best, ws);
         if (STATS) {
           atomicAdd(&walk_totals[0], (unsigned long long)ws[0]);
           atomicAdd(&walk_totals[1], (unsigned long long)ws[1]);
