@@ -66,6 +66,13 @@ int loam_b200_peer_disconnect(loam_b200_ctx* ctx);
 /* host logic of the slab partition: owner of the cell with x index cell_x; does `rank` store the point with coordinate x */
 int loam_b200_shard_owner(int cell_x, int slab_cells, int world);
 int loam_b200_shard_stores(float x, int rank, int world, int slab_cells);
+/* The library records some per-sweep enqueue sequences by stream capture and launches them as one graph.  While a stream
+ * records, cudaDeviceSynchronize() from any thread of the process returns an error, so the sequence issued by the context's
+ * helper thread (the asynchronous end-of-sweep map update) is only recorded after the caller has opted in here -- i.e. has
+ * promised to synchronise through loam_b200_sync / loam_b200_pipeline_sync (or per stream) rather than device-wide while
+ * sweeps are in flight.  The streaming pipeline (loam_b200_pipeline_submit) opts in.  LOAM_B200_NO_CAPTURE=1 disables all
+ * recording. */
+int loam_b200_allow_async_capture(loam_b200_ctx* ctx, int on);
 /* Bind the calling host thread to a CUDA device (cudaSetDevice): every host thread other than the one that created a
  * context must call this once before using the context (helper threads of the library do so themselves). */
 int loam_b200_bind_thread(int device);

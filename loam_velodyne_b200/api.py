@@ -96,6 +96,7 @@ def lib():
         "loam_b200_sync": (C.c_int, [vp]),
         "loam_b200_bind_thread": (C.c_int, [C.c_int]),
         "loam_b200_set_priority": (C.c_int, [vp, C.c_int]),
+        "loam_b200_allow_async_capture": (C.c_int, [vp, C.c_int]),
         "loam_b200_stream": (vp, [vp]),
         "loam_b200_extract_features": (C.c_int, [vp, _F, C.c_int, _I, _I, C.c_int, C.POINTER(RegParams),
                                                  C.POINTER(Features)]),
@@ -758,6 +759,7 @@ class Pipeline(_Handle):
             if r is None:
                 break
             res.append(r)
+        self.sync()  # the last sweep's asynchronous map update has been issued and has finished
         return res
 
 

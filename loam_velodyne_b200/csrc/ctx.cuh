@@ -21,6 +21,15 @@
 
 namespace loamb {
 
+// While a thread records an enqueue sequence by stream capture (run_captured, loam_b200.cu) the kernels it has "launched"
+// have not run yet: a buffer that grows in the middle of the sequence must not be freed under them.  The recording thread
+// points this at a list; buffers replaced during the recording are parked there and freed once the graph has executed.
+inline thread_local std::vector<void*>* tl_deferred_free = nullptr;
+inline void free_device_buffer(void* q) {
+  if (tl_deferred_free) tl_deferred_free->push_back(q);
+  else cudaFree(q);
+}
+
 // growable device allocation (never shrinks; geometric growth so steady-state sweeps allocate nothing)
 template <typename T>
 struct DevBuf {
@@ -30,7 +39,7 @@ struct DevBuf {
     if (n <= cap) return cudaSuccess;
     size_t want = cap ? cap : 256;
     while (want < n) want = 2 * want + 256;  // a reallocation synchronises the device: keep them rare (180 GB of HBM)
-    if (p) cudaFree(p);
+    if (p) free_device_buffer(p);
     p = nullptr;
     cap = 0;
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
@@ -148,7 +157,21 @@ struct LoopGraph {
 struct CapturedSeq {
   cudaGraphExec_t exec = nullptr;
   long long launches = 0, rebuilds = 0;
+  std::vector<void*> parked;      // device buffers replaced while a sequence was being recorded ...
+  cudaEvent_t parked_ev = nullptr;  // ... free once the launch that may still read them has finished
+  void free_parked(bool wait) {
+    if (parked.empty()) return;
+    if (parked_ev) {
+      if (wait) cudaEventSynchronize(parked_ev);
+      else if (cudaEventQuery(parked_ev) != cudaSuccess) { cudaGetLastError(); return; }
+    }
+    for (void* q : parked) cudaFree(q);
+    parked.clear();
+  }
   void destroy() {
+    free_parked(true);
+    if (parked_ev) cudaEventDestroy(parked_ev);
+    parked_ev = nullptr;
     if (exec) cudaGraphExecDestroy(exec);
     exec = nullptr;
   }
@@ -244,6 +267,11 @@ struct loam_b200_ctx {
   loamb::DevBuf<unsigned char> lm_state;  // OdomLmState + MapLmState (lmstep.cuh): pose of the device-resident loops
   loamb::LoopGraph odom_loop, map_loop;   // their loop graphs (loam_b200_odom_solve / loam_b200_map_solve)
   loamb::CapturedSeq seq_features, seq_begin_sweep, seq_end_sweep, seq_rebuild;  // per-sweep enqueue sequences (run_captured)
+  // While a stream records, cudaDeviceSynchronize() from ANY thread of the process fails (CUDA cannot wait for a recording
+  // stream).  Sequences recorded inside a blocking API call are safe for single-threaded callers; the end-of-sweep update
+  // runs on the helper thread while the caller is back in its own code, so it is only recorded when the caller opted in
+  // (loam_b200_allow_async_capture: the streaming pipeline, whose users synchronise through loam_b200_pipeline_sync).
+  bool async_capture_ok = false;
   // map_iterate_v2_kernel (persistent, warp-specialised, bulk-staged candidates): persistent grid per instantiation
   // [store / bounding-box lookup][stage API / device loop] for the candidate capacity in use, 0 = not yet queried
   int map_v2_grid[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};

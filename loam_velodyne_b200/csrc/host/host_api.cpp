@@ -149,6 +149,9 @@ struct StreamRunner {
   static constexpr size_t MAX_QUEUED = 2;
 
   explicit StreamRunner(PipeH* pipe) : p(pipe), device(loam::b200::defaultDevice()) {
+    // users of the streaming form synchronise through loam_b200_pipeline_sync: the helper thread may record its sequence
+    auto* mc = p->map.m.deviceContext();
+    mc->check(loam_b200_allow_async_capture(mc->get(), 1), "loam_b200_allow_async_capture");
     th[0] = std::thread([this] { run(0); });
     th[1] = std::thread([this] { run(1); });
     th[2] = std::thread([this] { run(2); });

@@ -398,15 +398,26 @@ int fetch_ints(loam_b200_ctx* c, const int* d_src, int n, int* h_dst) {
 
 // Run `body` (enqueues on c->stream and its lanes only: no host synchronisation, no waits on events of other contexts)
 // through capture + update + one launch (ctx.cuh: CapturedSeq).  LOAM_B200_NO_CAPTURE=1 or profiling: direct enqueues.
+static thread_local bool tl_in_worker = false;
+
 template <typename F>
 int run_captured(loam_b200_ctx* c, CapturedSeq& cs, F body) {
   static const bool off = getenv("LOAM_B200_NO_CAPTURE") != nullptr;
-  if (off || c->prof_on) return body();
+  if (off || c->prof_on || (tl_in_worker && !c->async_capture_ok)) return body();
   cudaStream_t origin = c->stream;
+  cs.free_parked(false);  // buffers replaced during an earlier recording whose launch has finished by now
   LB_CUDA(c, cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed));
+  std::vector<void*> replaced;
+  tl_deferred_free = &replaced;  // DevBuf::reserve parks replaced buffers instead of freeing them under recorded kernels
   const int rc = body();
+  tl_deferred_free = nullptr;
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(origin, &g);
+  if (!replaced.empty()) {  // (also on the failure path below: an earlier launch may still read them)
+    if (!cs.parked.empty()) cs.free_parked(true);  // rare: two growth steps in a row
+    cs.parked.swap(replaced);
+    if (!cs.parked_ev) cudaEventCreateWithFlags(&cs.parked_ev, cudaEventDisableTiming);
+  }
   if (rc != LOAM_B200_OK || e != cudaSuccess || !g) {
     if (g) cudaGraphDestroy(g);
     cudaGetLastError();
@@ -435,6 +446,10 @@ int run_captured(loam_b200_ctx* c, CapturedSeq& cs, F body) {
   const cudaError_t el = cudaGraphLaunch(cs.exec, origin);
   cudaGraphDestroy(g);
   if (el != cudaSuccess) return fail_cuda(c, el, "cudaGraphLaunch", __LINE__);
+  if (!cs.parked.empty()) {
+    if (!cs.parked_ev) cudaEventCreateWithFlags(&cs.parked_ev, cudaEventDisableTiming);
+    cudaEventRecord(cs.parked_ev, origin);
+  }
   cs.launches++;
   return LOAM_B200_OK;
 }
@@ -443,8 +458,6 @@ int run_captured(loam_b200_ctx* c, CapturedSeq& cs, F body) {
 
 #include "comm.inc"
 #include "peer.inc"
-
-static thread_local bool tl_in_worker = false;
 
 static int async_join(loam_b200_ctx* c) {
   AsyncWorker* w = c->worker;
@@ -669,6 +682,12 @@ int loam_b200_set_priority(loam_b200_ctx* c, int level) {
     if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
     l.stream = ls;
   }
+  return LOAM_B200_OK;
+}
+
+int loam_b200_allow_async_capture(loam_b200_ctx* c, int on) {
+  CHECK_CTX(c);
+  c->async_capture_ok = on != 0;
   return LOAM_B200_OK;
 }
 

@@ -579,7 +579,7 @@ def test_streaming_pipeline_equals_sequential(scene, sweeps_vlp16, map_200k):
         np.testing.assert_array_equal(od_a, od_b)
         np.testing.assert_array_equal(aft_a, aft_b)
     dev = [torch.from_numpy(p).cuda() for p, _ in sweeps_vlp16]
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()
     res = pc.run_stream(sweeps_vlp16, device_ptrs=[t.data_ptr() for t in dev])
     for (ok_a, od_a, aft_a, _), (ok_b, od_b, aft_b) in zip(seq, res):
         np.testing.assert_array_equal(aft_a, aft_b)
@@ -599,7 +599,7 @@ def test_device_resident_sweep_input(scene, sweeps_vlp16, map_200k):
     pb.seed_map(corner, surf)
     for pts, rs in sweeps_vlp16[:3]:
         t = torch.from_numpy(pts).cuda()
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         _, od_a, aft_a, _ = pa.sweep(pts, rs)
         _, od_b, aft_b, _ = pb.sweep_device(t.data_ptr(), rs)
         np.testing.assert_array_equal(od_a, od_b)
