@@ -327,6 +327,13 @@ struct loam_b200_ctx {
   loamb::CubeGridHost map_grid;
   int map_n_valid = 0;
   float map_leaf[2] = {0.2f, 0.4f};
+  // The end-of-sweep map update runs on its own stream (lane 3) so that the next sweep's hand-off and stack filters do not
+  // queue behind it: it starts after ev_loop_done (the loop of its sweep, main stream), and whatever reads the map next
+  // waits for ev_update first (async_join orders the main stream behind it; begin_sweep does so only after its filters).
+  cudaEvent_t ev_loop_done = nullptr, ev_update = nullptr;
+  bool update_pending = false;
+  loamb::DevBuf<float4> stack_alt[2];            // the two down-sized stacks are double-buffered (the update of sweep k
+  loamb::DevBuf<unsigned char> rank_of_cube_alt;  // still reads them / the cube table while sweep k + 1 writes its own)
   cudaEvent_t ev_xfer = nullptr;
   cudaEvent_t ev_table = nullptr;
   bool ev_table_pending = false;
@@ -404,6 +411,17 @@ struct LaneScope {
 inline cudaError_t lanes_fork(loam_b200_ctx* c, int n_lanes) {
   cudaError_t e = cudaEventRecord(c->ev_fork, c->stream);
   for (int i = 0; i < n_lanes && e == cudaSuccess; i++) e = cudaStreamWaitEvent(c->lanes[i].stream, c->ev_fork, 0);
+  return e;
+}
+// one particular lane (1-based) forked from / joined into the current stream
+inline cudaError_t lane_fork_one(loam_b200_ctx* c, int lane) {
+  cudaError_t e = cudaEventRecord(c->ev_fork, c->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c->lanes[lane - 1].stream, c->ev_fork, 0);
+  return e;
+}
+inline cudaError_t lane_join_one(loam_b200_ctx* c, int lane) {
+  cudaError_t e = cudaEventRecord(c->lanes[lane - 1].done, c->lanes[lane - 1].stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->lanes[lane - 1].done, 0);
   return e;
 }
 // ... and the main stream continues after all of them

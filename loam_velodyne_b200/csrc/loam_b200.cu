@@ -22,11 +22,18 @@ std::atomic<long long> g_total_launches{0};  // helper threads launch too
 }
 
 // every entry point first waits for the context's helper thread (ctx.cuh: AsyncWorker) and reports its status
-static int async_join(loam_b200_ctx* c);
+static int async_join(loam_b200_ctx* c, bool order = true);
 #define CHECK_CTX(c)                      \
   if (!(c)) return LOAM_B200_ERR_ARG;     \
   {                                       \
     const int _rcj = async_join(c);       \
+    if (_rcj) return _rcj;                \
+  }
+// ... without ordering the main stream behind a pending map update (entry points that do not read the map first)
+#define CHECK_CTX_NO_ORDER(c)             \
+  if (!(c)) return LOAM_B200_ERR_ARG;     \
+  {                                       \
+    const int _rcj = async_join(c, false);\
     if (_rcj) return _rcj;                \
   }
 
@@ -459,13 +466,25 @@ int run_captured(loam_b200_ctx* c, CapturedSeq& cs, F body) {
 #include "comm.inc"
 #include "peer.inc"
 
-static int async_join(loam_b200_ctx* c) {
+// the main stream continues behind the map update that runs on the update stream
+static int order_after_update(loam_b200_ctx* c) {
+  if (!c->update_pending) return LOAM_B200_OK;
+  c->update_pending = false;
+  LB_CUDA(c, cudaStreamWaitEvent(c->main_stream, c->ev_update, 0));
+  return LOAM_B200_OK;
+}
+
+static int async_join(loam_b200_ctx* c, bool order) {
   AsyncWorker* w = c->worker;
-  if (!w || tl_in_worker) return LOAM_B200_OK;
-  std::unique_lock<std::mutex> lk(w->m);
-  w->cv.wait(lk, [w] { return !w->busy && !w->has_job; });
-  const int rc = w->last_rc;
-  w->last_rc = LOAM_B200_OK;
+  if (tl_in_worker) return LOAM_B200_OK;
+  int rc = LOAM_B200_OK;
+  if (w) {
+    std::unique_lock<std::mutex> lk(w->m);
+    w->cv.wait(lk, [w] { return !w->busy && !w->has_job; });
+    rc = w->last_rc;
+    w->last_rc = LOAM_B200_OK;
+  }
+  if (rc == LOAM_B200_OK && order) rc = order_after_update(c);
   return rc;
 }
 
@@ -565,7 +584,9 @@ int loam_b200_create(loam_b200_ctx** out, int device) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_xfer, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_loop_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_update, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
     delete c;
     return LOAM_B200_ERR_CUDA;
@@ -644,6 +665,9 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_xfer) cudaEventDestroy(c->ev_xfer);
   if (c->ev_table) cudaEventDestroy(c->ev_table);
+  if (c->ev_loop_done) cudaEventDestroy(c->ev_loop_done);
+  if (c->ev_update) cudaEventDestroy(c->ev_update);
+  c->stack_alt[0].release(); c->stack_alt[1].release(); c->rank_of_cube_alt.release();
   for (auto& st : c->store) {
     st.keys.release(); st.keys_alt.release(); st.state.release(); st.state_alt.release(); st.pts_alt.release();
     st.table.release(); st.cube_stats.release(); st.valid_by_slot.release(); st.s_pts.release(); st.e_pts.release();
