@@ -304,13 +304,28 @@ __global__ void store_voxel_merge_kernel(const float4* __restrict__ s_pts, const
         if (x.a != qx.a) continue;  // pcl filters cube by cube: a voxel never merges across a cube face
         unsigned start = 0, count = 0;
         if (!store_probe(pool, torus_key(x, y, z), start, count, nullptr)) continue;
-        for (unsigned j = start; j < start + count; j++) {
-          if (pool_state[j] & (ST_RAW | ST_DEAD)) continue;
-          const float4 p = pool.pts[j];
-          if (floorf(p.x * inv_leaf) == fvx && floorf(p.y * inv_leaf) == fvy && floorf(p.z * inv_leaf) == fvz) {
-            sx += p.x; sy += p.y; sz += p.z; si += p.w;
-            cnt++;
-            pool_state[j] |= ST_DEAD;
+        // four points of the cell's run per step: the loads are issued together (the byte store below may alias anything
+        // as far as the compiler knows, so a plain loop became one dependent load per point: 39 us for ~20 k voxels),
+        // evaluated in order -- the summation order is unchanged
+        for (unsigned j0 = start; j0 < start + count; j0 += 4) {
+          unsigned char st4[4];
+          float4 p4[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const unsigned j = j0 + u;
+            const bool in = j < start + count;
+            st4[u] = in ? pool_state[j] : (unsigned char)ST_DEAD;
+            p4[u] = in ? __ldg(&pool.pts[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (st4[u] & (ST_RAW | ST_DEAD)) continue;
+            const float4 p = p4[u];
+            if (floorf(p.x * inv_leaf) == fvx && floorf(p.y * inv_leaf) == fvy && floorf(p.z * inv_leaf) == fvz) {
+              sx += p.x; sy += p.y; sz += p.z; si += p.w;
+              cnt++;
+              pool_state[j0 + u] = st4[u] | ST_DEAD;
+            }
           }
         }
       }
