@@ -94,6 +94,13 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def _run(self):
+        # keep the sampler off the cores the stage threads work on: last core of the set this process may use
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            if len(cores) > 8:
+                os.sched_setaffinity(threading.get_native_id(), {cores[-1]})
+        except Exception:
+            pass
         try:
             self._run_nvml()
         except Exception:
