@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENTRY_BYTES = 16          # bytes of one cell-table entry (csrc/gridnn.cuh)
-TRAFFIC_FILE = "r1_map_iterate_traffic.json"       # committed ncu DRAM bytes per launch, config 3
+TRAFFIC_FILE = "r2_map_iterate_traffic.json"       # committed ncu DRAM bytes per launch, config 3
 TRAFFIC_FILE_HBM = "r2_map_iterate_hbm_traffic.json"  # ... config 5
 
 WORKLOADS = {

@@ -137,6 +137,7 @@ MapCellLookup store_lookup_of(const loam_b200_ctx* c, int kind) {
   lk.g = MapGridView{st.table.p, st.mask, c->cloud[kind == 0 ? LOAM_B200_C_MAP_CORNER_POOL : LOAM_B200_C_MAP_SURF_POOL].p,
                      c->rank_of_cube.p, c->map_grid.cen_w, c->map_grid.cen_h, c->map_grid.cen_d, c->map_n_valid};
   lk.ax = lk.ay = lk.az = CellAxis{0, 0, 0};
+  lk.prune = (long long)c->cloud_n[LOAM_B200_C_MAP_CORNER_POOL] + c->cloud_n[LOAM_B200_C_MAP_SURF_POOL] > 4000000 ? 1 : 0;
   return lk;
 }
 

@@ -88,6 +88,7 @@ __device__ __forceinline__ bool store_probe(const MapGridView& g, unsigned key, 
 struct MapCellLookup {
   MapGridView g;
   CellAxis ax, ay, az;
+  int prune;  // see GridCellLookup
   __device__ __forceinline__ bool prepare(float qx, float qy, float qz) {
     ax = cell_axis((int)floorf(qx), CUBE_W);
     ay = cell_axis((int)floorf(qy), CUBE_H);
