@@ -242,7 +242,8 @@ def run_cuda(args, rank, world, local_rank):
         return b"".join(bytes(t.cpu().tolist()) for t in every)
 
     # what the timed windows run on: (corner map, surface map, host sweeps, device sweeps, cube-sharded?)
-    work = {"corner": corner, "surf": surf, "sweeps": sweeps, "d_sweeps": d_sweeps, "cube_sharded": sharded}
+    work = {"corner": corner, "surf": surf, "sweeps": sweeps, "d_sweeps": d_sweeps, "cube_sharded": sharded,
+            "warmup": args.warmup, "steps": args.steps}
 
     def fresh_pipeline():
         p = api.Pipeline()
@@ -290,12 +291,12 @@ def run_cuda(args, rank, world, local_rank):
                         acc["it_m"] += pipe.mapping.last_iterations()
             pipe.sync()
 
-        run(0, args.warmup, False)
+        run(0, work["warmup"], False)
         if streaming:
             pipe.stage_seconds(reset=True)
         barrier()
         t0 = time.perf_counter()
-        run(args.warmup, n_total, True)
+        run(work["warmup"], work["warmup"] + work["steps"], True)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if streaming:
@@ -441,35 +442,51 @@ def run_cuda(args, rank, world, local_rank):
 def sharded_section(args, api, torch, dev, rank, world, work, arm, ref_sweeps):
     """One sweep stream on `world` GPUs with the map sharded by cube slabs (DESIGN.md "Multi-GPU"): every rank feeds the
     same sweeps (registration and odometry are replicated), holds its slabs of the map, evaluates the queries
-    that fall into them; the per-iteration all-reduce is fused into the iteration kernel.  Timed like the main arms."""
-    lidar_name, m, desc = WORKLOADS[args.sharded_workload]
-    n_total = args.warmup + args.steps
-    _, corner, surf, sweeps = make_workload(args.sharded_workload, n_total, 0)  # the same stream on every rank
-    d_sweeps = [torch.from_numpy(p).to(dev) for p, _ in sweeps]
-    pinned = [torch.from_numpy(p).pin_memory() for p, _ in sweeps]
-    sweeps = [(pinned[i].numpy(), sweeps[i][1]) for i in range(len(sweeps))]
-    saved = dict(work)
-    work.update({"corner": corner, "surf": surf, "sweeps": sweeps, "d_sweeps": d_sweeps, "cube_sharded": True})
-    try:
-        a_stream = arm(True, True, min(args.min_seconds, 0.2), 12)
-        a_seq = arm(False, True, 0.0, 3)
-    finally:
-        work.clear()
-        work.update(saved)
+    that fall into them; the per-iteration all-reduce is fused into the iteration kernel.  Timed like the main arms.
+    BASELINE config 4 (HDL-64 vs 10 M) at every N > 1; config 5 (128 x 4096 vs 20 M) in addition on 8 GPUs."""
+
+    def one(workload, warmup, steps, with_sequential):
+        lidar_name, m, desc = WORKLOADS[workload]
+        _, corner, surf, sweeps = make_workload(workload, warmup + steps, 0)  # the same stream on every rank
+        d_sweeps = [torch.from_numpy(p).to(dev) for p, _ in sweeps]
+        pinned = [torch.from_numpy(p).pin_memory() for p, _ in sweeps]
+        sweeps = [(pinned[i].numpy(), sweeps[i][1]) for i in range(len(sweeps))]
+        saved = dict(work)
+        work.update({"corner": corner, "surf": surf, "sweeps": sweeps, "d_sweeps": d_sweeps, "cube_sharded": True,
+                     "warmup": warmup, "steps": steps})
+        try:
+            a_stream = arm(True, True, min(args.min_seconds, 0.2), 12 if with_sequential else 3)
+            a_seq = arm(False, True, 0.0, 3) if with_sequential else None
+        finally:
+            work.clear()
+            work.update(saved)
+        if rank != 0:
+            return None
+        ms = lambda x: round(1e3 * x, 3)
+        rep = {"workload": desc, "map_points": int(corner.shape[0] + surf.shape[0]), "sweep_points": int(sweeps[0][0].shape[0]),
+               "n_gpus": world, "steps": steps, "warmup": warmup,
+               "value": round(steps / a_stream["seconds"], 3), "unit": "sweeps/s", "scaling": "strong",
+               "window_ms_min_median_max": [ms(a_stream["min"]), ms(a_stream["seconds"]), ms(a_stream["max"])],
+               "windows": a_stream["windows"]}
+        if a_seq is not None:
+            last = a_seq["runs"][0]
+            rep.update({"sequential_value": round(steps / a_seq["seconds"], 3),
+                        "sequential_mapping_ms_per_sweep": round(1e3 * float(last[2][3]) / steps, 4),
+                        "map_iters_per_sweep": round(last[4] / steps, 2)})
+        return rep
+
+    rep = one(args.sharded_workload, args.warmup, args.steps, True)
+    rep5 = None
+    if world >= 8 or args.sharded_config5:
+        rep5 = one("dense128_20m", 3, min(args.steps, 8), False)
     if rank != 0:
         return None
-    ms = lambda x: round(1e3 * x, 3)
-    last = a_seq["runs"][0]
-    return {"workload": desc, "map_points": int(corner.shape[0] + surf.shape[0]), "n_gpus": world,
-            "what": "ONE sweep stream, map sharded by %d m cube slabs (+ 2 m halo) over the GPUs, queries evaluated by the owner "
-                    "of their cell, all-reduce of the 32 normal-equation sums fused into the iteration kernel (peer stores over "
-                    "NVLink, CUDA IPC inboxes); registration and odometry replicated" % args.slab,
-            "value": round(args.steps / a_stream["seconds"], 3), "unit": "sweeps/s", "scaling": "strong",
-            "window_ms_min_median_max": [ms(a_stream["min"]), ms(a_stream["seconds"]), ms(a_stream["max"])],
-            "windows": a_stream["windows"],
-            "sequential_value": round(args.steps / a_seq["seconds"], 3),
-            "sequential_mapping_ms_per_sweep": round(1e3 * float(last[2][3]) / args.steps, 4),
-            "map_iters_per_sweep": round(last[4] / args.steps, 2)}
+    rep["what"] = ("ONE sweep stream, map sharded by %d m cube slabs (+ 2 m halo) over the GPUs, queries evaluated by the owner "
+                   "of their cell, all-reduce of the 32 normal-equation sums fused into the iteration kernel (peer stores over "
+                   "NVLink, CUDA IPC inboxes); registration and odometry replicated" % args.slab)
+    if rep5 is not None:
+        rep["config5"] = rep5
+    return rep
 
 
 def kernel_roofline(args, api, corner, surf, sweep, pipe):
@@ -689,6 +706,8 @@ def main():
                     help="N > 1: workload of the additional single-stream run on the cube-sharded map")
     ap.add_argument("--only-hbm", action="store_true", help="development: print only the roofline_hbm object")
     ap.add_argument("--no-hbm-roofline", action="store_true", help="skip the config-5 (20 M-point map) kernel measurement")
+    ap.add_argument("--sharded-config5", action="store_true",
+                    help="N > 1: also run BASELINE config 5 (128x4096 vs 20M) on the cube-sharded map (default: only on 8 GPUs)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the cube-sharded single-stream section")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="repeat the K-step timed window (fresh pipeline each) until the windows add up to this")
