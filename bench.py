@@ -709,7 +709,7 @@ def main():
     ap.add_argument("--sharded-config5", action="store_true",
                     help="N > 1: also run BASELINE config 5 (128x4096 vs 20M) on the cube-sharded map (default: only on 8 GPUs)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the cube-sharded single-stream section")
-    ap.add_argument("--min-seconds", type=float, default=0.5,
+    ap.add_argument("--min-seconds", type=float, default=0.6,
                     help="repeat the K-step timed window (fresh pipeline each) until the windows add up to this")
     ap.add_argument("--max-windows", type=int, default=100)
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
