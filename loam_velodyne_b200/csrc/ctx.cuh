@@ -313,6 +313,7 @@ struct loam_b200_ctx {
     bool dirty = false;        // points were appended unsorted: rebuild before the next sweep
     bool check_grid = false;   // the next merge must drop points whose cube is outside the grid
     int n_raw_valid = 0;       // raw points in the cubes in view (exact, from begin_sweep's readback)
+    int n_cells = -1;          // occupied cells of the current table (exact, same readback; -1 = not known)
     int n_slot = 0;            // which of the two device-side pool counters is current
     int last_cen[3] = {1 << 30, 0, 0};
   } store[2];

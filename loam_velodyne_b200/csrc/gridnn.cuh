@@ -81,17 +81,22 @@ __global__ void grid_key_kernel(const float4* __restrict__ p, int m, const GridM
 }
 
 // one thread per sorted point; run heads insert (key, start, count) with linear probing
+// n_cells (optional): receives the number of run heads = occupied cells (one atomic per block)
 __global__ void grid_insert_kernel(const unsigned* __restrict__ keys, int m, uint4* __restrict__ table, unsigned mask,
-                                   const int* __restrict__ n_dev = nullptr) {
+                                   const int* __restrict__ n_dev = nullptr, int* __restrict__ n_cells = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) m = min(m, *n_dev);
-  if (i >= m) return;
+  const bool head = i < m && (i == 0 || keys[i - 1] != keys[i]);
+  if (n_cells) {
+    const int heads = __syncthreads_count(head ? 1 : 0);
+    if (threadIdx.x == 0 && heads > 0) atomicAdd(n_cells, heads);
+  }
+  if (!head) return;
   const unsigned k = keys[i];
-  if (i > 0 && keys[i - 1] == k) return;
   int cnt = 1;
   while (i + cnt < m && keys[i + cnt] == k) cnt++;
   unsigned h = grid_hash(k) & mask;
-  while (true) {
+  for (unsigned tries = 0; tries <= mask; tries++) {  // bounded: a full table (cannot happen at load <= 0.5) must not hang the GPU
     const unsigned prev = atomicCAS(&table[h].x, 0u, k + 1u);
     if (prev == 0u) {
       table[h].y = (unsigned)i;
