@@ -206,14 +206,6 @@ def run_cuda(args, rank, world, local_rank):
     lidar, corner, surf, sweeps = make_workload(args.workload, n_total, 0 if sharded else rank)
     dev = f"cuda:{local_rank}"
 
-    def fresh_nccl_id():
-        """One NCCL unique id per communicator (each Pipeline of the sharded mode creates its own)."""
-        nid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            nid = torch.tensor(list(api.nccl_unique_id()), dtype=torch.uint8, device=dev)
-        dist.broadcast(nid, 0)
-        return bytes(nid.cpu().tolist())
-
     streams = 1 if sharded else world  # independent sweep streams processed by the job
 
     def barrier():

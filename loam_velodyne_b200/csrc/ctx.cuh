@@ -225,6 +225,7 @@ struct loam_b200_ctx {
   int shard_slab = 0;
   unsigned* peer_inbox = nullptr;
   void* peer_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peer_is_ipc[8] = {false, false, false, false, false, false, false, false};  // opened with cudaIpcOpenMemHandle
   bool peer_ready = false;
 
   // scan registration

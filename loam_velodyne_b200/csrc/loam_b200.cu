@@ -317,8 +317,8 @@ static void unpack_normal_eq(const float* r, loam_b200_normal_eq* out) {
       k++;
     }
   for (int i = 0; i < 6; i++) out->AtB[i] = r[21 + i];
-  out->n_selected = (int)(r[27] + 0.5f);
-  out->n_corner_selected = (int)(r[28] + 0.5f);
+  out->n_selected = std::isfinite(r[27]) ? (int)(r[27] + 0.5f) : 0;
+  out->n_corner_selected = std::isfinite(r[28]) ? (int)(r[28] + 0.5f) : 0;
 }
 
 bool getenv_no_mailbox() {
@@ -677,6 +677,8 @@ int loam_b200_destroy(loam_b200_ctx* c) {
   c->odom_loop.destroy();
   c->map_loop.destroy();
   c->seq_features.destroy(); c->seq_begin_sweep.destroy(); c->seq_end_sweep.destroy(); c->seq_rebuild.destroy();
+  for (int p = 0; p < 8; p++)
+    if (c->peer_mapped[p] && c->peer_is_ipc[p]) cudaIpcCloseMemHandle(c->peer_mapped[p]);
   if (c->peer_inbox) cudaFree(c->peer_inbox);
   if (c->comm) loam_b200_comm_destroy(c); c->dbg_coeff.release();
   c->dbg_sel.release(); c->result_host.release(); c->lm_state.release(); c->bin_xyz.release(); c->od_ring_off[0].release(); c->result_mailbox.release(); c->int_mailbox.release(); c->ring_table_host.release(); c->od_q.release(); c->od_ind.release(); c->tmp_pts.release();
@@ -1067,6 +1069,11 @@ static int map_iterate_impl(loam_b200_ctx* c, const loam_b200_pose* pose, loam_b
   }
   int rc = mb.host ? fetch_normal_eq_mailbox(c, out) : fetch_normal_eq(c, out);
   if (rc) return rc;
+  if (c->peer_ready && c->shard_world > 1 && !std::isfinite(out->AtB[0] + out->AtA[0])) {
+    // the fused all-reduce gives up (NaN sums) when a peer's contribution does not arrive within ~2 s
+    c->last_error = "peer all-reduce timed out: a rank of the cube-sharded map did not run this iteration";
+    return LOAM_B200_ERR_COMM;
+  }
   if (dbg) {
     LB_CUDA(c, cudaMemcpyAsync(coeff, c->dbg_coeff.p, (size_t)(nc + ns) * 16, cudaMemcpyDeviceToHost, c->stream));
     if (selected)
