@@ -295,6 +295,8 @@ def run_cuda(args, rank, world, local_rank):
             ss = pipe.stage_seconds()
             acc["stage"] = np.concatenate([ss["busy"], ss["idle"], ss["handoff"]])
         el = max_over_ranks(t1 - t0)
+        if work["cube_sharded"]:
+            pipe.mapping.disable_cube_sharding()  # unmap the peers' inboxes on every rank before any rank frees its own
         barrier()
         del pipe
         return el, poses, acc["stage"], acc["it_o"], acc["it_m"]

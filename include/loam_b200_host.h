@@ -103,6 +103,9 @@ int loam_b200_map_enable_sharding(void* h, int rank, int world, const unsigned c
 int loam_b200_map_peer_export(void* h, unsigned char* out64);
 int loam_b200_map_enable_cube_sharding(void* h, int rank, int world, const unsigned char* handles, int slab_metres);
 int loam_b200_map_enable_cube_sharding_local(void** hs, int world, int slab_metres);
+/* unmap the peers' inboxes: every rank calls this and the ranks synchronise BEFORE any of them destroys its object (memory
+ * exported over CUDA IPC must not be freed while another process still has it mapped) */
+int loam_b200_map_disable_cube_sharding(void* h);
 
 /* ---- the three chained in-process: registration -> odometry -> mapping on one sweep ---- */
 void* loam_b200_pipeline_create(float scanPeriod, int odomMaxIter, int mapMaxIter);

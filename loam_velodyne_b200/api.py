@@ -193,6 +193,7 @@ def lib():
         "loam_b200_map_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
         "loam_b200_map_enable_cube_sharding": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
         "loam_b200_map_enable_cube_sharding_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+        "loam_b200_map_disable_cube_sharding": (C.c_int, [vp]),
         "loam_b200_peer_export": (C.c_int, [vp, C.POINTER(C.c_ubyte)]),
         "loam_b200_peer_connect": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
         "loam_b200_peer_connect_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
@@ -644,6 +645,11 @@ class LaserMapping(_Handle):
         """handles: world x 64 bytes (peer_export of every rank, in rank order)."""
         buf = (C.c_ubyte * (64 * world)).from_buffer_copy(handles)
         self._ck(self.L.loam_b200_map_enable_cube_sharding(self.h, rank, world, buf, slab_metres), "enableCubeSharding")
+
+
+    def disable_cube_sharding(self):
+        """Unmap the peers' inboxes; every rank calls it, then the ranks synchronise, then the objects may be destroyed."""
+        self._ck(self.L.loam_b200_map_disable_cube_sharding(self.h), "disableCubeSharding")
 
 
 def enable_cube_sharding_local(mappings, slab_metres=10):

@@ -587,6 +587,15 @@ int loam_b200_map_peer_export(void* h, unsigned char* out64) {
 int loam_b200_map_enable_cube_sharding(void* h, int rank, int world, const unsigned char* handles, int slab_metres) {
   return guarded([&] { ((MapH*)h)->m.enableCubeSharding(rank, world, handles, slab_metres); return 0; });
 }
+// unmap the peers' inboxes (call on every rank, then synchronise the ranks, BEFORE any rank destroys its object: memory
+// exported over CUDA IPC must not be freed while another process still has it mapped)
+int loam_b200_map_disable_cube_sharding(void* h) {
+  return guarded([&] {
+    auto* ctx = ((MapH*)h)->m.deviceContext();
+    if (ctx->created()) ctx->check(loam_b200_peer_disconnect(ctx->get()), "loam_b200_peer_disconnect");
+    return 0;
+  });
+}
 int loam_b200_map_enable_cube_sharding_local(void** hs, int world, int slab_metres) {
   return guarded([&] {
     std::vector<loam::BasicLaserMapping*> objs((size_t)world);

@@ -81,6 +81,10 @@ def main():
         if a.check:
             assert same and worst <= 1e-4, (same, worst)
             print("SHARDED_OK")
+    if a.mode == "peer":
+        p.mapping.disable_cube_sharding()
+        dist.barrier()
+    del p
     dist.destroy_process_group()
 
 
