@@ -689,7 +689,34 @@ def run_reference(args, rank, world):
             "e2e": {"value": round(v, 3), "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def guarded_single_gpu_run():
+    """N = 1 only: the measurement runs in a child process and is repeated ONCE if that process dies without a result.
+    (One of ~10 builder runs of this bench ended in a segmentation fault a few seconds after start-up that neither a rerun
+    under faulthandler nor 200 create / stream / destroy cycles of the pipeline reproduced; a lost bench line costs a
+    round, a rerun costs a minute.  The JSON line says whether a rerun was needed: "bench_reruns".)"""
+    env = dict(os.environ)
+    env["LOAM_B200_BENCH_CHILD"] = "1"
+    cmd = [sys.executable, "-X", "faulthandler", os.path.abspath(__file__)] + sys.argv[1:]
+    for attempt in range(2):
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        for l in r.stdout.splitlines():
+            if not l.startswith("{"):
+                print(l, file=sys.stderr)
+        if r.returncode == 0 and lines:
+            out = json.loads(lines[-1])
+            if isinstance(out, dict) and "metric" in out:
+                out["bench_reruns"] = attempt
+            print(json.dumps(out))
+            return 0
+        print(f"bench.py: measurement process ended with status {r.returncode} and no result (attempt {attempt + 1})", file=sys.stderr)
+    return 1
+
+
 def main():
+    if (int(os.environ.get("WORLD_SIZE", "1")) == 1 and "LOAM_B200_BENCH_CHILD" not in os.environ
+            and "--only-hbm" not in sys.argv and "LOAM_B200_BENCH_NO_GUARD" not in os.environ):
+        sys.exit(guarded_single_gpu_run())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -437,9 +437,10 @@ int run_captured(loam_b200_ctx* c, CapturedSeq& cs, F body) {
     cudaGraphExecUpdateResultInfo info;
     if (cudaGraphExecUpdate(cs.exec, g, &info) == cudaSuccess) {
       updated = true;
-    } else {  // the sequence took a different branch: instantiate anew
+    } else {  // the sequence took a different branch: instantiate anew (the parked buffers stay parked)
       cudaGetLastError();
-      cs.destroy();
+      cudaGraphExecDestroy(cs.exec);
+      cs.exec = nullptr;
     }
   }
   if (!updated) {
