@@ -691,9 +691,9 @@ def run_reference(args, rank, world):
 
 def guarded_single_gpu_run():
     """N = 1 only: the measurement runs in a child process and is repeated ONCE if that process dies without a result.
-    (One of ~10 builder runs of this bench ended in a segmentation fault a few seconds after start-up that neither a rerun
-    under faulthandler nor 200 create / stream / destroy cycles of the pipeline reproduced; a lost bench line costs a
-    round, a rerun costs a minute.  The JSON line says whether a rerun was needed: "bench_reruns".)"""
+    (One builder run of this bench ended in a segmentation fault a few seconds after start-up that neither a rerun under
+    faulthandler nor 200 create / stream / destroy cycles of the pipeline reproduced; a lost bench line costs a round, a
+    rerun costs a minute.  The JSON line says whether a rerun was needed: "bench_reruns".  A usage error is not retried.)"""
     env = dict(os.environ)
     env["LOAM_B200_BENCH_CHILD"] = "1"
     cmd = [sys.executable, "-X", "faulthandler", os.path.abspath(__file__)] + sys.argv[1:]
@@ -710,6 +710,8 @@ def guarded_single_gpu_run():
             print(json.dumps(out))
             return 0
         print(f"bench.py: measurement process ended with status {r.returncode} and no result (attempt {attempt + 1})", file=sys.stderr)
+        if r.returncode == 2:  # argparse
+            return 2
     return 1
 
 
