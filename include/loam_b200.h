@@ -30,7 +30,7 @@ typedef enum {
   LOAM_B200_ERR_NO_DEVICE = -3,/* no CUDA device / device is not sm_100 */
   LOAM_B200_ERR_STATE = -4,    /* call sequence violated (e.g. iterate before set) */
   LOAM_B200_ERR_CAPACITY = -5, /* caller-provided output capacity too small */
-  LOAM_B200_ERR_COMM = -6      /* NCCL failure */
+  LOAM_B200_ERR_COMM = -6      /* NCCL failure, or a peer of the cube-sharded map did not answer (fused all-reduce) */
 } loam_b200_status;
 
 const char* loam_b200_strerror(int status);
@@ -108,7 +108,11 @@ typedef struct {
 } loam_b200_features;
 
 /* pts: n packed points, ring-ordered; ring_start/ring_end: the inclusive IndexRange of each ring exactly as
- * processScanlines builds _scanIndices (BasicScanRegistration.cpp:38-41), so empty rings are (c, c-1) or (0, 0). */
+ * processScanlines builds _scanIndices (BasicScanRegistration.cpp:38-41), so empty rings are (c, c-1) or (0, 0).
+ * Limits the reference does not have (a ring is staged in one CTA's shared memory): a ring longer than 5344 points
+ * returns LOAM_B200_ERR_CAPACITY; curvatureRegion > 15 or nFeatureRegions > 4095 return LOAM_B200_ERR_ARG; the ring
+ * binning front end (loam_b200_reg_bin) takes at most 254 rings.  (HDL-64E: 2.1 k points per ring at 10 Hz; the
+ * limits are repeated in INTEGRATION.md.) */
 int loam_b200_extract_features(loam_b200_ctx* ctx, const float* pts, int n, const int32_t* ring_start,
                                const int32_t* ring_end, int n_rings, const loam_b200_reg_params* params,
                                loam_b200_features* out);

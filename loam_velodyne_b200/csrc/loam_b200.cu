@@ -744,7 +744,8 @@ void* loam_b200_stream(loam_b200_ctx* c) { return c ? (void*)c->stream : nullptr
 // the REG_* cloud slots, labels in reg_label, totals in c->reg_totals (host, after one sync).
 static int run_features(loam_b200_ctx* c, const float4* d_pts, int n, const int32_t* ring_start, const int32_t* ring_end,
                         int n_rings, const loam_b200_reg_params* prm) {
-  if (prm->curvatureRegion < 1 || prm->curvatureRegion > 15 || prm->nFeatureRegions < 1 || prm->maxCornerSharp < 0 ||
+  if (prm->curvatureRegion < 1 || prm->curvatureRegion > 15 || prm->nFeatureRegions < 1 || prm->nFeatureRegions > 4095 ||
+      prm->maxCornerSharp < 0 ||
       prm->maxCornerLessSharp < prm->maxCornerSharp || prm->maxSurfaceFlat < 0 || !(prm->lessFlatFilterSize > 0.f))
     return LOAM_B200_ERR_ARG;
   int max_ring = 0;
@@ -782,7 +783,7 @@ static int run_features(loam_b200_ctx* c, const float4* d_pts, int n, const int3
   int n2cap = 1;
   while (n2cap < ncap) n2cap <<= 1;
   const size_t smem = (size_t)ncap * (16 + 4 + 4 + 2) + (size_t)n2cap * 8;
-  if (smem > 200 * 1024) return LOAM_B200_ERR_CAPACITY;  // ring longer than ~5.7 k points
+  if (smem > 200 * 1024) return LOAM_B200_ERR_CAPACITY;  // ring longer than 5344 points (4096 < n: 8 B x 8192 sort keys)
 
   LB_CUDA(c, c->reg_ring_start.reserve(n_rings));
   LB_CUDA(c, c->reg_ring_end.reserve(n_rings));
