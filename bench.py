@@ -368,7 +368,11 @@ def run_cuda(args, rank, world, local_rank):
     # fused all-reduce of the normal equations over NVLink peer memory; reported next to the replica figure
     shard_report = None
     if world > 1 and not sharded and not args.no_sharded:
-        shard_report = sharded_section(args, api, torch, dev, rank, world, work, arm, ref_sweeps=None)
+        try:
+            shard_report = sharded_section(args, api, torch, dev, rank, world, work, arm, ref_sweeps=None)
+        except Exception as e:  # a lost peer turns into an error on every rank: keep the replica figures of the line
+            print(f"bench.py: rank {rank}: cube-sharded section failed: {e!r}", file=sys.stderr)
+            shard_report = {"error": repr(e)[:300]}
 
     # ---- kernel-level pass (rank 0, N = 1 semantics): north-star kernel roofline through the kernel ABI
     out = None
