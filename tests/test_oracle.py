@@ -72,6 +72,44 @@ def test_restatement_equals_compiled_reference_live(oracle, reference, scene):
             np.testing.assert_array_equal(pr.odom.cloud(name), po.odom.cloud(name))
 
 
+VARIANTS = {
+    # name: (rings, azimuth steps, lower, upper, yaw rate deg/s, velocity, max range, registration overrides, odom / map iterations)
+    "hdl32_ragged": (32, 700, -30.67, 10.67, 12.0, (0.5, 0.0, 2.0), 35.0, {}, (25, 10)),
+    "vlp16_params": (16, 900, -15.0, 15.0, -4.0, (0.0, 0.0, 0.8), 0.0,
+                     dict(n_regions=4, curv_region=3, max_sharp=3, max_flat=6, less_flat_leaf=0.3, curv_thr=0.05), (25, 10)),
+    "vlp16_few_iterations": (16, 600, -15.0, 15.0, 20.0, (1.0, 0.0, 4.0), 0.0, {}, (3, 2)),
+    "single_region": (16, 400, -15.0, 15.0, 5.0, (0.0, 0.0, 1.0), 25.0, dict(n_regions=1, curv_region=7), (25, 10)),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_restatement_equals_compiled_reference_variants(oracle, reference, scene, variant):
+    """Other sensor geometries, ragged rings (returns beyond max range dropped), non-default RegistrationParams and tight
+    iteration budgets: the restatement and the compiled reference agree bit for bit on poses, features and map."""
+    from loam_velodyne_b200 import synth
+    R, A, lo, hi, yaw, v, max_range, reg, (oi, mi) = VARIANTS[variant]
+    lidar = synth.Lidar(R, A, lo, hi)
+    corner, surf = synth.make_map(scene, 40_000)
+    pr, po = reference.pipeline(odom_iter=oi, map_iter=mi), oracle.pipeline(odom_iter=oi, map_iter=mi)
+    for p in (pr, po):
+        if reg:
+            p.scanreg.configure(**reg)
+        p.seed_map(corner, surf)
+    for i in range(4):
+        pts, rs = synth.make_sweep(scene, lidar, 5 + i, yaw_rate=math.radians(yaw), v=v, max_range=max_range)
+        if max_range > 0:
+            assert len(set(rs.tolist())) > 1  # the rings really are ragged
+        ok_r, od_r, aft_r, _ = pr.sweep(pts, rs)
+        ok_o, od_o, aft_o, _ = po.sweep(pts, rs)
+        assert ok_r == ok_o
+        np.testing.assert_array_equal(od_r, od_o)
+        np.testing.assert_array_equal(aft_r, aft_o)
+        for name in ("sharp", "less_sharp", "flat", "less_flat"):
+            np.testing.assert_array_equal(pr.scanreg.cloud(name), po.scanreg.cloud(name))
+    np.testing.assert_array_equal(pr.mapping.cloud("corner_cubes"), po.mapping.cloud("corner_cubes"))
+    np.testing.assert_array_equal(pr.mapping.cloud("surf_cubes"), po.mapping.cloud("surf_cubes"))
+
+
 def test_knn_against_brute_force(oracle):
     rng = np.random.RandomState(0)
     pts = np.zeros((3000, 4), np.float32)
